@@ -1,0 +1,121 @@
+// engine.cuh — shared declarations of the sm_100a MPPI/MPOPI sampling engine.
+//
+// Device data layout: the noise tensor E lives in HBM as [cs][ldk] doubles with the
+// SAMPLE index fastest (ldk = K_local rounded up to 32), i.e. the transpose of the reference's
+// cs x K column-major Julia matrix (POL:271). Thread-per-rollout kernels then read E[r][k] with
+// fully coalesced 8-byte loads across a warp, and every reduction over samples (weighted sums,
+// moments) streams contiguous rows. The C-ABI converts to/from the Julia layout at the boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpopis_b200.h"
+
+namespace mpopis {
+
+struct CarParams {  // CAR:2-21 in declaration order
+  double m, Izz, h_cm, l_f, l_r, C_D0, C_D1, C_af, C_ar, mu_f, mu_r, d_max, dd_max, Fx_max, Fx_min,
+      l_brake, l_drive, b_limit;
+};
+
+struct CarEnvArgs {
+  CarParams car[MPOPIS_MAX_CARS];
+  double cos_blimit[MPOPIS_MAX_CARS];  // cos(β_limit) for the atan-free β test (fast path)
+  double dt, ddt;
+  int nsub;  // round(Int, dt/δt), CAR:299
+  int n_cars;
+  int n_trk;
+  const double *trk;  // device: x[n_trk], y[n_trk], w[n_trk]
+};
+
+struct McEnvArgs {  // RLEnvs MountainCarEnv params
+  double min_pos, max_pos, max_speed, goal_pos, goal_vel, power, gravity;
+  long long max_steps;
+};
+
+struct RolloutArgs {
+  const double *E;      // [cs][ldk]
+  long long ldk;        // row pitch of E in doubles
+  const double *U;      // [cs] current proposal mean (pol.U inside the AIS loop)
+  const double *U_orig; // [cs]
+  const double *bvec;   // [cs] (γ U_orig') Σ_inv, or nullptr when γ = 0 (POL:272)
+  const double *state0; // [ss] env.state
+  const long long *env_t; // device scalar env.t (MountainCar max_steps term)
+  double *costs;        // [K_local]
+  double *traj;         // nullptr or [K_local][ss][T] (logger, UTL:139-141)
+  int K;                // samples of this shard
+  int T;                // horizon
+};
+
+// ---- launchers (host). Every kernel of the AIS loop takes the device-side `stop` flag ----------
+// rollout.cu  (variant 0 = fast math-equivalent formulation, 1 = literal libm call sequence)
+void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, const int *stop,
+                        cudaStream_t s);
+void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
+void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
+                        unsigned char *within, cudaStream_t s);
+void launch_env_step_car(const CarEnvArgs &env, double *state, const double *action, long long *env_t,
+                         double *reward, int variant, cudaStream_t s);
+void launch_env_step_mc(const McEnvArgs &env, double *state, const double *action, long long *env_t,
+                        double *reward, unsigned char *done, cudaStream_t s);
+void launch_env_reward_car(const CarEnvArgs &env, const double *state, double *reward, int variant, cudaStream_t s);
+void launch_env_reward_mc(const McEnvArgs &env, const double *state, int done, double *reward, cudaStream_t s);
+// sampling.cu
+void launch_philox_normals(double *Z, long long ldk, int cs, int K, long long k0, uint64_t seed, uint32_t step,
+                           uint32_t iter, const int *stop, cudaStream_t s);
+void launch_philox_uniforms(double *u, int K, uint64_t seed, uint32_t step, uint32_t iter, const int *stop,
+                            cudaStream_t s);
+void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E, long long ldk, int K,
+                    const int *stop, cudaStream_t s);
+void launch_transpose_in(const double *colmajor, double *dev, int cs, int K, long long ldk, cudaStream_t s);
+void launch_transpose_out(const double *dev, double *colmajor, int cs, int K, long long ldk, const double *shift_a,
+                          const double *shift_b, cudaStream_t s);
+// stats.cu
+void launch_weights(const double *costs, int K, double lambda, double *w, const int *stop, cudaStream_t s);
+int rowsum_nchunks(int n);
+void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
+                           const int *stop, cudaStream_t s);
+void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop, cudaStream_t s);
+void launch_finalize_mean(const double *sums, int rows, double *mu, double *U, const double *scale_dev,
+                          const int *stop, cudaStream_t s);
+int syrk_nchunks(int n);
+void launch_syrk_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu, double *P,
+                         const int *stop, cudaStream_t s);
+void launch_scatter_reduce(const double *P, int nchunks, int p, double *S, const int *stop, cudaStream_t s);
+void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
+                             const double *Sraw, const double *cnt_dev, int standardise, double *partial,
+                             const int *stop, cudaStream_t s);
+void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int corrected, int method,
+                         const double *qpart, int nq, double ridge, double *Sigma, double *lambda_out,
+                         const int *stop, cudaStream_t s);
+void launch_gather_cols(const double *E, long long ldk, int cs, const int *order, int m, long long k0, int Kloc,
+                        double *X, long long ldx, double *mask, const int *stop, cudaStream_t s);
+void launch_elite_stop(const double *sorted_costs, int m, int enabled, int *stop, cudaStream_t s);
+void launch_iter_begin(const int *stop, int *its, cudaStream_t s);
+void launch_pmc_counts(const double *wglobal, int K, const double *u, double *cdf, int *counts, long long k0,
+                       int Kloc, double *wloc, const int *stop, cudaStream_t s);
+void launch_ctrl_vec(const double *Sinv, int cs, const double *U_orig, double gamma, double *b, cudaStream_t s);
+void launch_finalize_control(const double *wsum, const double *U_orig, const double *U_cur, int cs, int as, int T,
+                             double *U_next, double *control, cudaStream_t s);
+// linalg.cu
+void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, double *Wglobal, int *info, int tag,
+                 const int *stop, cudaStream_t s);
+void launch_chol_solve(const double *Lt, int n, const double *u, double gamma, double *b, const int *stop,
+                       cudaStream_t s);
+void launch_transpose_sq(const double *in, double *out, int n, cudaStream_t s);
+// cma.cu
+int inv_sqrt_max_ctas(int num_sms);
+int launch_inv_sqrt(const double *A, int n, double *Cout, double *ws, int *info, int tag, const int *stop,
+                    int max_ctas, cudaStream_t s);  // returns a cudaError_t
+void launch_cma_lin_gather(const double *X, long long ldx, int cs, const int *order, int K, double *dvec,
+                           const int *stop, cudaStream_t s);
+void launch_cma_vec(const double *dw, const double *C, const double *dvec, const double *ws, int K, int cs,
+                    int n_iter, const mpopis_cma_t &c, double *psig, double *pSig, double *sigma_dev, double *U,
+                    double *Sigma, const int *stop, cudaStream_t s);
+// sort.cu
+int sort_nblocks(int K);
+size_t sort_hist_ints(int K);
+void launch_sortperm(const double *costs, int K, int m, unsigned long long *keys_a, unsigned long long *keys_b,
+                     int *order, int *vals_b, int *hist, double *sorted_costs, const int *stop, cudaStream_t s);
+
+}  // namespace mpopis

@@ -1,0 +1,112 @@
+// linalg.cu — G6: the small dense factorizations of the AIS loop.
+//
+//   chol      lower Cholesky factor of Σ′ (what MvNormal(Σ′) builds: POL:154,192,307,352,447,551,650,
+//             723,796). Failure mirrors Julia's PosDefException -> MPOPIS_ERR_NOT_PD.
+//   ctrl_vec  b = γ Σ′⁻¹ U_orig by two triangular solves (replaces invcov(P), POL:156,...,798, which
+//             the reference only ever uses inside γ U_origᵀ Σ⁻¹ (V − U_orig), POL:272).
+// cs is 15..300 for the reference's configs, so these are single-CTA latency kernels; every rank of
+// a sharded policy runs them redundantly on bit-identical inputs.
+#include "engine.cuh"
+
+namespace mpopis {
+
+// Right-looking Cholesky on W (row-major n x n, lower part used). W lives in shared memory when it
+// fits (n <= CHOL_SMEM_N) and in global scratch otherwise. Output Lt = L stored row-major with an
+// explicit zero upper triangle. `sigma_dev` (nullable): factor σ²·A instead (CMA, POL:551).
+// info: set to `tag` (first failure wins) if a pivot is not > 0.
+__global__ void __launch_bounds__(1024) chol_kernel(const double *__restrict__ A, int n, const double *sigma_dev,
+                                                     double *__restrict__ Lt, double *__restrict__ Wglobal,
+                                                     int use_smem, int *info, int tag, const int *stop) {
+  if (stop && *stop) return;
+  extern __shared__ double Wsm[];
+  __shared__ int bad;
+  double *W = use_smem ? Wsm : Wglobal;
+  const double sc = sigma_dev ? (*sigma_dev) * (*sigma_dev) : 1.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) W[e] = sigma_dev ? sc * A[e] : A[e];
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = W[(size_t)j * n + j];
+      if (!(d > 0.0)) bad = 1;
+      else W[(size_t)j * n + j] = sqrt(d);
+    }
+    __syncthreads();
+    if (bad) break;
+    const double ljj = W[(size_t)j * n + j];
+    for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) W[(size_t)i * n + j] = W[(size_t)i * n + j] / ljj;
+    __syncthreads();
+    const int rem = n - j - 1;
+    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+      if (k <= i) W[(size_t)i * n + k] -= W[(size_t)i * n + j] * W[(size_t)k * n + j];
+    }
+    __syncthreads();
+  }
+  if (bad) {
+    if (threadIdx.x == 0) atomicCAS(info, 0, tag);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, k = e % n;
+    Lt[e] = k <= i ? W[e] : 0.0;
+  }
+}
+
+constexpr int CHOL_SMEM_N = 160;  // 160² · 8 B = 200 KB
+
+void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, double *Wglobal, int *info, int tag,
+                 const int *stop, cudaStream_t s) {
+  const int use_smem = n <= CHOL_SMEM_N;
+  const size_t smem = use_smem ? sizeof(double) * n * n : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(double) * CHOL_SMEM_N * CHOL_SMEM_N));
+    attr_set = true;
+  }
+  chol_kernel<<<1, 1024, smem, s>>>(A, n, sigma_dev, Lt, Wglobal, use_smem, info, tag, stop);
+}
+
+// b = γ (L Lᵀ)⁻¹ u : forward then backward substitution, column-oriented (one barrier per column).
+__global__ void __launch_bounds__(1024) chol_solve_kernel(const double *__restrict__ Lt, int n,
+                                                           const double *__restrict__ u, double gamma,
+                                                           double *__restrict__ b, const int *stop) {
+  if (stop && *stop) return;
+  extern __shared__ double y[];  // n
+  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = u[i];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {  // L y = u
+    if (threadIdx.x == 0) y[j] = y[j] / Lt[(size_t)j * n + j];
+    __syncthreads();
+    const double yj = y[j];
+    for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) y[i] -= Lt[(size_t)i * n + j] * yj;
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; --j) {  // Lᵀ x = y
+    if (threadIdx.x == 0) y[j] = y[j] / Lt[(size_t)j * n + j];
+    __syncthreads();
+    const double xj = y[j];
+    for (int i = threadIdx.x; i < j; i += blockDim.x) y[i] -= Lt[(size_t)j * n + i] * xj;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] = gamma * y[i];
+}
+
+void launch_chol_solve(const double *Lt, int n, const double *u, double gamma, double *b, const int *stop,
+                       cudaStream_t s) {
+  chol_solve_kernel<<<1, 1024, sizeof(double) * n, s>>>(Lt, n, u, gamma, b, stop);
+}
+
+// plain transposes of small square matrices (Lt <-> column-major L at the ABI boundary)
+__global__ void transpose_sq_kernel(const double *__restrict__ in, double *__restrict__ out, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  out[(size_t)(e % n) * n + e / n] = in[e];
+}
+void launch_transpose_sq(const double *in, double *out, int n, cudaStream_t s) {
+  transpose_sq_kernel<<<(n * n + 255) / 256, 256, 0, s>>>(in, out, n);
+}
+
+}  // namespace mpopis

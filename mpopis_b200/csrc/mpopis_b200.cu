@@ -1,0 +1,999 @@
+// mpopis_b200.cu — handle, AIS-loop orchestration and the C-ABI of include/mpopis_b200.h.
+//
+// One handle = one policy object on one GPU (optionally one shard of a K-sharded policy). A control
+// step (`plan`) is a fixed, stream-ordered sequence of kernel launches with no host synchronisation
+// inside: the CE/CMA early stop (POL:459-461, 567-569) is a device flag every later kernel checks,
+// Cholesky failure is a device flag read back with the result. Host <-> device traffic per step is
+// state (ss) + U (cs) in, control (as) + U (cs) + three ints out.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+using namespace mpopis;
+
+namespace {
+
+thread_local char g_err[1024] = "";
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(MPOPIS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- NCCL through dlopen: the library has no link-time NCCL dependency (single-GPU users, and a
+// host process that already loaded its own libnccl.so.2, e.g. torch's, share that copy). ----------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+#define SYM(field, name) field = (decltype(field))dlsym(lib, name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
+  }
+} g_nccl;
+
+#define NC(call)                                                                                          \
+  do {                                                                                                    \
+    ncclResult_t r_ = (call);                                                                             \
+    if (r_ != ncclSuccess)                                                                                \
+      return fail(MPOPIS_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+  } while (0)
+
+template <class T>
+int dalloc(T **p, size_t n) {
+  CU(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+  CU(cudaMemset(*p, 0, sizeof(T) * (n ? n : 1)));
+  return 0;
+}
+
+}  // namespace
+
+struct mpopis_handle {
+  mpopis_cfg_t cfg{};
+  int K = 0, Kloc = 0, T = 0, N = 0, as = 0, cs = 0, ss = 0, m_elite = 0;
+  long long k0 = 0, ldk = 0, ldm = 0;
+  int dev = 0, world = 1, rank = 0;
+  cudaStream_t st = nullptr;
+  ncclComm_t comm = nullptr;
+  bool env_set = false, cma_set = false;
+  CarEnvArgs car{};
+  McEnvArgs mc{};
+  double gamma = 0.0;
+  uint64_t seed = 0;
+  long long step = 0;
+  int rollout_variant = 0, rollout_block = 64, coop_max = 1;
+  int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
+  bool L0_valid = false;
+  mpopis_cma_t cma{};
+  long long launches = 0;
+  // device state
+  double *d_trk = nullptr, *d_state = nullptr, *d_U_orig = nullptr, *d_U_cur = nullptr, *d_U_next = nullptr,
+         *d_control = nullptr, *d_Sigma0 = nullptr, *d_Sigma = nullptr, *d_Lt = nullptr, *d_Lt0 = nullptr,
+         *d_cholW = nullptr, *d_bvec = nullptr, *d_Z = nullptr, *d_E = nullptr, *d_stage = nullptr,
+         *d_costs = nullptr, *d_w = nullptr, *d_sorted = nullptr, *d_X = nullptr, *d_mask = nullptr,
+         *d_part = nullptr, *d_sums = nullptr, *d_mu = nullptr, *d_P = nullptr, *d_Sraw = nullptr,
+         *d_qpart = nullptr, *d_q = nullptr, *d_lambda = nullptr, *d_traj = nullptr, *d_u = nullptr,
+         *d_cdf = nullptr, *d_wcnt = nullptr, *d_ws = nullptr, *d_sigma = nullptr, *d_psig = nullptr,
+         *d_pSig = nullptr, *d_dw = nullptr, *d_C = nullptr, *d_ns = nullptr, *d_reward = nullptr,
+         *d_ones = nullptr;
+  long long *d_env_t = nullptr;
+  unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
+  int *d_order = nullptr, *d_vals_b = nullptr, *d_hist = nullptr, *d_counts = nullptr, *d_flags = nullptr;
+  unsigned char *d_done = nullptr;
+  size_t part_doubles = 0;
+  // d_flags: [0] stop, [1] its, [2] info
+  int *stop() { return d_flags; }
+  int *its() { return d_flags + 1; }
+  int *info() { return d_flags + 2; }
+  // pinned staging
+  double *h_in = nullptr, *h_out = nullptr;
+  int *h_flags = nullptr;
+  // timing
+  std::vector<cudaEvent_t> ev;  // 2 per iteration + 2 total
+  int last_its_launched = 0;
+  double last_rollout_ms = 0, last_total_ms = 0;
+  bool timing_valid = false;
+};
+
+namespace {
+
+int set_device(mpopis_t *h) {
+  CU(cudaSetDevice(h->dev));
+  return 0;
+}
+
+bool is_g_family(int pol) { return pol != MPOPIS_POLICY_MPPI; }
+bool adapts_sigma(int pol) {
+  return pol == MPOPIS_POLICY_CEMPPI || pol == MPOPIS_POLICY_CMAMPPI || pol == MPOPIS_POLICY_MUSIGMAAISMPPI ||
+         pol == MPOPIS_POLICY_PMCMPPI;
+}
+
+int allreduce_sum(mpopis_t *h, double *buf, size_t n) {
+  if (h->world == 1) return 0;
+  NC(g_nccl.AllReduce(buf, buf, n, ncclFloat64, ncclSum, h->comm, h->st));
+  return 0;
+}
+int allgather_costs(mpopis_t *h) {
+  if (h->world == 1) return 0;
+  NC(g_nccl.AllGather(h->d_costs + h->k0, h->d_costs, (size_t)h->Kloc, ncclFloat64, h->comm, h->st));
+  return 0;
+}
+
+// (weighted) mean [+ covariance] of the columns of X ([cs][ld], n local columns) — G5.
+// w: per-local-column weights or nullptr. Adds the mean to U_cur when update_U (scaled by *scale_dev).
+int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, bool want_cov, int corrected,
+            int method, double ridge, bool update_U, const double *scale_dev, double *Sigma_out) {
+  const int cs = h->cs;
+  const int *stop = h->stop();
+  const int nch = rowsum_nchunks(n);
+  launch_rowsum_partial(X, ld, cs, n, w, h->d_part, stop, h->st);
+  launch_reduce_partials(h->d_part, nch, cs + 1, h->d_sums, stop, h->st);
+  h->launches += 2;
+  if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
+  launch_finalize_mean(h->d_sums, cs, h->d_mu, update_U ? h->d_U_cur : nullptr, scale_dev, stop, h->st);
+  h->launches += 1;
+  if (!want_cov) return 0;
+  launch_syrk_partial(X, ld, cs, n, w, h->d_mu, h->d_P, stop, h->st);
+  launch_scatter_reduce(h->d_P, syrk_nchunks(n), cs, h->d_Sraw, stop, h->st);
+  h->launches += 2;
+  if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs)) return rc;
+  int nq = 0;
+  if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
+    const int nb = (n + 255) / 256;
+    launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS,
+                            h->d_qpart, stop, h->st);
+    launch_reduce_partials(h->d_qpart, nb, 1, h->d_q, stop, h->st);
+    h->launches += 2;
+    if (int rc = allreduce_sum(h, h->d_q, 1)) return rc;
+    nq = 1;
+  }
+  launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, corrected, method, h->d_q, nq, ridge, Sigma_out, h->d_lambda,
+                      stop, h->st);
+  h->launches += 1;
+  return 0;
+}
+
+int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, const double *bvec) {
+  RolloutArgs a{};
+  a.E = h->d_E, a.ldk = h->ldk, a.U = U_cur, a.U_orig = U_orig, a.bvec = bvec;
+  a.state0 = h->d_state, a.env_t = h->d_env_t, a.costs = h->d_costs + h->k0;
+  a.traj = h->cfg.log_trajectories ? h->d_traj : nullptr;
+  a.K = h->Kloc, a.T = h->T;
+  if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
+    launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->stop(), h->st);
+  else
+    launch_rollout_mc(h->mc, a, h->rollout_block, h->stop(), h->st);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int cma_update(mpopis_t *h, int n_iter);  // cma.cu-style section below
+
+// The AIS loop + final control, entirely on h->st. Z_host: injected normals (cs x K x N col-major)
+// or nullptr for the Philox generator; u_host: injected PMC uniforms (K x (N-1)) or nullptr.
+int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
+  const int cs = h->cs, K = h->K, Kloc = h->Kloc, N = h->N, pol = h->cfg.policy;
+  int *stop = h->stop();
+  cudaStream_t st = h->st;
+  if (!h->env_set) return fail(MPOPIS_ERR_BAD_ARG, "environment not set");
+  if (pol == MPOPIS_POLICY_CMAMPPI && !h->cma_set) return fail(MPOPIS_ERR_BAD_ARG, "CMA constants not set");
+  if (pol == MPOPIS_POLICY_PMCMPPI && N > 1 && Z_host && !u_host)
+    return fail(MPOPIS_ERR_BAD_ARG, "pmcmppi with injected noise needs resample_u");
+  CU(cudaEventRecord(h->ev[0], st));
+  CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 2, st));  // stop, its (info is sticky until read)
+  CU(cudaMemcpyAsync(h->d_U_cur, h->d_U_orig, sizeof(double) * cs, cudaMemcpyDeviceToDevice, st));
+  const bool adapt = adapts_sigma(pol) && N > 1;
+  if (adapt) CU(cudaMemcpyAsync(h->d_Sigma, h->d_Sigma0, sizeof(double) * cs * cs, cudaMemcpyDeviceToDevice, st));
+  if (pol == MPOPIS_POLICY_CMAMPPI) {
+    CU(cudaMemcpyAsync(h->d_sigma, &h->cma.sigma, sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->d_psig, 0, sizeof(double) * cs, st));
+    CU(cudaMemsetAsync(h->d_pSig, 0, sizeof(double) * cs, st));
+  }
+  if (!h->L0_valid) {  // factor the initial Σ once per set_sigma()
+    launch_chol(h->d_Sigma0, cs, nullptr, h->d_Lt0, h->d_cholW, h->info(), 1000, nullptr, st);
+    h->launches += 1;
+    h->L0_valid = true;
+  }
+  const double *Lt = h->d_Lt0;
+  int bs = h->sigma_bs;
+  const double *bvec = nullptr;
+  for (int n = 0; n < N; ++n) {
+    launch_iter_begin(stop, h->its(), st);
+    h->launches += 1;
+    // --- proposal factor L of Σ′ (POL:447; CMA samples from σ²Σ, POL:550-554) ---
+    const bool cma_scaled = pol == MPOPIS_POLICY_CMAMPPI && N > 1;
+    if ((adapt && n > 0) || cma_scaled) {
+      launch_chol(adapt && n > 0 ? h->d_Sigma : h->d_Sigma0, cs, cma_scaled ? h->d_sigma : nullptr, h->d_Lt,
+                  h->d_cholW, h->info(), n + 1, stop, st);
+      h->launches += 1;
+      Lt = h->d_Lt;
+      if (n > 0) bs = cs;
+    }
+    if (h->gamma != 0.0 && (n == 0 || Lt == h->d_Lt)) {  // b = γ Σ′⁻¹ U_orig (POL:449 + POL:272)
+      launch_chol_solve(Lt, cs, h->d_U_orig, h->gamma, h->d_bvec, stop, st);
+      h->launches += 1;
+      bvec = h->d_bvec;
+    }
+    // --- Z, E = L Z (POL:448) ---
+    if (Z_host) {
+      const double *src = Z_host + ((size_t)n * K + h->k0) * cs;
+      CU(cudaMemcpyAsync(h->d_stage, src, sizeof(double) * cs * Kloc, cudaMemcpyHostToDevice, st));
+      launch_transpose_in(h->d_stage, h->d_Z, cs, Kloc, h->ldk, st);
+    } else {
+      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, (uint32_t)h->step, (uint32_t)n, stop, st);
+    }
+    launch_apply_L(Lt, cs, bs, h->d_Z, h->d_E, h->ldk, Kloc, stop, st);
+    h->launches += 2;
+    // --- rollouts (POL:452 -> POL:261-278) ---
+    CU(cudaEventRecord(h->ev[2 + 2 * n], st));
+    if (int rc = launch_rollouts(h, h->d_U_cur, h->d_U_orig, bvec)) return rc;
+    CU(cudaEventRecord(h->ev[3 + 2 * n], st));
+    if (int rc = allgather_costs(h)) return rc;
+    if (n == N - 1) break;
+    // --- adaptation (the `if n < N` blocks) ---
+    switch (pol) {
+      case MPOPIS_POLICY_IMPPI:
+      case MPOPIS_POLICY_MUAISMPPI:
+      case MPOPIS_POLICY_MUSIGMAAISMPPI: {  // POL:361-365, 659-663, 729-734
+        const double lam = pol == MPOPIS_POLICY_IMPPI ? h->cfg.lambda : h->cfg.lambda_ais;
+        launch_weights(h->d_costs, K, lam, h->d_w, stop, st);
+        h->launches += 1;
+        const bool cov = pol == MPOPIS_POLICY_MUSIGMAAISMPPI;
+        if (int rc = moments(h, h->d_E, h->ldk, Kloc, h->d_w + h->k0, cov, 0, MPOPIS_SIGMA_MLE, 10e-9, true,
+                             nullptr, h->d_Sigma))
+          return rc;
+        break;
+      }
+      case MPOPIS_POLICY_PMCMPPI: {  // POL:802-809
+        launch_weights(h->d_costs, K, h->cfg.lambda_ais, h->d_w, stop, st);
+        if (u_host) CU(cudaMemcpyAsync(h->d_u, u_host + (size_t)n * K, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+        else launch_philox_uniforms(h->d_u, K, h->seed, (uint32_t)h->step, (uint32_t)n, stop, st);
+        launch_pmc_counts(h->d_w, K, h->d_u, h->d_cdf, h->d_counts, h->k0, Kloc, h->d_wcnt, stop, st);
+        h->launches += 5;
+        if (int rc = moments(h, h->d_E, h->ldk, Kloc, h->d_wcnt, true, 1, MPOPIS_SIGMA_MLE, 10e-9, true, nullptr,
+                             h->d_Sigma))
+          return rc;
+        break;
+      }
+      case MPOPIS_POLICY_CEMPPI:
+      case MPOPIS_POLICY_CMAMPPI: {  // POL:455-465, 563-599
+        const int m = h->m_elite;
+        launch_sortperm(h->d_costs, K, m, h->d_keys_a, h->d_keys_b, h->d_order, h->d_vals_b, h->d_hist,
+                        h->d_sorted, stop, st);
+        launch_elite_stop(h->d_sorted, m, h->cfg.early_stop, stop, st);
+        launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, m, h->k0, Kloc, h->d_X, h->ldm,
+                           h->world > 1 ? h->d_mask : nullptr, stop, st);
+        h->launches += 29;
+        if (pol == MPOPIS_POLICY_CEMPPI) {
+          if (int rc = moments(h, h->d_X, h->ldm, m, h->world > 1 ? h->d_mask : nullptr, true, 0,
+                               h->cfg.sigma_est, 10e-9, true, nullptr, h->d_Sigma))
+            return rc;
+        } else {
+          if (int rc = cma_update(h, n + 1)) return rc;
+        }
+        break;
+      }
+      default: break;
+    }
+  }
+  h->last_its_launched = N;
+  // --- final weights (always λ: POL:313,367,470,604,665,736,811), weighted noise, control, roll ---
+  launch_weights(h->d_costs, K, h->cfg.lambda, h->d_w, nullptr, st);
+  launch_rowsum_partial(h->d_E, h->ldk, cs, Kloc, h->d_w + h->k0, h->d_part, nullptr, st);
+  launch_reduce_partials(h->d_part, rowsum_nchunks(Kloc), cs + 1, h->d_sums, nullptr, st);
+  h->launches += 3;
+  if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
+  launch_finalize_control(h->d_sums, h->d_U_orig, h->d_U_cur, cs, h->as, h->T, h->d_U_next, h->d_control, st);
+  h->launches += 1;
+  CU(cudaEventRecord(h->ev[1], st));
+  CU(cudaGetLastError());
+  h->step += 1;
+  h->timing_valid = false;
+  return 0;
+}
+
+int finish_timing(mpopis_t *h) {
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+  h->last_total_ms = ms;
+  double r = 0;
+  for (int n = 0; n < h->last_its_launched; ++n) {
+    CU(cudaEventElapsedTime(&ms, h->ev[2 + 2 * n], h->ev[3 + 2 * n]));
+    r += ms;
+  }
+  h->last_rollout_ms = r;
+  h->timing_valid = true;
+  return 0;
+}
+
+int check_info(mpopis_t *h, int info) {
+  if (info != 0)
+    return fail(MPOPIS_ERR_NOT_PD, "PosDefException: matrix is not positive definite; Cholesky factorization failed (%s)",
+                info >= 1000 ? "initial Σ" : (std::string("AIS iteration ") + std::to_string(info)).c_str());
+  return 0;
+}
+
+// CMA-ES adaptation (POL:571-599): δw row sums, the linear-index gather for the scalar "rank-μ"
+// term, Σ^-0.5 (one cooperative kernel) and the vector-sized updates (one CTA).
+int cma_update(mpopis_t *h, int n_iter) {
+  const int cs = h->cs, m = h->m_elite, K = h->K;
+  const int *stop = h->stop();
+  launch_rowsum_partial(h->d_X, h->ldm, cs, m, h->d_ws, h->d_part, stop, h->st);
+  launch_reduce_partials(h->d_part, rowsum_nchunks(m), cs + 1, h->d_sums, stop, h->st);
+  if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
+  launch_cma_lin_gather(h->d_X, h->ldm, cs, h->d_order, K, h->d_cdf, stop, h->st);
+  if (int rc = allreduce_sum(h, h->d_cdf, K)) return rc;
+  cudaError_t e = (cudaError_t)launch_inv_sqrt(h->d_Sigma, cs, h->d_C, h->d_ns, h->info(), 2000 + n_iter, stop,
+                                               h->coop_max, h->st);
+  if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  launch_cma_vec(h->d_sums, h->d_C, h->d_cdf, h->d_ws, K, cs, n_iter, h->cma, h->d_psig, h->d_pSig, h->d_sigma,
+                 h->d_U_cur, h->d_Sigma, stop, h->st);
+  h->launches += 5;
+  return 0;
+}
+
+int ensure_elite_capacity(mpopis_t *h, int m) {
+  const long long ldm = ((long long)m + 31) / 32 * 32;
+  if (h->d_X && ldm <= h->ldm) return 0;
+  if (h->d_X) cudaFree(h->d_X), cudaFree(h->d_mask);
+  h->ldm = ldm;
+  if (int rc = dalloc(&h->d_X, (size_t)h->cs * ldm)) return rc;
+  return dalloc(&h->d_mask, (size_t)ldm);
+}
+
+int upload_inputs(mpopis_t *h, const double *state, int64_t env_t, const double *U) {
+  memcpy(h->h_in, state, sizeof(double) * h->ss);
+  memcpy(h->h_in + h->ss, U, sizeof(double) * h->cs);
+  long long t = env_t;
+  memcpy(h->h_in + h->ss + h->cs, &t, sizeof t);
+  CU(cudaMemcpyAsync(h->d_state, h->h_in, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_U_orig, h->h_in + h->ss, sizeof(double) * h->cs, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_env_t, h->h_in + h->ss + h->cs, sizeof(long long), cudaMemcpyHostToDevice, h->st));
+  return 0;
+}
+
+int download_outputs(mpopis_t *h, double *U_out, double *control_out, int32_t *its_out, double *state_out) {
+  CU(cudaMemcpyAsync(h->h_out, h->d_control, sizeof(double) * h->as, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(h->h_out + h->as, h->d_U_next, sizeof(double) * h->cs, cudaMemcpyDeviceToHost, h->st));
+  if (state_out)
+    CU(cudaMemcpyAsync(h->h_out + h->as + h->cs, h->d_state, sizeof(double) * h->ss, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int) * 3, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  if (int rc = finish_timing(h)) return rc;
+  if (int rc = check_info(h, h->h_flags[2])) return rc;
+  if (control_out) memcpy(control_out, h->h_out, sizeof(double) * h->as);
+  if (U_out) memcpy(U_out, h->h_out + h->as, sizeof(double) * h->cs);
+  if (state_out) memcpy(state_out, h->h_out + h->as + h->cs, sizeof(double) * h->ss);
+  if (its_out) *its_out = h->h_flags[1];
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+int mpopis_b200_abi_version(void) { return MPOPIS_B200_ABI_VERSION; }
+const char *mpopis_b200_last_error(void) { return g_err; }
+
+int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
+  if (!cfg || !out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MPOPIS_B200_ABI_VERSION) return fail(MPOPIS_ERR_BAD_ARG, "abi version mismatch");
+  if (cfg->policy < 0 || cfg->policy > MPOPIS_POLICY_PMCMPPI)
+    return fail(MPOPIS_ERR_BAD_ARG, "No policy_type of %d", cfg->policy);
+  if (cfg->num_samples < 1 || cfg->horizon < 1 || cfg->opt_its < 1 || cfg->num_samples > (1LL << 30))
+    return fail(MPOPIS_ERR_BAD_ARG, "num_samples, horizon and opt_its must be positive");
+  if (!(cfg->lambda > 0.0)) return fail(MPOPIS_ERR_BAD_ARG, "λ must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(MPOPIS_ERR_NO_DEVICE, "no CUDA device visible: the engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MPOPIS_ERR_BAD_ARG, "device ordinal out of range");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(MPOPIS_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                prop.major, prop.minor);
+  const int world = cfg->world_size < 1 ? 1 : cfg->world_size;
+  if (cfg->rank < 0 || cfg->rank >= world) return fail(MPOPIS_ERR_BAD_ARG, "rank out of range");
+  if (cfg->num_samples % world) return fail(MPOPIS_ERR_BAD_ARG, "num_samples must be divisible by world_size");
+
+  mpopis_t *h = new mpopis_handle();
+  h->cfg = *cfg;
+  h->dev = cfg->device, h->world = world, h->rank = cfg->rank;
+  h->K = (int)cfg->num_samples, h->T = (int)cfg->horizon;
+  h->N = (cfg->policy == MPOPIS_POLICY_MPPI || cfg->policy == MPOPIS_POLICY_GMPPI) ? 1 : (int)cfg->opt_its;
+  if (cfg->env == MPOPIS_ENV_CAR_RACING) {
+    if (cfg->n_cars < 1 || cfg->n_cars > MPOPIS_MAX_CARS) {
+      delete h;
+      return fail(MPOPIS_ERR_BAD_ARG, "n_cars must be in 1..%d", MPOPIS_MAX_CARS);
+    }
+    h->as = 2 * cfg->n_cars, h->ss = 8 * cfg->n_cars;
+  } else if (cfg->env == MPOPIS_ENV_MOUNTAIN_CAR) {
+    h->as = 1, h->ss = 2;
+  } else {
+    delete h;
+    return fail(MPOPIS_ERR_BAD_ARG, "unknown env %d", cfg->env);
+  }
+  h->cs = h->as * h->T;  // POL:59
+  h->Kloc = h->K / world, h->k0 = (long long)h->rank * h->Kloc;
+  h->ldk = ((long long)h->Kloc + 31) / 32 * 32;
+  h->gamma = cfg->lambda * (1 - cfg->alpha);  // POL:266
+  h->sigma_bs = 1;
+  if (cfg->policy == MPOPIS_POLICY_CEMPPI) {
+    h->m_elite = (int)llrint((double)h->K * (1 - cfg->ce_elite_threshold));  // POL:437, ties-to-even
+    if (h->N > 1 && (h->m_elite < 2 || h->m_elite > h->K)) {
+      delete h;
+      return fail(MPOPIS_ERR_BAD_ARG, "m_elite = %d out of range", h->m_elite);
+    }
+  }
+  if (const char *e = getenv("MPOPIS_ROLLOUT_VARIANT")) h->rollout_variant = atoi(e);
+  if (const char *e = getenv("MPOPIS_ROLLOUT_BLOCK")) h->rollout_block = atoi(e);
+  if (h->rollout_block < 32 || h->rollout_block > 128 || h->rollout_block % 32) h->rollout_block = 64;
+
+  auto bail = [&](int rc) {
+    mpopis_b200_destroy(h);
+    return rc;
+  };
+#define TRY(x)                    \
+  do {                            \
+    if (int rc_ = (x)) return bail(rc_); \
+  } while (0)
+  TRY(set_device(h));
+  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(MPOPIS_ERR_CUDA, "cudaStreamCreate failed"));
+  const size_t cs = h->cs, K = h->K, Kloc = h->Kloc, ld = h->ldk;
+  TRY(dalloc(&h->d_state, h->ss));
+  TRY(dalloc(&h->d_env_t, 1));
+  TRY(dalloc(&h->d_U_orig, cs));
+  TRY(dalloc(&h->d_U_cur, cs));
+  TRY(dalloc(&h->d_U_next, cs));
+  TRY(dalloc(&h->d_control, h->as));
+  TRY(dalloc(&h->d_Sigma0, cs * cs));
+  TRY(dalloc(&h->d_Sigma, cs * cs));
+  TRY(dalloc(&h->d_Lt, cs * cs));
+  TRY(dalloc(&h->d_Lt0, cs * cs));
+  TRY(dalloc(&h->d_cholW, cs * cs));
+  TRY(dalloc(&h->d_bvec, cs));
+  TRY(dalloc(&h->d_Z, cs * ld));
+  TRY(dalloc(&h->d_E, cs * ld));
+  TRY(dalloc(&h->d_stage, cs * Kloc));
+  TRY(dalloc(&h->d_costs, K));
+  TRY(dalloc(&h->d_w, K));
+  TRY(dalloc(&h->d_sorted, K));
+  TRY(dalloc(&h->d_keys_a, K));
+  TRY(dalloc(&h->d_keys_b, K));
+  TRY(dalloc(&h->d_order, K));
+  TRY(dalloc(&h->d_vals_b, K));
+  TRY(dalloc(&h->d_hist, sort_hist_ints((int)K)));
+  TRY(dalloc(&h->d_flags, 4));
+  TRY(dalloc(&h->d_sums, cs + 1));
+  TRY(dalloc(&h->d_mu, cs));
+  TRY(dalloc(&h->d_Sraw, cs * cs));
+  TRY(dalloc(&h->d_P, (size_t)66 * cs * cs));
+  TRY(dalloc(&h->d_q, 1));
+  TRY(dalloc(&h->d_lambda, 1));
+  TRY(dalloc(&h->d_reward, 1));
+  TRY(dalloc(&h->d_done, 1));
+  const size_t nmax = K;  // moments may run over Kloc samples or up to K elites
+  h->part_doubles = (size_t)(rowsum_nchunks((int)nmax) + 1) * (cs + 1);
+  TRY(dalloc(&h->d_part, h->part_doubles));
+  TRY(dalloc(&h->d_qpart, (nmax + 255) / 256 + 1));
+  if (cfg->policy == MPOPIS_POLICY_CEMPPI) TRY(ensure_elite_capacity(h, h->m_elite));
+  if (cfg->policy == MPOPIS_POLICY_PMCMPPI || cfg->policy == MPOPIS_POLICY_CMAMPPI) {
+    TRY(dalloc(&h->d_u, K));
+    TRY(dalloc(&h->d_cdf, K));
+    TRY(dalloc(&h->d_counts, K));
+    TRY(dalloc(&h->d_wcnt, Kloc));
+  }
+  if (cfg->policy == MPOPIS_POLICY_CMAMPPI) {
+    TRY(dalloc(&h->d_ws, K));
+    TRY(dalloc(&h->d_sigma, 1));
+    TRY(dalloc(&h->d_psig, cs));
+    TRY(dalloc(&h->d_pSig, cs));
+    TRY(dalloc(&h->d_C, cs * cs));
+    TRY(dalloc(&h->d_ns, 5 * cs * cs + 8));
+  }
+  if (cfg->log_trajectories) TRY(dalloc(&h->d_traj, Kloc * (size_t)h->T * h->ss));
+  if (cudaMallocHost((void **)&h->h_in, sizeof(double) * (h->ss + cs + 2)) != cudaSuccess ||
+      cudaMallocHost((void **)&h->h_out, sizeof(double) * (h->as + cs + h->ss + 2)) != cudaSuccess ||
+      cudaMallocHost((void **)&h->h_flags, sizeof(int) * 4) != cudaSuccess)
+    return bail(fail(MPOPIS_ERR_CUDA, "cudaMallocHost failed"));
+  h->ev.resize(2 + 2 * h->N);
+  for (auto &e : h->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MPOPIS_ERR_CUDA, "cudaEventCreate failed"));
+  h->coop_max = inv_sqrt_max_ctas(prop.multiProcessorCount);
+  {  // Σ defaults to the identity until set_sigma()
+    std::vector<double> I(cs * cs, 0.0);
+    for (size_t i = 0; i < cs; ++i) I[i * cs + i] = 1.0;
+    if (cudaMemcpy(h->d_Sigma0, I.data(), sizeof(double) * cs * cs, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(MPOPIS_ERR_CUDA, "cudaMemcpy failed"));
+  }
+#undef TRY
+  *out = h;
+  return 0;
+}
+
+int mpopis_b200_destroy(mpopis_t *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->dev);
+  if (h->st) cudaStreamSynchronize(h->st);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void *ptrs[] = {h->d_trk,    h->d_state, h->d_U_orig, h->d_U_cur,  h->d_U_next, h->d_control, h->d_Sigma0,
+                  h->d_Sigma,  h->d_Lt,    h->d_Lt0,    h->d_cholW,  h->d_bvec,   h->d_Z,       h->d_E,
+                  h->d_stage,  h->d_costs, h->d_w,      h->d_sorted, h->d_X,      h->d_mask,    h->d_part,
+                  h->d_sums,   h->d_mu,    h->d_P,      h->d_Sraw,   h->d_qpart,  h->d_q,       h->d_lambda,
+                  h->d_traj,   h->d_u,     h->d_cdf,    h->d_wcnt,   h->d_ws,     h->d_sigma,   h->d_psig,
+                  h->d_pSig,   h->d_C,     h->d_ns,     h->d_reward, h->d_env_t,  h->d_keys_a,  h->d_keys_b,
+                  h->d_order,  h->d_vals_b, h->d_hist,  h->d_counts, h->d_flags,  h->d_done};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_in) cudaFreeHost(h->h_in);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  for (auto &e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+int mpopis_b200_comm_id(void *out128) {
+  if (!out128) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (!g_nccl.load()) return fail(MPOPIS_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int mpopis_b200_comm_init(mpopis_t *h, const void *id128) {
+  if (!h || !id128) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->world == 1) return 0;
+  if (!g_nccl.load()) return fail(MPOPIS_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+  if (int rc = set_device(h)) return rc;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NC(g_nccl.CommInitRank(&h->comm, h->world, id, h->rank));
+  return 0;
+}
+
+int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params, double dt, double ddt,
+                            const double *trk_x, const double *trk_y, const double *trk_w, int64_t n_trk) {
+  if (!h || !params || !trk_x || !trk_y || !trk_w) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->cfg.env != MPOPIS_ENV_CAR_RACING || n_cars != h->cfg.n_cars)
+    return fail(MPOPIS_ERR_BAD_ARG, "handle was created for a different environment");
+  if (n_trk < 2 || n_trk > 9000) return fail(MPOPIS_ERR_BAD_ARG, "track must have 2..9000 sampled points");
+  if (!(dt > 0) || !(ddt > 0)) return fail(MPOPIS_ERR_BAD_ARG, "dt and δt must be positive");
+  if (int rc = set_device(h)) return rc;
+  static_assert(sizeof(CarParams) == sizeof(double) * MPOPIS_CAR_NPARAMS, "CarParams layout");
+  for (int c = 0; c < n_cars; ++c) {
+    memcpy(&h->car.car[c], params + (size_t)c * MPOPIS_CAR_NPARAMS, sizeof(CarParams));
+    h->car.cos_blimit[c] = h->car.car[c].b_limit >= M_PI ? -2.0 : std::cos(h->car.car[c].b_limit);
+  }
+  h->car.dt = dt, h->car.ddt = ddt, h->car.nsub = (int)lrint(dt / ddt);  // CAR:299
+  h->car.n_cars = n_cars, h->car.n_trk = (int)n_trk;
+  if (h->d_trk) cudaFree(h->d_trk), h->d_trk = nullptr;
+  if (int rc = dalloc(&h->d_trk, 3 * (size_t)n_trk)) return rc;
+  CU(cudaMemcpy(h->d_trk, trk_x, sizeof(double) * n_trk, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_trk + n_trk, trk_y, sizeof(double) * n_trk, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_trk + 2 * n_trk, trk_w, sizeof(double) * n_trk, cudaMemcpyHostToDevice));
+  h->car.trk = h->d_trk;
+  h->env_set = true;
+  return 0;
+}
+
+int mpopis_b200_set_mountaincar_env(mpopis_t *h, const double *p, int64_t max_steps) {
+  if (!h || !p) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->cfg.env != MPOPIS_ENV_MOUNTAIN_CAR)
+    return fail(MPOPIS_ERR_BAD_ARG, "handle was created for a different environment");
+  h->mc = McEnvArgs{p[0], p[1], p[2], p[3], p[4], p[5], p[6], (long long)max_steps};
+  h->env_set = true;
+  return 0;
+}
+
+// cov_mat handling of MPPI_Policy_Params (POL:66-81) + block_diagm (UTL:9-21)
+int mpopis_b200_set_sigma(mpopis_t *h, const double *Sigma, int64_t n) {
+  if (!h || !Sigma) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  const int cs = h->cs, as = h->as;
+  const int check = is_g_family(h->cfg.policy) ? cs : as;  // POL:66-74
+  std::vector<double> S((size_t)cs * cs, 0.0);
+  if (n == as) {
+    for (int b = 0; b < cs; b += as)
+      for (int i = 0; i < as; ++i)
+        for (int j = 0; j < as; ++j) S[(size_t)(b + j) * cs + b + i] = Sigma[(size_t)j * as + i];
+    h->sigma_bs = as;
+  } else if (n == cs && check == cs) {
+    memcpy(S.data(), Sigma, sizeof(double) * cs * cs);
+    h->sigma_bs = cs;
+  } else {
+    return fail(MPOPIS_ERR_BAD_ARG, "Covariance matrix size problem");
+  }
+  for (int i = 0; i < cs; ++i)
+    for (int j = 0; j < i; ++j)
+      if (S[(size_t)j * cs + i] != S[(size_t)i * cs + j])
+        return fail(MPOPIS_ERR_NOT_PD, "PosDefException: covariance matrix is not symmetric");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemcpy(h->d_Sigma0, S.data(), sizeof(double) * cs * cs, cudaMemcpyHostToDevice));
+  h->L0_valid = false;
+  return 0;
+}
+
+int mpopis_b200_set_cma(mpopis_t *h, const mpopis_cma_t *cma, const double *ws, int64_t n_ws) {
+  if (!h || !cma || !ws) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->cfg.policy != MPOPIS_POLICY_CMAMPPI) return fail(MPOPIS_ERR_BAD_ARG, "not a :cmamppi handle");
+  if (n_ws != h->K) return fail(MPOPIS_ERR_BAD_ARG, "ws must have num_samples entries");
+  if (h->N > 1 && (cma->m_elite < 2 || cma->m_elite > h->K)) return fail(MPOPIS_ERR_BAD_ARG, "m_elite out of range");
+  if (h->N > 1 && (long long)h->cs * cma->m_elite < h->K)
+    return fail(MPOPIS_ERR_BAD_ARG, "BoundsError: CMA linear index exceeds cs*m_elite (POL:593)");
+  if (int rc = set_device(h)) return rc;
+  h->cma = *cma;
+  h->m_elite = (int)cma->m_elite;
+  if (int rc = ensure_elite_capacity(h, h->m_elite)) return rc;
+  CU(cudaMemcpy(h->d_ws, ws, sizeof(double) * n_ws, cudaMemcpyHostToDevice));
+  h->cma_set = true;
+  return 0;
+}
+
+int mpopis_b200_seed(mpopis_t *h, uint64_t seed) {
+  if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  h->seed = seed;
+  h->step = 0;
+  return 0;
+}
+
+int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
+  if (!h || !key) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (!strcmp(key, "rollout_variant")) h->rollout_variant = value != 0.0;
+  else if (!strcmp(key, "rollout_block")) {
+    const int b = (int)value;
+    if (b < 32 || b > 128 || b % 32) return fail(MPOPIS_ERR_BAD_ARG, "rollout_block must be 32, 64, 96 or 128");
+    h->rollout_block = b;
+  } else
+    return fail(MPOPIS_ERR_BAD_ARG, "unknown option %s", key);
+  return 0;
+}
+
+int mpopis_b200_plan_with_noise(mpopis_t *h, const double *state, int64_t env_t, double *U_inout,
+                                const double *Z, const double *resample_u, double *control_out,
+                                int32_t *its_run_out) {
+  if (!h || !state || !U_inout || !control_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemsetAsync(h->info(), 0, sizeof(int), h->st));
+  if (int rc = upload_inputs(h, state, env_t, U_inout)) return rc;
+  if (int rc = plan_core(h, Z, resample_u)) {
+    cudaStreamSynchronize(h->st);
+    return rc;
+  }
+  return download_outputs(h, U_inout, control_out, its_run_out, nullptr);
+}
+
+int mpopis_b200_plan(mpopis_t *h, const double *state, int64_t env_t, double *U_inout, double *control_out,
+                     int32_t *its_run_out) {
+  return mpopis_b200_plan_with_noise(h, state, env_t, U_inout, nullptr, nullptr, control_out, its_run_out);
+}
+
+int mpopis_b200_fetch(mpopis_t *h, double *costs, double *weights, double *E, double *traj) {
+  if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  if (costs) CU(cudaMemcpyAsync(costs, h->d_costs, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->st));
+  if (weights) CU(cudaMemcpyAsync(weights, h->d_w, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->st));
+  if (E) {  // E .+ (pol.U − U_orig), POL:370,468,602,668,739,814, back in Julia's cs x K layout
+    launch_transpose_out(h->d_E, h->d_stage, h->cs, h->Kloc, h->ldk, h->d_U_cur, h->d_U_orig, h->st);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(E, h->d_stage, sizeof(double) * h->cs * h->Kloc, cudaMemcpyDeviceToHost, h->st));
+  }
+  if (traj) {
+    if (!h->d_traj) return fail(MPOPIS_ERR_BAD_ARG, "log_trajectories was not enabled");
+    // device layout [k][ss][T] is exactly K column-major T x ss matrices
+    CU(cudaMemcpyAsync(traj, h->d_traj, sizeof(double) * (size_t)h->Kloc * h->T * h->ss, cudaMemcpyDeviceToHost, h->st));
+  }
+  CU(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int mpopis_b200_fetch_proposal(mpopis_t *h, double *Sigma_last, double *U_last) {
+  if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  const size_t cs = h->cs;
+  if (Sigma_last) {  // Σ′ the last executed iteration sampled from = L Lᵀ is not stored; return the matrix factored
+    const bool adapted = adapts_sigma(h->cfg.policy) && h->N > 1;
+    CU(cudaMemcpyAsync(Sigma_last, adapted ? h->d_Sigma : h->d_Sigma0, sizeof(double) * cs * cs,
+                       cudaMemcpyDeviceToHost, h->st));
+  }
+  if (U_last) CU(cudaMemcpyAsync(U_last, h->d_U_cur, sizeof(double) * cs, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int mpopis_b200_rollout_costs(mpopis_t *h, const double *state, int64_t env_t, const double *U,
+                              const double *U_orig, const double *E, const double *Sigma_inv,
+                              double *costs_out) {
+  if (!h || !state || !U || !U_orig || !E || !costs_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (!h->env_set) return fail(MPOPIS_ERR_BAD_ARG, "environment not set");
+  if (h->gamma != 0.0 && !Sigma_inv) return fail(MPOPIS_ERR_BAD_ARG, "Sigma_inv required when γ = λ(1-α) != 0");
+  if (int rc = set_device(h)) return rc;
+  const int cs = h->cs;
+  cudaStream_t st = h->st;
+  if (int rc = upload_inputs(h, state, env_t, U_orig)) return rc;
+  CU(cudaMemcpyAsync(h->d_U_cur, U, sizeof(double) * cs, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3, st));
+  CU(cudaMemcpyAsync(h->d_stage, E + (size_t)h->k0 * cs, sizeof(double) * cs * h->Kloc, cudaMemcpyHostToDevice, st));
+  launch_transpose_in(h->d_stage, h->d_E, cs, h->Kloc, h->ldk, st);
+  const double *bvec = nullptr;
+  if (h->gamma != 0.0) {
+    CU(cudaMemcpyAsync(h->d_cholW, Sigma_inv, sizeof(double) * cs * cs, cudaMemcpyHostToDevice, st));
+    launch_ctrl_vec(h->d_cholW, cs, h->d_U_orig, h->gamma, h->d_bvec, st);
+    bvec = h->d_bvec;
+    h->launches += 1;
+  }
+  h->launches += 1;
+  if (int rc = launch_rollouts(h, h->d_U_cur, h->d_U_orig, bvec)) return rc;
+  if (int rc = allgather_costs(h)) return rc;
+  CU(cudaMemcpyAsync(costs_out, h->d_costs, sizeof(double) * h->K, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mpopis_b200_weights(mpopis_t *h, const double *costs, int64_t K, double lambda, double *w_out) {
+  if (!h || !costs || !w_out || K < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (int rc = set_device(h)) return rc;
+  double *dc = nullptr, *dw = nullptr;
+  if (int rc = dalloc(&dc, (size_t)K)) return rc;
+  if (int rc = dalloc(&dw, (size_t)K)) return rc;
+  CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
+  launch_weights(dc, (int)K, lambda, dw, nullptr, h->st);
+  h->launches += 1;
+  CU(cudaMemcpyAsync(w_out, dw, sizeof(double) * K, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  cudaFree(dc), cudaFree(dw);
+  return 0;
+}
+
+int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *idx_out, int32_t *idx2_out,
+                            double *dist_out, uint8_t *within_out) {
+  if (!h || !pos || n < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (!h->env_set || h->cfg.env != MPOPIS_ENV_CAR_RACING) return fail(MPOPIS_ERR_BAD_ARG, "car env not set");
+  if (int rc = set_device(h)) return rc;
+  double *dp = nullptr, *dd = nullptr;
+  int *di = nullptr, *dj = nullptr;
+  unsigned char *dw = nullptr;
+  if (int rc = dalloc(&dp, 2 * (size_t)n)) return rc;
+  if (int rc = dalloc(&dd, (size_t)n)) return rc;
+  if (int rc = dalloc(&di, (size_t)n)) return rc;
+  if (int rc = dalloc(&dj, (size_t)n)) return rc;
+  if (int rc = dalloc(&dw, (size_t)n)) return rc;
+  CU(cudaMemcpyAsync(dp, pos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->st));
+  launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->st);
+  h->launches += 1;
+  if (idx_out) CU(cudaMemcpyAsync(idx_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));
+  if (idx2_out) CU(cudaMemcpyAsync(idx2_out, dj, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));
+  if (dist_out) CU(cudaMemcpyAsync(dist_out, dd, sizeof(double) * n, cudaMemcpyDeviceToHost, h->st));
+  if (within_out) CU(cudaMemcpyAsync(within_out, dw, n, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  cudaFree(dp), cudaFree(dd), cudaFree(di), cudaFree(dj), cudaFree(dw);
+  return 0;
+}
+
+static int env_step_device(mpopis_t *h, const double *d_action) {
+  if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
+    launch_env_step_car(h->car, h->d_state, d_action, h->d_env_t, h->d_reward, h->rollout_variant, h->st);
+  else
+    launch_env_step_mc(h->mc, h->d_state, d_action, h->d_env_t, h->d_reward, h->d_done, h->st);
+  h->launches += 1;
+  return 0;
+}
+
+int mpopis_b200_env_step(mpopis_t *h, double *state_inout, const double *action, int64_t *env_t_inout,
+                         double *reward_out, uint8_t *done_out) {
+  if (!h || !state_inout || !action || !env_t_inout) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (!h->env_set) return fail(MPOPIS_ERR_BAD_ARG, "environment not set");
+  if (int rc = set_device(h)) return rc;
+  long long t = *env_t_inout;
+  CU(cudaMemcpyAsync(h->d_state, state_inout, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_env_t, &t, sizeof t, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_control, action, sizeof(double) * h->as, cudaMemcpyHostToDevice, h->st));
+  env_step_device(h, h->d_control);
+  double rew = 0;
+  unsigned char done = 0;
+  CU(cudaMemcpyAsync(state_inout, h->d_state, sizeof(double) * h->ss, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(&t, h->d_env_t, sizeof t, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(&rew, h->d_reward, sizeof rew, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(&done, h->d_done, 1, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  *env_t_inout = t;
+  if (reward_out) *reward_out = rew;
+  if (done_out) *done_out = h->cfg.env == MPOPIS_ENV_MOUNTAIN_CAR ? done : 0;
+  return 0;
+}
+
+int mpopis_b200_env_reward(mpopis_t *h, const double *state, uint8_t done, double *reward_out) {
+  if (!h || !state || !reward_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (!h->env_set) return fail(MPOPIS_ERR_BAD_ARG, "environment not set");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemcpyAsync(h->d_state, state, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));
+  if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
+    launch_env_reward_car(h->car, h->d_state, h->d_reward, h->rollout_variant, h->st);
+  else
+    launch_env_reward_mc(h->mc, h->d_state, done, h->d_reward, h->st);
+  h->launches += 1;
+  CU(cudaMemcpyAsync(reward_out, h->d_reward, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mpopis_b200_sample_normals(mpopis_t *h, int64_t step, int64_t iteration, double *Z_out) {
+  if (!h || !Z_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  launch_philox_normals(h->d_Z, h->ldk, h->cs, h->Kloc, h->k0, h->seed, (uint32_t)step, (uint32_t)iteration, nullptr,
+                        h->st);
+  launch_transpose_out(h->d_Z, h->d_stage, h->cs, h->Kloc, h->ldk, nullptr, nullptr, h->st);
+  h->launches += 2;
+  CU(cudaMemcpyAsync(Z_out, h->d_stage, sizeof(double) * h->cs * h->Kloc, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mpopis_b200_cov_estimate(mpopis_t *h, int32_t sigma_est, const double *X, int64_t p, int64_t n,
+                             const double *w, int32_t corrected, double *mean_out, double *cov_out) {
+  if (!h || !X || n < 2) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (p != h->cs) return fail(MPOPIS_ERR_BAD_ARG, "p must equal the handle's control size cs = %d", h->cs);
+  if (n > h->K) return fail(MPOPIS_ERR_BAD_ARG, "n exceeds the handle's capacity (num_samples)");
+  if (h->world != 1) return fail(MPOPIS_ERR_BAD_ARG, "cov_estimate is a single-shard parity surface");
+  if (int rc = set_device(h)) return rc;
+  const long long ld = ((long long)n + 31) / 32 * 32;
+  double *dcm = nullptr, *dX = nullptr, *dw = nullptr, *dS = nullptr;
+  if (int rc = dalloc(&dcm, (size_t)p * n)) return rc;
+  if (int rc = dalloc(&dX, (size_t)p * ld)) return rc;
+  if (int rc = dalloc(&dS, (size_t)p * p)) return rc;
+  CU(cudaMemcpyAsync(dcm, X, sizeof(double) * p * n, cudaMemcpyHostToDevice, h->st));
+  launch_transpose_in(dcm, dX, (int)p, (int)n, ld, h->st);
+  if (w) {
+    if (int rc = dalloc(&dw, (size_t)n)) return rc;
+    CU(cudaMemcpyAsync(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+  }
+  CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3, h->st));
+  const int method = (w || corrected) ? MPOPIS_SIGMA_MLE : sigma_est;
+  if (int rc = moments(h, dX, ld, (int)n, dw, cov_out != nullptr, corrected, method, 0.0, false, nullptr, dS)) return rc;
+  if (mean_out) CU(cudaMemcpyAsync(mean_out, h->d_mu, sizeof(double) * p, cudaMemcpyDeviceToHost, h->st));
+  if (cov_out) CU(cudaMemcpyAsync(cov_out, dS, sizeof(double) * p * p, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  cudaFree(dcm), cudaFree(dX), cudaFree(dS);
+  if (dw) cudaFree(dw);
+  return 0;
+}
+
+int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out) {
+  if (!h || !lambda_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemcpy(lambda_out, h->d_lambda, sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int mpopis_b200_cholesky(mpopis_t *h, const double *A, int64_t n, double *L_out) {
+  if (!h || !A || !L_out || n < 1 || n > 4096) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (int rc = set_device(h)) return rc;
+  double *dA = nullptr, *dLt = nullptr, *dW = nullptr;
+  int *dinfo = nullptr, info = 0;
+  const size_t nn = (size_t)n * n;
+  if (int rc = dalloc(&dA, nn)) return rc;
+  if (int rc = dalloc(&dLt, nn)) return rc;
+  if (int rc = dalloc(&dW, nn)) return rc;
+  if (int rc = dalloc(&dinfo, 1)) return rc;
+  CU(cudaMemcpyAsync(dA, A, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
+  launch_chol(dA, (int)n, nullptr, dLt, dW, dinfo, 1, nullptr, h->st);
+  launch_transpose_sq(dLt, dA, (int)n, h->st);  // row-major L -> column-major L
+  h->launches += 2;
+  CU(cudaMemcpyAsync(L_out, dA, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  cudaFree(dA), cudaFree(dLt), cudaFree(dW), cudaFree(dinfo);
+  if (info) return fail(MPOPIS_ERR_NOT_PD, "PosDefException: matrix is not positive definite; Cholesky factorization failed.");
+  return 0;
+}
+
+int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out) {
+  if (!h || !A || !C_out || n < 1 || n > 4096) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (int rc = set_device(h)) return rc;
+  double *dA = nullptr, *dC = nullptr, *dws = nullptr;
+  int *dinfo = nullptr, info = 0;
+  const size_t nn = (size_t)n * n;
+  if (int rc = dalloc(&dA, nn)) return rc;
+  if (int rc = dalloc(&dC, nn)) return rc;
+  if (int rc = dalloc(&dws, 5 * nn + 8)) return rc;
+  if (int rc = dalloc(&dinfo, 1)) return rc;
+  CU(cudaMemcpyAsync(dA, A, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
+  cudaError_t e = (cudaError_t)launch_inv_sqrt(dA, (int)n, dC, dws, dinfo, 1, nullptr, h->coop_max, h->st);
+  if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  h->launches += 1;
+  CU(cudaMemcpyAsync(C_out, dC, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  cudaFree(dA), cudaFree(dC), cudaFree(dws), cudaFree(dinfo);
+  if (info) return fail(MPOPIS_ERR_NOT_PD, "Σ^-0.5: matrix is not positive definite");
+  return 0;
+}
+
+int mpopis_b200_resident_reset(mpopis_t *h, const double *state, int64_t env_t, const double *U) {
+  if (!h || !state || !U) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemsetAsync(h->info(), 0, sizeof(int), h->st));
+  if (int rc = upload_inputs(h, state, env_t, U)) return rc;
+  CU(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int mpopis_b200_resident_plan(mpopis_t *h, int32_t advance_env) {
+  if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  if (int rc = plan_core(h, nullptr, nullptr)) return rc;
+  if (advance_env) env_step_device(h, h->d_control);  // env(act), car_example.jl:205-207
+  CU(cudaMemcpyAsync(h->d_U_orig, h->d_U_next, sizeof(double) * h->cs, cudaMemcpyDeviceToDevice, h->st));
+  return 0;
+}
+
+int mpopis_b200_resident_read(mpopis_t *h, double *state_out, double *U_out, double *control_out,
+                              int32_t *its_run_out) {
+  if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  return download_outputs(h, U_out, control_out, its_run_out, state_out ? state_out : nullptr);
+}
+
+int64_t mpopis_b200_launch_count(mpopis_t *h) { return h ? h->launches : 0; }
+
+int mpopis_b200_last_timing(mpopis_t *h, double *rollout_ms, double *total_ms, int32_t *rollout_launches) {
+  if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (!h->timing_valid) return fail(MPOPIS_ERR_BAD_ARG, "no completed plan to report");
+  if (rollout_ms) *rollout_ms = h->last_rollout_ms;
+  if (total_ms) *total_ms = h->last_total_ms;
+  if (rollout_launches) *rollout_launches = h->last_its_launched;
+  return 0;
+}
+
+void *mpopis_b200_stream(mpopis_t *h) { return h ? (void *)h->st : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+// stats.cu — G4/G5/G7/G8/G10: everything between two rollout batches of the AIS loop.
+//
+//   G7  compute_weights(Information_Theoretic, costs)                      UTL:79-86
+//   G8  weighted noise  Σ_k w_k E[r,k]  + shift/clamp/roll                 POL:226-231, UTL:88-101
+//   G4  elite gather + early-stop test                                     POL:455-461, 563-569
+//   G5  mean / covariance of elites or weighted samples                    POL:464-465, 364, 662, 732, 807
+//       + CovarianceEstimation shrinkage (:lw :ss :rblw :oas)              POL:414-426
+//   G10 multinomial resampling (PMC) as per-sample counts                  POL:804-806
+//
+// All reductions are two-phase (per-chunk partials in a fixed grid, then an ordered sum), so
+// results are deterministic run to run; in the sharded configuration the ordered sums are what
+// gets all-reduced. Every kernel of the AIS loop takes the device-side `stop` flag (CE/CMA
+// early stop) and returns immediately once it is set, so the host never has to synchronise
+// inside a control step.
+#include <math_constants.h>
+
+#include "engine.cuh"
+
+namespace mpopis {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide reductions (result valid in every thread); red = shared scratch of >= 33 doubles
+template <int OP>  // 0 sum, 1 min, 2 max
+__device__ __forceinline__ double block_reduce(double v, double *red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = OP == 0 ? warp_sum(v) : (OP == 1 ? warp_min(v) : warp_max(v));
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = lane < nw ? red[lane] : (OP == 0 ? 0.0 : (OP == 1 ? CUDART_INF : -CUDART_INF));
+    t = OP == 0 ? warp_sum(t) : (OP == 1 ? warp_min(t) : warp_max(t));
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ---- G7: importance weights -------------------------------------------------------------------
+// w_k = exp(-(c_k − ρ)/λ) / η, ρ = min c, η = Σ exp(...)  (UTL:79-86). Single CTA: K values are
+// at most a few MB and this runs once per AIS iteration.
+__global__ void __launch_bounds__(1024) weights_kernel(const double *__restrict__ costs, int K, double lambda,
+                                                        double *__restrict__ w, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[33];
+  double mn = CUDART_INF;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) mn = fmin(mn, costs[k]);
+  const double rho = block_reduce<1>(mn, red);
+  const double ninv = -1 / lambda;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const double e = exp(ninv * (costs[k] - rho));
+    w[k] = e;
+    s += e;
+  }
+  const double eta = block_reduce<0>(s, red);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) w[k] = w[k] / eta;
+}
+
+void launch_weights(const double *costs, int K, double lambda, double *w, const int *stop, cudaStream_t s) {
+  weights_kernel<<<1, 1024, 0, s>>>(costs, K, lambda, w, stop);
+}
+
+// ---- G8 / G5: weighted row sums ---------------------------------------------------------------
+// partial[c][r] = Σ_{k in chunk c} w_k X[r][k] for r < rows, and partial[c][rows] = Σ_{k in chunk c} w_k
+// (w == nullptr: w_k = 1). X is [rows][ld] with the sample index contiguous, so every warp streams
+// 256-byte row segments: this is the one genuinely HBM-bound kernel of the path (8·cs·K bytes).
+constexpr int RS_THREADS = 256, RS_ROWS = 4, RS_CHUNK = 4096;
+__global__ void __launch_bounds__(RS_THREADS) rowsum_partial_kernel(const double *__restrict__ X, long long ld,
+                                                                     int rows, int n,
+                                                                     const double *__restrict__ w,
+                                                                     double *__restrict__ partial,
+                                                                     const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[33];
+  const int c = blockIdx.x, r0 = blockIdx.y * RS_ROWS;
+  const int kbeg = c * RS_CHUNK, kend = min(n, kbeg + RS_CHUNK);
+  double acc[RS_ROWS];
+#pragma unroll
+  for (int q = 0; q < RS_ROWS; ++q) acc[q] = 0.0;
+  for (int k = kbeg + threadIdx.x; k < kend; k += RS_THREADS) {
+    const double wk = w ? w[k] : 1.0;
+#pragma unroll
+    for (int q = 0; q < RS_ROWS; ++q) {
+      const int r = r0 + q;
+      if (r < rows) acc[q] = fma(wk, X[(size_t)r * ld + k], acc[q]);
+      else if (r == rows) acc[q] += wk;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < RS_ROWS; ++q) {
+    const double t = block_reduce<0>(acc[q], red);
+    if (threadIdx.x == 0 && r0 + q <= rows) partial[(size_t)c * (rows + 1) + r0 + q] = t;
+  }
+}
+
+int rowsum_nchunks(int n) { return (n + RS_CHUNK - 1) / RS_CHUNK; }
+
+void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
+                           const int *stop, cudaStream_t s) {
+  dim3 grid(rowsum_nchunks(n), (rows + 1 + RS_ROWS - 1) / RS_ROWS);
+  rowsum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop);
+}
+
+// out[i] = Σ_c partial[c][i] in chunk order (deterministic)
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int n,
+                                       double *__restrict__ out, const int *stop) {
+  if (stop && *stop) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * n + i];
+  out[i] = s;
+}
+
+void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop,
+                            cudaStream_t s) {
+  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, nchunks, n, out, stop);
+}
+
+// μ = sums[0:rows] / sums[rows]; optionally U += scale * μ  (pol.U = pol.U + vec(μ′), POL:365,465,...)
+__global__ void finalize_mean_kernel(const double *__restrict__ sums, int rows, double *__restrict__ mu,
+                                     double *__restrict__ U, const double *scale_dev, const int *stop) {
+  if (stop && *stop) return;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const double m = sums[r] / sums[rows];
+  if (mu) mu[r] = m;
+  if (U) U[r] = U[r] + (scale_dev ? *scale_dev : 1.0) * m;
+}
+
+void launch_finalize_mean(const double *sums, int rows, double *mu, double *U, const double *scale_dev,
+                          const int *stop, cudaStream_t s) {
+  finalize_mean_kernel<<<(rows + 127) / 128, 128, 0, s>>>(sums, rows, mu, U, scale_dev, stop);
+}
+
+// ---- G5: centred (weighted) scatter matrix ------------------------------------------------------
+// P[c][i][j] = Σ_{k in chunk c} w_k (X[i][k] − μ_i)(X[j][k] − μ_j) for the lower 32x32 tiles.
+// 16x16 threads, 2x2 outputs per thread, 32-sample slabs staged (centred) in shared memory.
+constexpr int SY_T = 32;
+__global__ void __launch_bounds__(256) syrk_partial_kernel(const double *__restrict__ X, long long ld, int p,
+                                                            int n, const double *__restrict__ w,
+                                                            const double *__restrict__ mu, int chunk,
+                                                            double *__restrict__ P, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double As[SY_T][SY_T + 1], Bs[SY_T][SY_T + 1];
+  // decode lower-triangular tile index
+  int t = blockIdx.x, bi = 0;
+  while (t > bi) t -= bi + 1, ++bi;
+  const int bj = t;
+  const int c = blockIdx.y;
+  const int kbeg = c * chunk, kend = min(n, kbeg + chunk);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += SY_T) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < SY_T * SY_T; e += 256) {
+      const int rr = e >> 5, kk = e & 31, k = k0 + kk;
+      const int ia = bi * SY_T + rr, ib = bj * SY_T + rr;
+      const bool ok = k < kend;
+      const double wk = ok ? (w ? w[k] : 1.0) : 0.0;
+      As[rr][kk] = (ok && ia < p) ? wk * (X[(size_t)ia * ld + k] - mu[ia]) : 0.0;
+      Bs[rr][kk] = (ok && ib < p) ? (X[(size_t)ib * ld + k] - mu[ib]) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < SY_T; ++kk) {
+      const double x0 = As[2 * ty][kk], x1 = As[2 * ty + 1][kk];
+      const double y0 = Bs[2 * tx][kk], y1 = Bs[2 * tx + 1][kk];
+      a00 = fma(x0, y0, a00), a01 = fma(x0, y1, a01);
+      a10 = fma(x1, y0, a10), a11 = fma(x1, y1, a11);
+    }
+  }
+  double *Pc = P + (size_t)c * p * p;
+  const int i0 = bi * SY_T + 2 * ty, j0 = bj * SY_T + 2 * tx;
+  if (i0 < p && j0 < p) Pc[(size_t)i0 * p + j0] = a00;
+  if (i0 < p && j0 + 1 < p) Pc[(size_t)i0 * p + j0 + 1] = a01;
+  if (i0 + 1 < p && j0 < p) Pc[(size_t)(i0 + 1) * p + j0] = a10;
+  if (i0 + 1 < p && j0 + 1 < p) Pc[(size_t)(i0 + 1) * p + j0 + 1] = a11;
+}
+
+int syrk_chunk(int n) {
+  // aim for <= 64 chunks, multiples of 32 samples
+  int chunk = ((n + 63) / 64 + 31) / 32 * 32;
+  return chunk < 32 ? 32 : chunk;
+}
+int syrk_nchunks(int n) {
+  const int ch = syrk_chunk(n);
+  return (n + ch - 1) / ch;
+}
+
+void launch_syrk_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
+                         double *P, const int *stop, cudaStream_t s) {
+  const int nt = (p + SY_T - 1) / SY_T;
+  dim3 grid(nt * (nt + 1) / 2, syrk_nchunks(n));
+  syrk_partial_kernel<<<grid, 256, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop);
+}
+
+// S[i][j] (lower, i >= j) = Σ_c P[c][i][j] in chunk order; raw scatter sums, mirrored to full storage.
+__global__ void scatter_reduce_kernel(const double *__restrict__ P, int nchunks, int p, double *__restrict__ S,
+                                      const int *stop) {
+  if (stop && *stop) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p * p) return;
+  const int i = e / p, j = e % p;
+  if (j > i) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += P[(size_t)c * p * p + e];
+  S[(size_t)i * p + j] = s;
+  S[(size_t)j * p + i] = s;
+}
+
+void launch_scatter_reduce(const double *P, int nchunks, int p, double *S, const int *stop, cudaStream_t s) {
+  scatter_reduce_kernel<<<(p * p + 255) / 256, 256, 0, s>>>(P, nchunks, p, S, stop);
+}
+
+// Σ_{i≠j} Σ_k (z_ki z_kj)² = Σ_k [(Σ_i z_ki²)² − Σ_i z_ki⁴], z = (x − μ)·d  (d_i = 1/sqrt(S_ii/n) for :ss,
+// 1 for :lw). O(n p) instead of a second p x p x n contraction. Sraw = raw scatter sums (S = Sraw/n).
+__global__ void __launch_bounds__(256) shrink_q_partial_kernel(const double *__restrict__ X, long long ld,
+                                                                int p, int n, const double *__restrict__ w,
+                                                                const double *__restrict__ mu,
+                                                                const double *__restrict__ Sraw,
+                                                                const double *cnt_dev, int standardise,
+                                                                double *__restrict__ partial, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[33];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double q = 0.0;
+  if (k < n && (!w || w[k] != 0.0)) {
+    const double cnt = *cnt_dev;  // global number of observations (Σ of ownership weights)
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < p; ++i) {
+      double z = X[(size_t)i * ld + k] - mu[i];
+      if (standardise) z = z * (1.0 / sqrt(Sraw[(size_t)i * p + i] / cnt));
+      const double z2 = z * z;
+      a += z2;
+      b = fma(z2, z2, b);
+    }
+    q = a * a - b;
+  }
+  const double t = block_reduce<0>(q, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
+                             const double *Sraw, const double *cnt_dev, int standardise, double *partial,
+                             const int *stop, cudaStream_t s) {
+  shrink_q_partial_kernel<<<(n + 255) / 256, 256, 0, s>>>(X, ld, p, n, w, mu, Sraw, cnt_dev, standardise, partial,
+                                                          stop);
+}
+
+// Final covariance: Σ′ = shrink(method, Sraw / denom) + ridge·I, written to Sigma (symmetric, so
+// row/column-major coincide). denom = count − corrected where count = *cnt_dev (Σw or n).
+//   :mle          SimpleCovariance()                                           S
+//   :lw / :ss     (1−λ)S + λ diag(S), λ = Σ_{i≠j}Var^(s_ij)/Σ_{i≠j}s_ij² (on correlations for :ss)
+//   :rblw / :oas  (1−λ)S + λ tr(S)/p I, Chen et al. (2010) eq. 17/19 and 23
+// (restated from the published formulas — unpinned, like the oracle.)
+__global__ void __launch_bounds__(1024) cov_finalize_kernel(const double *__restrict__ Sraw, int p,
+                                                             const double *cnt_dev, int corrected, int method,
+                                                             const double *__restrict__ qpart, int nq,
+                                                             double ridge, double *__restrict__ Sigma,
+                                                             double *lambda_out, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[33];
+  const double cnt = *cnt_dev, denom = cnt - (corrected ? 1.0 : 0.0), inv = 1.0 / denom;
+  double lam = 0.0;
+  if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
+    const bool ss = method == MPOPIS_SIGMA_SS;
+    double q = 0.0, r2 = 0.0;
+    for (int c = threadIdx.x; c < nq; c += blockDim.x) q += qpart[c];
+    q = block_reduce<0>(q, red);
+    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+      const int i = e / p, j = e % p;
+      if (i == j) continue;
+      double v = Sraw[e] * inv;
+      if (ss) v = v * (1.0 / sqrt(Sraw[(size_t)i * p + i] * inv)) * (1.0 / sqrt(Sraw[(size_t)j * p + j] * inv));
+      r2 = fma(v, v, r2);
+    }
+    r2 = block_reduce<0>(r2, red);
+    const double n = cnt;
+    const double num = (q - n * r2) * n / ((n - 1.0) * n * n);
+    lam = fmin(fmax(num / r2, 0.0), 1.0);
+  } else if (method == MPOPIS_SIGMA_RBLW || method == MPOPIS_SIGMA_OAS) {
+    double tr = 0.0, tr2 = 0.0;
+    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+      const double v = Sraw[e] * inv;
+      tr2 = fma(v, v, tr2);
+      if (e / p == e % p) tr += v;
+    }
+    tr = block_reduce<0>(tr, red);
+    tr2 = block_reduce<0>(tr2, red);
+    const double n = cnt, pd = (double)p, trsq = tr * tr;
+    if (method == MPOPIS_SIGMA_RBLW) lam = ((n - 2) / n * tr2 + trsq) / ((n + 2) * (tr2 - trsq / pd));
+    else lam = ((1.0 - 2.0 / pd) * tr2 + trsq) / ((n + 1.0 - 2.0 / pd) * (tr2 - trsq / pd));
+    lam = fmin(fmax(lam, 0.0), 1.0);
+    const double F = tr / pd;
+    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+      const bool dg = e / p == e % p;
+      Sigma[e] = (1.0 - lam) * (Sraw[e] * inv) + (dg ? lam * F : 0.0) + (dg ? ridge : 0.0);
+    }
+    if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
+    return;
+  }
+  for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+    const bool dg = e / p == e % p;
+    const double v = Sraw[e] * inv;
+    Sigma[e] = dg ? v + ridge : (1.0 - lam) * v;
+  }
+  if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
+}
+
+void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int corrected, int method,
+                         const double *qpart, int nq, double ridge, double *Sigma, double *lambda_out,
+                         const int *stop, cudaStream_t s) {
+  cov_finalize_kernel<<<1, 1024, 0, s>>>(Sraw, p, cnt_dev, corrected, method, qpart, nq, ridge, Sigma,
+                                         lambda_out, stop);
+}
+
+// ---- G4: elite gather + early-stop test ---------------------------------------------------------
+// X[r][j] = E[r][order[j] − k0] for the elites that live in this shard (k0 <= order[j] < k0 + Kloc);
+// elites owned by other shards contribute zeros (they are summed in by the all-reduce).
+__global__ void gather_cols_kernel(const double *__restrict__ E, long long ldk, int cs, const int *__restrict__ order,
+                                   int m, long long k0, int Kloc, double *__restrict__ X, long long ldx,
+                                   double *__restrict__ mask, const int *stop) {
+  if (stop && *stop) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (j >= m) return;
+  const long long k = (long long)order[j] - k0;
+  const bool own = k >= 0 && k < Kloc;
+  X[(size_t)r * ldx + j] = own ? E[(size_t)r * ldk + k] : 0.0;
+  if (mask && r == 0) mask[j] = own ? 1.0 : 0.0;  // ownership weights for the sharded moments
+}
+
+void launch_gather_cols(const double *E, long long ldk, int cs, const int *order, int m, long long k0, int Kloc,
+                        double *X, long long ldx, double *mask, const int *stop, cudaStream_t s) {
+  dim3 grid((m + 255) / 256, cs);
+  gather_cols_kernel<<<grid, 256, 0, s>>>(E, ldk, cs, order, m, k0, Kloc, X, ldx, mask, stop);
+}
+
+// maximum(abs.(diff(elite_traj_cost))) < 10e-3 -> break (POL:458-461, 566-569). Sets *stop.
+__global__ void __launch_bounds__(1024) elite_stop_kernel(const double *__restrict__ sorted_costs, int m,
+                                                           int enabled, int *stop) {
+  if (*stop) return;
+  __shared__ double red[33];
+  double mx = -CUDART_INF;
+  for (int j = threadIdx.x; j + 1 < m; j += blockDim.x) mx = fmax(mx, fabs(sorted_costs[j + 1] - sorted_costs[j]));
+  mx = block_reduce<2>(mx, red);
+  if (threadIdx.x == 0 && enabled && mx < 10e-3) *stop = 1;
+}
+
+void launch_elite_stop(const double *sorted_costs, int m, int enabled, int *stop, cudaStream_t s) {
+  elite_stop_kernel<<<1, 1024, 0, s>>>(sorted_costs, m, enabled, stop);
+}
+
+__global__ void iter_begin_kernel(const int *stop, int *its) {
+  if (!*stop) *its += 1;
+}
+void launch_iter_begin(const int *stop, int *its, cudaStream_t s) { iter_begin_kernel<<<1, 1, 0, s>>>(stop, its); }
+
+// ---- G10: PMC multinomial resampling -------------------------------------------------------------
+// Categorical(ws) draws by inverse CDF (POL:804-805); E′ = E[:, idxs] (POL:806) enters the moments
+// only through how often each column was drawn, so the gather is replaced by integer counts.
+__global__ void __launch_bounds__(1024) inclusive_scan_kernel(const double *__restrict__ w, int K,
+                                                               double *__restrict__ cdf, const int *stop) {
+  if (stop && *stop) return;
+  // sequential-in-chunks scan: each thread owns a contiguous segment (deterministic order)
+  __shared__ double seg[1024];
+  const int per = (K + blockDim.x - 1) / blockDim.x;
+  const int beg = threadIdx.x * per, end = min(K, beg + per);
+  double s = 0.0;
+  for (int k = beg; k < end; ++k) s += w[k];
+  seg[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+      const double v = seg[t];
+      seg[t] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  double run = seg[threadIdx.x];
+  for (int k = beg; k < end; ++k) {
+    run += w[k];
+    cdf[k] = run;
+  }
+}
+
+__global__ void resample_count_kernel(const double *__restrict__ cdf, int K, const double *__restrict__ u,
+                                      int ndraws, int *__restrict__ counts, const int *stop) {
+  if (stop && *stop) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ndraws) return;
+  const double ui = u[i];
+  int lo = 0, hi = K - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ui < cdf[mid]) hi = mid;
+    else lo = mid + 1;
+  }
+  atomicAdd(counts + lo, 1);
+}
+
+__global__ void counts_to_weights_kernel(const int *__restrict__ counts, long long k0, int Kloc,
+                                         double *__restrict__ w, const int *stop) {
+  if (stop && *stop) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < Kloc) w[k] = (double)counts[k0 + k];
+}
+
+void launch_pmc_counts(const double *wglobal, int K, const double *u, double *cdf, int *counts, long long k0,
+                       int Kloc, double *wloc, const int *stop, cudaStream_t s) {
+  cudaMemsetAsync(counts, 0, sizeof(int) * K, s);
+  inclusive_scan_kernel<<<1, 1024, 0, s>>>(wglobal, K, cdf, stop);
+  resample_count_kernel<<<(K + 255) / 256, 256, 0, s>>>(cdf, K, u, K, counts, stop);
+  counts_to_weights_kernel<<<(Kloc + 255) / 256, 256, 0, s>>>(counts, k0, Kloc, wloc, stop);
+}
+
+// ---- control-cost vector ---------------------------------------------------------------------------
+// b = (γ U_orig') Σ_inv for a caller-supplied Σ_inv (depth-(i) ABI): b[j] = Σ_i γ U_orig[i] Σ_inv[i][j]
+__global__ void ctrl_vec_kernel(const double *__restrict__ Sinv, int cs, const double *__restrict__ U_orig,
+                                double gamma, double *__restrict__ b) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cs) return;
+  double s = 0.0;
+  for (int i = 0; i < cs; ++i) s += (gamma * U_orig[i]) * Sinv[(size_t)j * cs + i];  // col-major, column j
+  b[j] = s;
+}
+void launch_ctrl_vec(const double *Sinv, int cs, const double *U_orig, double gamma, double *b, cudaStream_t s) {
+  ctrl_vec_kernel<<<(cs + 127) / 128, 128, 0, s>>>(Sinv, cs, U_orig, gamma, b);
+}
+
+// ---- final control: weighted_controls, clamp, roll (POL:226-231, UTL:88-101) -------------------------
+// wsum[r] = Σ_k w_k E[r][k] (un-shifted E), wsum[cs] = Σ_k w_k. The reference shifts E by
+// (pol.U − U_orig) before weighting (POL:468): Σ_k w_k (E[r,k] + Δ_r) = wsum[r] + Δ_r Σ_k w_k.
+__global__ void finalize_control_kernel(const double *__restrict__ wsum, const double *__restrict__ U_orig,
+                                        const double *__restrict__ U_cur, int cs, int as, int T,
+                                        double *__restrict__ U_next, double *__restrict__ control) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= cs) return;
+  const double wc = U_orig[r] + (wsum[r] + (U_cur[r] - U_orig[r]) * wsum[cs]);
+  if (r < as) control[r] = fmin(fmax(wc, -1.0), 1.0);  // UTL:91
+  if (T > 1) {
+    if (r >= as) U_next[r - as] = wc;                   // UTL:95
+    if (r >= cs - as) U_next[r] = U_orig[r];            // UTL:96 is a no-op (App. B-2): tail keeps its values
+  } else {
+    U_next[r] = wc;  // UTL:98
+  }
+}
+void launch_finalize_control(const double *wsum, const double *U_orig, const double *U_cur, int cs, int as, int T,
+                             double *U_next, double *control, cudaStream_t s) {
+  finalize_control_kernel<<<(cs + 127) / 128, 128, 0, s>>>(wsum, U_orig, U_cur, cs, as, T, U_next, control);
+}
+
+}  // namespace mpopis
