@@ -179,6 +179,8 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
  * (MountainCar only; NULL allowed). */
 int mpopis_b200_env_step(mpopis_t *h, double *state_inout, const double *action, int64_t *env_t_inout,
                          double *reward_out, uint8_t *done_out);
+/* order = sortperm(costs) (POL:455, 563): stable ascending permutation, 0-based. Integer parity surface. */
+int mpopis_b200_sortperm(mpopis_t *h, const double *costs, int64_t K, int64_t *perm_out);
 /* reward(env) of the current state without stepping (CAR:201-213, MCR:145-158, EXM:10-22; `done` is
  * env.done, used by the MountainCar reward only). */
 int mpopis_b200_env_reward(mpopis_t *h, const double *state, uint8_t done, double *reward_out);
@@ -208,6 +210,12 @@ int mpopis_b200_resident_reset(mpopis_t *h, const double *state, int64_t env_t, 
 int mpopis_b200_resident_plan(mpopis_t *h, int32_t advance_env);
 int mpopis_b200_resident_read(mpopis_t *h, double *state_out, double *U_out, double *control_out,
                               int32_t *its_run_out);
+
+/* AIS iterations executed since resident_reset() (summed over resident_plan() calls). */
+int mpopis_b200_resident_total_its(mpopis_t *h, int64_t *total_its_out);
+/* Measured FP64 FMA issue rate of the device (thread-level DFMA/s, dependent-chain micro-benchmark):
+ * the roofline denominator of the FP64-bound rollout kernel, which MEASURED_PEAKS.json lacks. */
+int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out);
 
 /* Timing/introspection: kernels launched by this handle so far, device milliseconds spent in the
  * rollout kernel during the last plan (CUDA events on the handle's stream), the handle's

@@ -129,6 +129,24 @@ int launch_inv_sqrt(const double *A, int n, double *Cout, double *ws, int *info,
   return (int)cudaLaunchCooperativeKernel((const void *)inv_sqrt_ns_kernel, dim3(grid), dim3(256), args, 0, s);
 }
 
+// ---- FP64 pipe roofline denominator ------------------------------------------------------------
+// The rollout kernel is bound by FP64 instruction issue, and MEASURED_PEAKS.json has no FP64 figure,
+// so bench.py measures it in the same run: 8 independent DFMA chains per thread, all SMs busy.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// returns DFMA thread-instructions launched; out must hold grid*256 doubles
+long long launch_dfma_peak(double *out, int grid, int iters, cudaStream_t s) {
+  dfma_peak_kernel<<<grid, 256, 0, s>>>(out, iters, 0.999999, 1e-9);
+  return (long long)grid * 256 * iters * 8;
+}
+
 // d_ii = elite_E[order[ii]] for ii < K: `order[ii]` is used as a LINEAR index into the cs x m elite
 // matrix (SURVEY App. B-1 — the reference's "rank-μ" term is a scalar). Columns of X not owned by
 // this shard hold zeros and are summed in by the all-reduce.

@@ -91,7 +91,7 @@ void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int c
 void launch_gather_cols(const double *E, long long ldk, int cs, const int *order, int m, long long k0, int Kloc,
                         double *X, long long ldx, double *mask, const int *stop, cudaStream_t s);
 void launch_elite_stop(const double *sorted_costs, int m, int enabled, int *stop, cudaStream_t s);
-void launch_iter_begin(const int *stop, int *its, cudaStream_t s);
+void launch_iter_begin(const int *stop, int *its, int *total_its, cudaStream_t s);
 void launch_pmc_counts(const double *wglobal, int K, const double *u, double *cdf, int *counts, long long k0,
                        int Kloc, double *wloc, const int *stop, cudaStream_t s);
 void launch_ctrl_vec(const double *Sinv, int cs, const double *U_orig, double gamma, double *b, cudaStream_t s);
@@ -104,6 +104,7 @@ void launch_chol_solve(const double *Lt, int n, const double *u, double gamma, d
                        cudaStream_t s);
 void launch_transpose_sq(const double *in, double *out, int n, cudaStream_t s);
 // cma.cu
+long long launch_dfma_peak(double *out, int grid, int iters, cudaStream_t s);
 int inv_sqrt_max_ctas(int num_sms);
 int launch_inv_sqrt(const double *A, int n, double *Cout, double *ws, int *info, int tag, const int *stop,
                     int max_ctas, cudaStream_t s);  // returns a cudaError_t

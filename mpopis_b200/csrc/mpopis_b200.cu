@@ -231,7 +231,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   int bs = h->sigma_bs;
   const double *bvec = nullptr;
   for (int n = 0; n < N; ++n) {
-    launch_iter_begin(stop, h->its(), st);
+    launch_iter_begin(stop, h->its(), h->d_flags + 3, st);
     h->launches += 1;
     // --- proposal factor L of Σ′ (POL:447; CMA samples from σ²Σ, POL:550-554) ---
     const bool cma_scaled = pol == MPOPIS_POLICY_CMAMPPI && N > 1;
@@ -787,6 +787,31 @@ int mpopis_b200_weights(mpopis_t *h, const double *costs, int64_t K, double lamb
   return 0;
 }
 
+int mpopis_b200_sortperm(mpopis_t *h, const double *costs, int64_t K, int64_t *perm_out) {
+  if (!h || !costs || !perm_out || K < 1 || K > (1LL << 30)) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (int rc = set_device(h)) return rc;
+  double *dc = nullptr, *ds = nullptr;
+  unsigned long long *ka = nullptr, *kb = nullptr;
+  int *ord = nullptr, *vb = nullptr, *hist = nullptr;
+  if (int rc = dalloc(&dc, (size_t)K)) return rc;
+  if (int rc = dalloc(&ds, (size_t)K)) return rc;
+  if (int rc = dalloc(&ka, (size_t)K)) return rc;
+  if (int rc = dalloc(&kb, (size_t)K)) return rc;
+  if (int rc = dalloc(&ord, (size_t)K)) return rc;
+  if (int rc = dalloc(&vb, (size_t)K)) return rc;
+  if (int rc = dalloc(&hist, sort_hist_ints((int)K))) return rc;
+  CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
+  launch_sortperm(dc, (int)K, (int)K, ka, kb, ord, vb, hist, ds, nullptr, h->st);
+  h->launches += 26;
+  std::vector<int> tmp((size_t)K);
+  CU(cudaMemcpyAsync(tmp.data(), ord, sizeof(int) * K, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  for (int64_t i = 0; i < K; ++i) perm_out[i] = tmp[(size_t)i];
+  cudaFree(dc), cudaFree(ds), cudaFree(ka), cudaFree(kb), cudaFree(ord), cudaFree(vb), cudaFree(hist);
+  return 0;
+}
+
 int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *idx_out, int32_t *idx2_out,
                             double *dist_out, uint8_t *within_out) {
   if (!h || !pos || n < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
@@ -961,7 +986,7 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
 int mpopis_b200_resident_reset(mpopis_t *h, const double *state, int64_t env_t, const double *U) {
   if (!h || !state || !U) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (int rc = set_device(h)) return rc;
-  CU(cudaMemsetAsync(h->info(), 0, sizeof(int), h->st));
+  CU(cudaMemsetAsync(h->info(), 0, sizeof(int) * 2, h->st));  // info + accumulated iteration count
   if (int rc = upload_inputs(h, state, env_t, U)) return rc;
   CU(cudaStreamSynchronize(h->st));
   return 0;
@@ -981,6 +1006,45 @@ int mpopis_b200_resident_read(mpopis_t *h, double *state_out, double *U_out, dou
   if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (int rc = set_device(h)) return rc;
   return download_outputs(h, U_out, control_out, its_run_out, state_out ? state_out : nullptr);
+}
+
+int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out) {
+  if (!h || !dfma_per_s_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->dev));
+  const int grid = prop.multiProcessorCount * 8;  // 2048 threads / SM
+  double *out = nullptr;
+  if (int rc = dalloc(&out, (size_t)grid * 256)) return rc;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  launch_dfma_peak(out, grid, 2000, h->st);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0, h->st));
+    const long long n = launch_dfma_peak(out, grid, 20000, h->st);
+    CU(cudaEventRecord(e1, h->st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double rate = (double)n / (ms * 1e-3);
+    if (rate > best) best = rate;
+  }
+  h->launches += 6;
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(out);
+  *dfma_per_s_out = best;
+  return 0;
+}
+
+int mpopis_b200_resident_total_its(mpopis_t *h, int64_t *total_its_out) {
+  if (!h || !total_its_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  int v = 0;
+  CU(cudaMemcpyAsync(&v, h->d_flags + 3, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  *total_its_out = v;
+  return 0;
 }
 
 int64_t mpopis_b200_launch_count(mpopis_t *h) { return h ? h->launches : 0; }

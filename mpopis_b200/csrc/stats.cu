@@ -367,10 +367,12 @@ void launch_elite_stop(const double *sorted_costs, int m, int enabled, int *stop
   elite_stop_kernel<<<1, 1024, 0, s>>>(sorted_costs, m, enabled, stop);
 }
 
-__global__ void iter_begin_kernel(const int *stop, int *its) {
-  if (!*stop) *its += 1;
+__global__ void iter_begin_kernel(const int *stop, int *its, int *total_its) {
+  if (!*stop) *its += 1, *total_its += 1;
 }
-void launch_iter_begin(const int *stop, int *its, cudaStream_t s) { iter_begin_kernel<<<1, 1, 0, s>>>(stop, its); }
+void launch_iter_begin(const int *stop, int *its, int *total_its, cudaStream_t s) {
+  iter_begin_kernel<<<1, 1, 0, s>>>(stop, its, total_its);
+}
 
 // ---- G10: PMC multinomial resampling -------------------------------------------------------------
 // Categorical(ws) draws by inverse CDF (POL:804-805); E′ = E[:, idxs] (POL:806) enters the moments

@@ -235,6 +235,22 @@ class Engine:
         self._chk(self.b.resident_read(self.h, _d(s), _d(u), _d(c), C.byref(its)))
         return s, u, c, its.value
 
+    def resident_total_its(self) -> int:
+        v = C.c_int64(0)
+        self._chk(self.b.resident_total_its(self.h, C.byref(v)))
+        return v.value
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        self._chk(self.b.measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    def sortperm(self, costs):
+        c = _f64(costs)
+        out = np.zeros(c.size, dtype=np.int64)
+        self._chk(self.b.sortperm(self.h, _d(c), c.size, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     def comm_init(self, nccl_id: bytes):
         buf = C.create_string_buffer(nccl_id, 128)
         self._chk(self.b.comm_init(self.h, buf))

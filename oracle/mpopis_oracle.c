@@ -425,13 +425,20 @@ static void compute_weights(const double *costs, int64_t K, double lambda, doubl
 }
 
 /* stable ascending arg-sort (Julia sortperm: merge sort, ties keep index order), POL:455,563 */
+/* Base.isless for Float64: total order with -0.0 < +0.0 and NaN last (sortperm's default lt). */
+static int jl_isless(double a, double b) {
+  if (isnan(a)) return 0;
+  if (isnan(b)) return 1;
+  if (a < b) return 1;
+  return a == b && signbit(a) && !signbit(b);
+}
 static void msort(const double *x, int64_t *a, int64_t *tmp, int64_t n) {
   if (n < 2) return;
   int64_t h = n / 2;
   msort(x, a, tmp, h);
   msort(x, a + h, tmp, n - h);
   int64_t i = 0, j = h, o = 0;
-  while (i < h && j < n) tmp[o++] = (x[a[j]] < x[a[i]]) ? a[j++] : a[i++];
+  while (i < h && j < n) tmp[o++] = jl_isless(x[a[j]], x[a[i]]) ? a[j++] : a[i++];
   while (i < h) tmp[o++] = a[i++];
   while (j < n) tmp[o++] = a[j++];
   memcpy(a, tmp, sizeof(int64_t) * n);
