@@ -26,6 +26,11 @@ struct CarEnvArgs {
   int n_cars;
   int n_trk;
   const double *trk;  // device: x[n_trk], y[n_trk], w[n_trk]
+  // exact nearest-point pruning table (rollout.cu within_track<true>): lut_nx x lut_ny cells of
+  // 1/lut_inv_c metres starting at (lut_x0, lut_y0); nullptr disables it
+  const uint4 *lut;
+  double lut_x0, lut_y0, lut_inv_c;
+  int lut_nx, lut_ny;
 };
 
 struct McEnvArgs {  // RLEnvs MountainCarEnv params
@@ -53,7 +58,7 @@ void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant
                         cudaStream_t s);
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
-                        unsigned char *within, cudaStream_t s);
+                        unsigned char *within, int use_lut, cudaStream_t s);
 void launch_env_step_car(const CarEnvArgs &env, double *state, const double *action, long long *env_t,
                          double *reward, int variant, cudaStream_t s);
 void launch_env_step_mc(const McEnvArgs &env, double *state, const double *action, long long *env_t,
@@ -71,7 +76,9 @@ void launch_transpose_in(const double *colmajor, double *dev, int cs, int K, lon
 void launch_transpose_out(const double *dev, double *colmajor, int cs, int K, long long ldk, const double *shift_a,
                           const double *shift_b, cudaStream_t s);
 // stats.cu
-void launch_weights(const double *costs, int K, double lambda, double *w, const int *stop, cudaStream_t s);
+// returns the number of kernels launched; scratch: 512 doubles (nullptr forces the single-CTA kernel)
+int launch_weights(const double *costs, int K, double lambda, double *w, double *scratch, const int *stop,
+                   cudaStream_t s);
 int rowsum_nchunks(int n);
 void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
                            const int *stop, cudaStream_t s);
@@ -82,6 +89,7 @@ int syrk_nchunks(int n);
 void launch_syrk_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu, double *P,
                          const int *stop, cudaStream_t s);
 void launch_scatter_reduce(const double *P, int nchunks, int p, double *S, const int *stop, cudaStream_t s);
+int shrink_q_nblocks(int n);
 void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
                              const double *Sraw, const double *cnt_dev, int standardise, double *partial,
                              const int *stop, cudaStream_t s);
@@ -114,9 +122,8 @@ void launch_cma_vec(const double *dw, const double *C, const double *dvec, const
                     int n_iter, const mpopis_cma_t &c, double *psig, double *pSig, double *sigma_dev, double *U,
                     double *Sigma, const int *stop, cudaStream_t s);
 // sort.cu
-int sort_nblocks(int K);
-size_t sort_hist_ints(int K);
+int sort_launches(int K);
 void launch_sortperm(const double *costs, int K, int m, unsigned long long *keys_a, unsigned long long *keys_b,
-                     int *order, int *vals_b, int *hist, double *sorted_costs, const int *stop, cudaStream_t s);
+                     int *order, int *vals_b, double *sorted_costs, const int *stop, cudaStream_t s);
 
 }  // namespace mpopis

@@ -19,51 +19,58 @@ __global__ void __launch_bounds__(1024) chol_kernel(const double *__restrict__ A
                                                      int use_smem, int *info, int tag, const int *stop) {
   if (stop && *stop) return;
   extern __shared__ double Wsm[];
-  __shared__ int bad;
   double *W = use_smem ? Wsm : Wglobal;
+  const int ldw = n | 1;  // odd row pitch: the column reads W[k][j] (k across lanes) are bank-conflict free
   const double sc = sigma_dev ? (*sigma_dev) * (*sigma_dev) : 1.0;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) W[e] = sigma_dev ? sc * A[e] : A[e];
-  if (threadIdx.x == 0) bad = 0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x)
+    W[(size_t)(e / n) * ldw + e % n] = sigma_dev ? sc * A[e] : A[e];
+  // Square-root-free right-looking elimination with ONE barrier per column: column j is left unscaled
+  // (W[i][j] = l_ij * l_jj) and the trailing update divides by the pivot d_j = l_jj², so there is no
+  // separate scaling phase; L is formed at the end as W[i][j] / sqrt(d_j). Threads form a 32 x 32 grid
+  // over (row, column) of the trailing block — no integer divisions in the loop.
   __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  bool failed = false;
   for (int j = 0; j < n; ++j) {
-    if (threadIdx.x == 0) {
-      const double d = W[(size_t)j * n + j];
-      if (!(d > 0.0)) bad = 1;
-      else W[(size_t)j * n + j] = sqrt(d);
+    const double d = W[(size_t)j * ldw + j];  // final after the barrier that ended step j-1
+    if (!(d > 0.0)) {                         // uniform: every thread reads the same value
+      failed = true;
+      break;
     }
-    __syncthreads();
-    if (bad) break;
-    const double ljj = W[(size_t)j * n + j];
-    for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) W[(size_t)i * n + j] = W[(size_t)i * n + j] / ljj;
-    __syncthreads();
-    const int rem = n - j - 1;
-    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-      if (k <= i) W[(size_t)i * n + k] -= W[(size_t)i * n + j] * W[(size_t)k * n + j];
+    const double inv_d = 1.0 / d;
+    for (int i = j + 1 + ty; i < n; i += 32) {
+      const double wij = W[(size_t)i * ldw + j] * inv_d;
+      for (int k = j + 1 + tx; k <= i; k += 32) W[(size_t)i * ldw + k] -= wij * W[(size_t)k * ldw + j];
     }
     __syncthreads();
   }
-  if (bad) {
+  if (failed) {
     if (threadIdx.x == 0) atomicCAS(info, 0, tag);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, k = e % n;
-    Lt[e] = k <= i ? W[e] : 0.0;
+    double v = 0.0;
+    if (k <= i) {
+      const double r = sqrt(W[(size_t)k * ldw + k]);
+      v = k == i ? r : W[(size_t)i * ldw + k] / r;
+    }
+    Lt[e] = v;
   }
 }
 
-constexpr int CHOL_SMEM_N = 160;  // 160² · 8 B = 200 KB
+constexpr int CHOL_SMEM_N = 160;  // 160 · 161 · 8 B = 201 KB
 
+// Wglobal: scratch of n (n|1) doubles, used when n > CHOL_SMEM_N
 void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, double *Wglobal, int *info, int tag,
                  const int *stop, cudaStream_t s) {
   const int use_smem = n <= CHOL_SMEM_N;
-  const size_t smem = use_smem ? sizeof(double) * n * n : 0;
+  const size_t smem = use_smem ? sizeof(double) * n * (n | 1) : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(double) * CHOL_SMEM_N * CHOL_SMEM_N));
+                         (int)(sizeof(double) * CHOL_SMEM_N * (CHOL_SMEM_N | 1)));
     attr_set = true;
   }
   chol_kernel<<<1, 1024, smem, s>>>(A, n, sigma_dev, Lt, Wglobal, use_smem, info, tag, stop);

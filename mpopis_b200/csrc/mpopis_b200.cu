@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -112,6 +113,7 @@ struct mpopis_handle {
   unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
   int *d_order = nullptr, *d_vals_b = nullptr, *d_hist = nullptr, *d_counts = nullptr, *d_flags = nullptr;
   unsigned char *d_done = nullptr;
+  uint4 *d_lut = nullptr;
   size_t part_doubles = 0;
   // d_flags: [0] stop, [1] its, [2] info
   int *stop() { return d_flags; }
@@ -171,7 +173,7 @@ int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, 
   if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs)) return rc;
   int nq = 0;
   if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
-    const int nb = (n + 255) / 256;
+    const int nb = shrink_q_nblocks(n);
     launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS,
                             h->d_qpart, stop, h->st);
     launch_reduce_partials(h->d_qpart, nb, 1, h->d_q, stop, h->st);
@@ -269,8 +271,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       case MPOPIS_POLICY_MUAISMPPI:
       case MPOPIS_POLICY_MUSIGMAAISMPPI: {  // POL:361-365, 659-663, 729-734
         const double lam = pol == MPOPIS_POLICY_IMPPI ? h->cfg.lambda : h->cfg.lambda_ais;
-        launch_weights(h->d_costs, K, lam, h->d_w, stop, st);
-        h->launches += 1;
+        h->launches += launch_weights(h->d_costs, K, lam, h->d_w, h->d_ones, stop, st);
         const bool cov = pol == MPOPIS_POLICY_MUSIGMAAISMPPI;
         if (int rc = moments(h, h->d_E, h->ldk, Kloc, h->d_w + h->k0, cov, 0, MPOPIS_SIGMA_MLE, 10e-9, true,
                              nullptr, h->d_Sigma))
@@ -278,7 +279,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
         break;
       }
       case MPOPIS_POLICY_PMCMPPI: {  // POL:802-809
-        launch_weights(h->d_costs, K, h->cfg.lambda_ais, h->d_w, stop, st);
+        h->launches += launch_weights(h->d_costs, K, h->cfg.lambda_ais, h->d_w, h->d_ones, stop, st) - 1;
         if (u_host) CU(cudaMemcpyAsync(h->d_u, u_host + (size_t)n * K, sizeof(double) * K, cudaMemcpyHostToDevice, st));
         else launch_philox_uniforms(h->d_u, K, h->seed, (uint32_t)h->step, (uint32_t)n, stop, st);
         launch_pmc_counts(h->d_w, K, h->d_u, h->d_cdf, h->d_counts, h->k0, Kloc, h->d_wcnt, stop, st);
@@ -291,12 +292,12 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       case MPOPIS_POLICY_CEMPPI:
       case MPOPIS_POLICY_CMAMPPI: {  // POL:455-465, 563-599
         const int m = h->m_elite;
-        launch_sortperm(h->d_costs, K, m, h->d_keys_a, h->d_keys_b, h->d_order, h->d_vals_b, h->d_hist,
+        launch_sortperm(h->d_costs, K, m, h->d_keys_a, h->d_keys_b, h->d_order, h->d_vals_b,
                         h->d_sorted, stop, st);
         launch_elite_stop(h->d_sorted, m, h->cfg.early_stop, stop, st);
         launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, m, h->k0, Kloc, h->d_X, h->ldm,
                            h->world > 1 ? h->d_mask : nullptr, stop, st);
-        h->launches += 29;
+        h->launches += 2 + sort_launches(K);
         if (pol == MPOPIS_POLICY_CEMPPI) {
           if (int rc = moments(h, h->d_X, h->ldm, m, h->world > 1 ? h->d_mask : nullptr, true, 0,
                                h->cfg.sigma_est, 10e-9, true, nullptr, h->d_Sigma))
@@ -311,10 +312,10 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   }
   h->last_its_launched = N;
   // --- final weights (always λ: POL:313,367,470,604,665,736,811), weighted noise, control, roll ---
-  launch_weights(h->d_costs, K, h->cfg.lambda, h->d_w, nullptr, st);
+  h->launches += launch_weights(h->d_costs, K, h->cfg.lambda, h->d_w, h->d_ones, nullptr, st);
   launch_rowsum_partial(h->d_E, h->ldk, cs, Kloc, h->d_w + h->k0, h->d_part, nullptr, st);
   launch_reduce_partials(h->d_part, rowsum_nchunks(Kloc), cs + 1, h->d_sums, nullptr, st);
-  h->launches += 3;
+  h->launches += 2;
   if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
   launch_finalize_control(h->d_sums, h->d_U_orig, h->d_U_cur, cs, h->as, h->T, h->d_U_next, h->d_control, st);
   h->launches += 1;
@@ -363,6 +364,52 @@ int cma_update(mpopis_t *h, int n_iter) {
                  h->d_U_cur, h->d_Sigma, stop, h->st);
   h->launches += 5;
   return 0;
+}
+
+// Exact pruning table for the arg-min of within_track (TRK:71-73). For every cell of a uniform grid over
+// the track's bounding box (+ margin) it lists the sampled points that can be nearest to SOME position in
+// the cell: point i is kept iff  dmin(cell, p_i) <= min_j dmax(cell, p_j)  (with slack for rounding and for
+// positions that the kernel's own cell-index arithmetic puts one ulp across a cell edge). The true arg-min
+// always satisfies that inequality, so scanning the candidates in index order with the reference's
+// arithmetic returns the same index as the full scan. Cells with more than 7 candidates (or positions
+// outside the table) fall back to the full scan. Layout per cell: 8 x u16 = {count, idx0..idx6}.
+void build_track_lut(const double *x, const double *y, const double *w, int n, std::vector<uint16_t> &cells,
+                     double &x0, double &y0, double &cell, int &nx, int &ny) {
+  double xmin = x[0], xmax = x[0], ymin = y[0], ymax = y[0], wmax = w[0];
+  for (int i = 1; i < n; ++i) {
+    xmin = std::min(xmin, x[i]), xmax = std::max(xmax, x[i]);
+    ymin = std::min(ymin, y[i]), ymax = std::max(ymax, y[i]);
+    wmax = std::max(wmax, w[i]);
+  }
+  const double margin = wmax + 40.0;
+  cell = 2.0;
+  x0 = xmin - margin, y0 = ymin - margin;
+  const double wx = xmax + margin - x0, wy = ymax + margin - y0;
+  while ((wx / cell) * (wy / cell) > 4.0e6 || (wx / cell) * (wy / cell) * n > 4.0e8) cell *= 2.0;
+  nx = (int)std::ceil(wx / cell), ny = (int)std::ceil(wy / cell);
+  cells.assign((size_t)nx * ny * 8, 0);
+  const double hh = 0.5 * cell * (1.0 + 1e-9) + 1e-6;
+  std::vector<double> dmin(n);
+  for (int iy = 0; iy < ny; ++iy)
+    for (int ix = 0; ix < nx; ++ix) {
+      const double cx = x0 + (ix + 0.5) * cell, cy = y0 + (iy + 0.5) * cell;
+      double bound = INFINITY;
+      for (int j = 0; j < n; ++j) {
+        const double ax = std::fabs(cx - x[j]), ay = std::fabs(cy - y[j]);
+        const double fx = ax + hh, fy = ay + hh, nxm = std::max(ax - hh, 0.0), nym = std::max(ay - hh, 0.0);
+        bound = std::min(bound, std::sqrt(fx * fx + fy * fy));
+        dmin[j] = std::sqrt(nxm * nxm + nym * nym);
+      }
+      bound = bound * (1.0 + 1e-9) + 1e-9;
+      uint16_t *c = &cells[((size_t)iy * nx + ix) * 8];
+      int cnt = 0;
+      for (int j = 0; j < n && cnt <= 7; ++j)
+        if (dmin[j] <= bound) {
+          if (cnt < 7) c[1 + cnt] = (uint16_t)j;
+          ++cnt;
+        }
+      c[0] = cnt <= 7 ? (uint16_t)cnt : (uint16_t)0xFFFF;
+    }
 }
 
 int ensure_elite_capacity(mpopis_t *h, int m) {
@@ -488,7 +535,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_Sigma, cs * cs));
   TRY(dalloc(&h->d_Lt, cs * cs));
   TRY(dalloc(&h->d_Lt0, cs * cs));
-  TRY(dalloc(&h->d_cholW, cs * cs));
+  TRY(dalloc(&h->d_cholW, cs * (cs + 1)));
   TRY(dalloc(&h->d_bvec, cs));
   TRY(dalloc(&h->d_Z, cs * ld));
   TRY(dalloc(&h->d_E, cs * ld));
@@ -500,7 +547,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_keys_b, K));
   TRY(dalloc(&h->d_order, K));
   TRY(dalloc(&h->d_vals_b, K));
-  TRY(dalloc(&h->d_hist, sort_hist_ints((int)K)));
+  TRY(dalloc(&h->d_hist, 1));
   TRY(dalloc(&h->d_flags, 4));
   TRY(dalloc(&h->d_sums, cs + 1));
   TRY(dalloc(&h->d_mu, cs));
@@ -508,12 +555,13 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_P, (size_t)66 * cs * cs));
   TRY(dalloc(&h->d_q, 1));
   TRY(dalloc(&h->d_lambda, 1));
+  TRY(dalloc(&h->d_ones, 512));  // scratch of the multi-CTA weights kernels
   TRY(dalloc(&h->d_reward, 1));
   TRY(dalloc(&h->d_done, 1));
   const size_t nmax = K;  // moments may run over Kloc samples or up to K elites
   h->part_doubles = (size_t)(rowsum_nchunks((int)nmax) + 1) * (cs + 1);
   TRY(dalloc(&h->d_part, h->part_doubles));
-  TRY(dalloc(&h->d_qpart, (nmax + 255) / 256 + 1));
+  TRY(dalloc(&h->d_qpart, (size_t)shrink_q_nblocks((int)nmax) + 1));
   if (cfg->policy == MPOPIS_POLICY_CEMPPI) TRY(ensure_elite_capacity(h, h->m_elite));
   if (cfg->policy == MPOPIS_POLICY_PMCMPPI || cfg->policy == MPOPIS_POLICY_CMAMPPI) {
     TRY(dalloc(&h->d_u, K));
@@ -560,7 +608,8 @@ int mpopis_b200_destroy(mpopis_t *h) {
                   h->d_sums,   h->d_mu,    h->d_P,      h->d_Sraw,   h->d_qpart,  h->d_q,       h->d_lambda,
                   h->d_traj,   h->d_u,     h->d_cdf,    h->d_wcnt,   h->d_ws,     h->d_sigma,   h->d_psig,
                   h->d_pSig,   h->d_C,     h->d_ns,     h->d_reward, h->d_env_t,  h->d_keys_a,  h->d_keys_b,
-                  h->d_order,  h->d_vals_b, h->d_hist,  h->d_counts, h->d_flags,  h->d_done};
+                  h->d_order,  h->d_vals_b, h->d_hist,  h->d_counts, h->d_flags,  h->d_done,   h->d_lut,
+                  h->d_ones};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->h_in) cudaFreeHost(h->h_in);
@@ -615,6 +664,17 @@ int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params, d
   CU(cudaMemcpy(h->d_trk + n_trk, trk_y, sizeof(double) * n_trk, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_trk + 2 * n_trk, trk_w, sizeof(double) * n_trk, cudaMemcpyHostToDevice));
   h->car.trk = h->d_trk;
+  {  // exact nearest-point pruning table for the fast rollout variant
+    std::vector<uint16_t> cells;
+    double x0, y0, cell;
+    int nx, ny;
+    build_track_lut(trk_x, trk_y, trk_w, (int)n_trk, cells, x0, y0, cell, nx, ny);
+    if (h->d_lut) cudaFree(h->d_lut), h->d_lut = nullptr;
+    CU(cudaMalloc((void **)&h->d_lut, cells.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(h->d_lut, cells.data(), cells.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    h->car.lut = h->d_lut, h->car.lut_x0 = x0, h->car.lut_y0 = y0, h->car.lut_inv_c = 1.0 / cell;
+    h->car.lut_nx = nx, h->car.lut_ny = ny;
+  }
   h->env_set = true;
   return 0;
 }
@@ -680,7 +740,10 @@ int mpopis_b200_seed(mpopis_t *h, uint64_t seed) {
 
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
   if (!h || !key) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
-  if (!strcmp(key, "rollout_variant")) h->rollout_variant = value != 0.0;
+  if (!strcmp(key, "rollout_variant")) {
+    if (value != 0.0 && value != 1.0 && value != 2.0) return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1 or 2");
+    h->rollout_variant = (int)value;
+  }
   else if (!strcmp(key, "rollout_block")) {
     const int b = (int)value;
     if (b < 32 || b > 128 || b % 32) return fail(MPOPIS_ERR_BAD_ARG, "rollout_block must be 32, 64, 96 or 128");
@@ -779,8 +842,7 @@ int mpopis_b200_weights(mpopis_t *h, const double *costs, int64_t K, double lamb
   if (int rc = dalloc(&dc, (size_t)K)) return rc;
   if (int rc = dalloc(&dw, (size_t)K)) return rc;
   CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
-  launch_weights(dc, (int)K, lambda, dw, nullptr, h->st);
-  h->launches += 1;
+  h->launches += launch_weights(dc, (int)K, lambda, dw, h->d_ones, nullptr, h->st);
   CU(cudaMemcpyAsync(w_out, dw, sizeof(double) * K, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   cudaFree(dc), cudaFree(dw);
@@ -799,10 +861,10 @@ int mpopis_b200_sortperm(mpopis_t *h, const double *costs, int64_t K, int64_t *p
   if (int rc = dalloc(&kb, (size_t)K)) return rc;
   if (int rc = dalloc(&ord, (size_t)K)) return rc;
   if (int rc = dalloc(&vb, (size_t)K)) return rc;
-  if (int rc = dalloc(&hist, sort_hist_ints((int)K))) return rc;
+  if (int rc = dalloc(&hist, 1)) return rc;
   CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
-  launch_sortperm(dc, (int)K, (int)K, ka, kb, ord, vb, hist, ds, nullptr, h->st);
-  h->launches += 26;
+  launch_sortperm(dc, (int)K, (int)K, ka, kb, ord, vb, ds, nullptr, h->st);
+  h->launches += sort_launches((int)K);
   std::vector<int> tmp((size_t)K);
   CU(cudaMemcpyAsync(tmp.data(), ord, sizeof(int) * K, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
@@ -826,7 +888,7 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
   if (int rc = dalloc(&dj, (size_t)n)) return rc;
   if (int rc = dalloc(&dw, (size_t)n)) return rc;
   CU(cudaMemcpyAsync(dp, pos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->st));
-  launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->st);
+  launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->rollout_variant == 0, h->st);
   h->launches += 1;
   if (idx_out) CU(cudaMemcpyAsync(idx_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));
   if (idx2_out) CU(cudaMemcpyAsync(idx2_out, dj, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));
@@ -945,7 +1007,7 @@ int mpopis_b200_cholesky(mpopis_t *h, const double *A, int64_t n, double *L_out)
   const size_t nn = (size_t)n * n;
   if (int rc = dalloc(&dA, nn)) return rc;
   if (int rc = dalloc(&dLt, nn)) return rc;
-  if (int rc = dalloc(&dW, nn)) return rc;
+  if (int rc = dalloc(&dW, nn + (size_t)n)) return rc;
   if (int rc = dalloc(&dinfo, 1)) return rc;
   CU(cudaMemcpyAsync(dA, A, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
   launch_chol(dA, (int)n, nullptr, dLt, dW, dinfo, 1, nullptr, h->st);

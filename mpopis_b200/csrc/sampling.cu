@@ -85,47 +85,66 @@ __global__ void __launch_bounds__(256) apply_L_block_kernel(const double *Lt, in
   E[(size_t)r * ldk + k] = acc;
 }
 
-// Dense lower-triangular E = L Z. CTA = 64 samples x 4 row-groups; it owns a 32-row block of E
-// (8 rows per thread) and walks j in chunks of 32 rows of Z staged in shared memory. L is read
-// through the row-major copy Lt with warp-uniform (broadcast) 16-byte loads.
-constexpr int AL_KT = 64, AL_RB = 32, AL_JC = 32;
+// Dense lower-triangular E = L Z as a register-tiled FP64 GEMM: CTA tile = 32 rows x 128 samples,
+// 256 threads as 8 (row groups) x 32 (sample groups), 4 x 4 outputs per thread; j is walked in slabs of
+// 16 staged in shared memory (L slab transposed so a thread's 4 rows are one 32-byte read, broadcast
+// across the 32 lanes of a warp; Z slab read as 32-byte vectors). Row tile b only needs j < 32(b+1)
+// (Lt carries explicit zeros above the diagonal), so the triangle costs ~half a square GEMM.
+// FP64 has no tcgen05 kind and DMMA (mma.sync m8n8k4) has the same peak as the DFMA pipe on B200, so
+// this stays on the FMA pipe.
+constexpr int AL_BM = 32, AL_BN = 128, AL_BJ = 16;
 __global__ void __launch_bounds__(256) apply_L_dense_kernel(const double *__restrict__ Lt, int cs,
                                                              const double *__restrict__ Z,
                                                              double *__restrict__ E, long long ldk, int K,
                                                              const int *stop) {
   if (stop && *stop) return;
-  __shared__ double Zs[AL_JC][AL_KT];
-  const int tx = threadIdx.x & (AL_KT - 1), ty = threadIdx.x / AL_KT;  // ty in 0..3
-  const int kbase = blockIdx.x * AL_KT, i0 = blockIdx.y * AL_RB;
-  const int k = kbase + tx;
-  double acc[8];
+  __shared__ __align__(16) double Ls[AL_BJ][AL_BM];  // Ls[j][i]
+  __shared__ __align__(16) double Zs[AL_BJ][AL_BN];  // Zs[j][k]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty: 0..7
+  const int kbase = blockIdx.x * AL_BN, i0 = blockIdx.y * AL_BM;
+  double acc[4][4];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-  const int jend = min(i0 + AL_RB, cs);  // rows of this block need j < jend
-  for (int jc = 0; jc < jend; jc += AL_JC) {
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  const int jend = min(i0 + AL_BM, cs);
+  for (int jc = 0; jc < jend; jc += AL_BJ) {
     __syncthreads();
-    for (int e = threadIdx.x; e < AL_JC * AL_KT; e += 256) {
-      const int jj = e / AL_KT, kk = e % AL_KT;
+    for (int e = threadIdx.x; e < AL_BJ * AL_BM; e += 256) {  // L slab: coalesced along j, stored transposed
+      const int ii = e / AL_BJ, jj = e % AL_BJ;
+      const int i = i0 + ii, j = jc + jj;
+      Ls[jj][ii] = (i < cs && j < cs) ? __ldg(Lt + (size_t)i * cs + j) : 0.0;
+    }
+    for (int e = threadIdx.x; e < AL_BJ * AL_BN; e += 256) {
+      const int jj = e / AL_BN, kk = e % AL_BN;
       const int j = jc + jj, kg = kbase + kk;
       Zs[jj][kk] = (j < cs && kg < K) ? Z[(size_t)j * ldk + kg] : 0.0;
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = i0 + ty * 8 + q;
-      if (i >= cs) continue;
-      const int jmax = min(AL_JC, i - jc + 1);  // j <= i
-      const double *Lrow = Lt + (size_t)i * cs + jc;
-      double a = acc[q];
-      for (int jj = 0; jj < jmax; ++jj) a = fma(__ldg(Lrow + jj), Zs[jj][tx], a);
-      acc[q] = a;
+    for (int jj = 0; jj < AL_BJ; ++jj) {
+      const double2 l01 = *reinterpret_cast<const double2 *>(&Ls[jj][ty * 4]);
+      const double2 l23 = *reinterpret_cast<const double2 *>(&Ls[jj][ty * 4 + 2]);
+      // samples {2tx, 2tx+1} and {64+2tx, 64+2tx+1}: consecutive lanes read consecutive 16-byte words
+      const double2 z01 = *reinterpret_cast<const double2 *>(&Zs[jj][tx * 2]);
+      const double2 z23 = *reinterpret_cast<const double2 *>(&Zs[jj][64 + tx * 2]);
+      const double l[4] = {l01.x, l01.y, l23.x, l23.y}, z[4] = {z01.x, z01.y, z23.x, z23.y};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(l[a], z[b], acc[a][b]);
     }
   }
-  if (k < K) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = i0 + ty * 8 + q;
-      if (i < cs) E[(size_t)i * ldk + k] = acc[q];
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ty * 4 + a;
+    if (i >= cs) continue;
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int k = kbase + 64 * hlf + tx * 2;
+      double *dst = E + (size_t)i * ldk + k;
+      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[a][2 * hlf], acc[a][2 * hlf + 1]);
+      else if (k < K) dst[0] = acc[a][2 * hlf];
     }
   }
 }
@@ -136,7 +155,7 @@ void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E
     dim3 grid((K + 255) / 256, cs);
     apply_L_block_kernel<<<grid, 256, 0, s>>>(Lt, cs, bs, Z, E, ldk, K, stop);
   } else {
-    dim3 grid((K + AL_KT - 1) / AL_KT, (cs + AL_RB - 1) / AL_RB);
+    dim3 grid((K + AL_BN - 1) / AL_BN, (cs + AL_BM - 1) / AL_BM);
     apply_L_dense_kernel<<<grid, 256, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);
   }
 }

@@ -1,122 +1,135 @@
 // sort.cu — G4: stable ascending arg-sort of the K trajectory costs.
 //
 // Replaces `order = sortperm(trajectory_cost)` (POL:455, 563). Julia's sortperm is a stable merge
-// sort on isless (ties keep index order, −0.0 < +0.0, NaN last). An LSD radix sort over the
-// order-preserving 64-bit image of the doubles is stable and induces exactly that total order, so
-// given identical costs the permutation is bit-identical to the reference's (tests/test_parity_*).
-// 8 passes of 8 bits: per pass a per-block digit histogram, an exclusive scan over (digit, block)
-// and a stable scatter — written here rather than calling a library sort.
+// sort on isless (ties keep index order, −0.0 < +0.0, NaN last). Here every sample gets the
+// composite key (order-preserving 64-bit image of the cost, sample index): composite keys are
+// unique, so ANY comparison sort of them yields exactly the stable permutation. The sort is a merge
+// sort like the reference's: one bitonic pass sorts 2048-key tiles in shared memory, then
+// log2(K/2048) merge-path passes merge runs pairwise with every CTA producing one 2048-key output
+// tile (6 launches at K = 65 536; round 1 started with a 26-launch LSD radix sort — see
+// profiles/README.md for the before/after).
 #include "engine.cuh"
 
 namespace mpopis {
 
+namespace {
+
+constexpr int TILE = 2048;
+constexpr unsigned long long KEY_PAD = ~0ULL;
+
 __device__ __forceinline__ unsigned long long key_of(double c) {
-  unsigned long long b = (unsigned long long)__double_as_longlong(c);
+  const unsigned long long b = (unsigned long long)__double_as_longlong(c);
   return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
 }
-
-constexpr int RS_BLOCK = 256;  // threads per block
-constexpr int RS_ITEMS = 8;    // keys per thread (contiguous per thread -> stable ranking)
-constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;
-
-__global__ void sort_init_kernel(const double *__restrict__ costs, int K, unsigned long long *__restrict__ keys,
-                                 int *__restrict__ vals, const int *stop) {
-  if (stop && *stop) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < K) keys[i] = key_of(costs[i]), vals[i] = i;
+__device__ __forceinline__ bool lt(unsigned long long ka, int ia, unsigned long long kb, int ib) {
+  return ka < kb || (ka == kb && ia < ib);
 }
 
-// hist[d * nblocks + b] = number of keys of tile b whose digit is d
-__global__ void __launch_bounds__(RS_BLOCK) radix_hist_kernel(const unsigned long long *__restrict__ keys, int K,
-                                                               int shift, int nblocks, int *__restrict__ hist,
-                                                               const int *stop) {
+// Sorts tile blockIdx.x of (key_of(costs[i]), i) with a bitonic network in shared memory.
+__global__ void __launch_bounds__(1024) tile_sort_kernel(const double *__restrict__ costs, int n,
+                                                          unsigned long long *__restrict__ keys,
+                                                          int *__restrict__ vals, const int *stop) {
   if (stop && *stop) return;
-  __shared__ int h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const int base = blockIdx.x * RS_TILE;
-  for (int q = 0; q < RS_ITEMS; ++q) {
-    const int i = base + q * RS_BLOCK + threadIdx.x;
-    if (i < K) atomicAdd(&h[(keys[i] >> shift) & 255], 1);
+  __shared__ unsigned long long sk[TILE];
+  __shared__ int sv[TILE];
+  const int base = blockIdx.x * TILE;
+  for (int e = threadIdx.x; e < TILE; e += 1024) {
+    const int i = base + e;
+    sk[e] = i < n ? key_of(costs[i]) : KEY_PAD;
+    sv[e] = i < n ? i : 0x7fffffff;
   }
   __syncthreads();
-  hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
-}
-
-// exclusive scan of hist (256 * nblocks ints), single CTA
-__global__ void __launch_bounds__(1024) radix_scan_kernel(int *__restrict__ hist, int n, const int *stop) {
-  if (stop && *stop) return;
-  __shared__ int seg[1024];
-  const int per = (n + blockDim.x - 1) / blockDim.x;
-  const int beg = threadIdx.x * per, end = min(n, beg + per);
-  int s = 0;
-  for (int i = beg; i < end; ++i) s += hist[i];
-  seg[threadIdx.x] = s;
-  __syncthreads();
-  // Hillis–Steele inclusive scan over the 1024 segment sums
-  for (int off = 1; off < 1024; off <<= 1) {
-    int v = threadIdx.x >= off ? seg[threadIdx.x - off] : 0;
-    __syncthreads();
-    seg[threadIdx.x] += v;
-    __syncthreads();
-  }
-  int run = seg[threadIdx.x] - s;
-  for (int i = beg; i < end; ++i) {
-    const int v = hist[i];
-    hist[i] = run;
-    run += v;
-  }
-}
-
-// stable scatter: within a tile, keys with equal digit keep their input order. One warp-serial
-// ranking per digit would be slow; instead each thread ranks its keys with a per-digit running
-// counter built from a ballot-free two-level count: (1) per-thread-chunk digit counts in shared
-// memory laid out [thread][...] are too large, so the tile is processed in RS_ITEMS rounds of
-// RS_BLOCK consecutive keys; in each round a key's rank among equal digits is the number of
-// lower-indexed threads holding the same digit (match_any + popc per warp, plus per-warp digit
-// offsets accumulated in shared memory).
-__global__ void __launch_bounds__(RS_BLOCK) radix_scatter_kernel(const unsigned long long *__restrict__ keys_in,
-                                                                  const int *__restrict__ vals_in, int K, int shift,
-                                                                  int nblocks, const int *__restrict__ hist,
-                                                                  unsigned long long *__restrict__ keys_out,
-                                                                  int *__restrict__ vals_out, const int *stop) {
-  if (stop && *stop) return;
-  __shared__ int digit_base[256];          // running output offset per digit for this tile
-  __shared__ int warp_cnt[RS_BLOCK / 32][256];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  digit_base[threadIdx.x] = hist[threadIdx.x * nblocks + blockIdx.x];
-  const int base = blockIdx.x * RS_TILE;
-  for (int q = 0; q < RS_ITEMS; ++q) {
-    for (int d = lane; d < 256; d += 32) warp_cnt[wid][d] = 0;
-    __syncthreads();
-    const int i = base + q * RS_BLOCK + threadIdx.x;
-    const bool ok = i < K;
-    unsigned long long key = 0;
-    int val = 0, d = 0;
-    if (ok) key = keys_in[i], val = vals_in[i], d = (int)((key >> shift) & 255);
-    // rank within the warp among lanes with the same digit
-    const unsigned act = __ballot_sync(0xffffffffu, ok);
-    unsigned same = __match_any_sync(0xffffffffu, ok ? d : (256 + lane));
-    same &= act;
-    const int rank_in_warp = __popc(same & ((1u << lane) - 1));
-    if (ok && rank_in_warp == 0) warp_cnt[wid][d] = __popc(same);
-    __syncthreads();
-    if (ok) {
-      int off = digit_base[d];
-      for (int w2 = 0; w2 < wid; ++w2) off += warp_cnt[w2][d];
-      const int dst = off + rank_in_warp;
-      keys_out[dst] = key;
-      vals_out[dst] = val;
+  for (int k = 2; k <= TILE; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int t = threadIdx.x;
+      const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair, bit j clear
+      const int p = i | j;
+      const bool up = (i & k) == 0;
+      const unsigned long long ka = sk[i], kb = sk[p];
+      const int va = sv[i], vb = sv[p];
+      if (lt(kb, vb, ka, va) == up) sk[i] = kb, sv[i] = vb, sk[p] = ka, sv[p] = va;
+      __syncthreads();
     }
-    __syncthreads();
-    {  // advance the per-digit base by this round's totals
-      const int dd = threadIdx.x;
-      int tot = 0;
+  for (int e = threadIdx.x; e < TILE; e += 1024) {
+    const int i = base + e;
+    if (i < n) keys[i] = sk[e], vals[i] = sv[e];
+  }
+}
+
+// number of elements taken from A among the first `diag` outputs of merge(A, B)
+__device__ __forceinline__ int merge_path(const unsigned long long *ak, const int *av, int na,
+                                          const unsigned long long *bk, const int *bv, int nb, int diag) {
+  int lo = max(0, diag - nb), hi = min(diag, na);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int bi = diag - 1 - mid;
+    if (lt(bk[bi], bv[bi], ak[mid], av[mid])) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+
+// Same partition point, found by one warp with a 33-ary search: every lane probes one split and the
+// ballot of the (monotone) predicate narrows [lo, hi] 33-fold per round — 3 dependent global-memory
+// round trips instead of 15 for the run lengths of K = 65 536 (the pass is latency-, not bandwidth-bound).
+__device__ __forceinline__ int merge_path_warp(const unsigned long long *ak, const int *av, int na,
+                                               const unsigned long long *bk, const int *bv, int nb, int diag) {
+  const int lane = threadIdx.x & 31;
+  int lo = max(0, diag - nb), hi = min(diag, na);
+  while (hi > lo) {
+    const int mid = lo + (int)(((long long)(hi - lo) * (lane + 1)) / 33);  // in [lo, hi)
+    const int bi = diag - 1 - mid;
+    const bool gt = !lt(bk[bi], bv[bi], ak[mid], av[mid]);  // partition point lies above `mid`
+    const int c = __popc(__ballot_sync(0xffffffffu, gt));   // lanes 0..c-1 say "above"
+    const int lo_c = __shfl_sync(0xffffffffu, mid, max(c - 1, 0)) + 1;
+    const int hi_c = __shfl_sync(0xffffffffu, mid, min(c, 31));
+    lo = c > 0 ? lo_c : lo;
+    hi = c < 32 ? hi_c : hi;
+  }
+  return lo;
+}
+
+// One merge pass: sorted runs of length L are merged pairwise; CTA b writes output tile b.
+__global__ void __launch_bounds__(256) merge_pass_kernel(const unsigned long long *__restrict__ kin,
+                                                          const int *__restrict__ vin, int n, int L,
+                                                          unsigned long long *__restrict__ kout,
+                                                          int *__restrict__ vout, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ unsigned long long sk[TILE];
+  __shared__ int sv[TILE];
+  __shared__ int sa[2];
+  const int out0 = blockIdx.x * TILE;
+  const int pair_base = (out0 / (2 * L)) * (2 * L);
+  const int na = min(L, n - pair_base), nb = max(0, min(L, n - pair_base - L));
+  const unsigned long long *ak = kin + pair_base, *bk = kin + pair_base + L;
+  const int *av = vin + pair_base, *bv = vin + pair_base + L;
+  const int d0 = out0 - pair_base, d1 = min(d0 + TILE, na + nb);
+  if (threadIdx.x < 64) {  // warp 0 -> start diagonal, warp 1 -> end diagonal
+    const int wsel = threadIdx.x >> 5;
+    const int r = merge_path_warp(ak, av, na, bk, bv, nb, wsel ? d1 : d0);
+    if ((threadIdx.x & 31) == 0) sa[wsel] = r;
+  }
+  __syncthreads();
+  const int a0 = sa[0], a1 = sa[1], b0 = d0 - a0, b1 = d1 - a1;
+  const int la = a1 - a0, lb = b1 - b0;  // la + lb = d1 - d0 <= TILE
+  for (int e = threadIdx.x; e < la; e += 256) sk[e] = ak[a0 + e], sv[e] = av[a0 + e];
+  for (int e = threadIdx.x; e < lb; e += 256) sk[la + e] = bk[b0 + e], sv[la + e] = bv[b0 + e];
+  __syncthreads();
+  constexpr int VT = TILE / 256;
+  const int diag = min(threadIdx.x * VT, la + lb);
+  int ia = merge_path(sk, sv, la, sk + la, sv + la, lb, diag), ib = diag - ia;
 #pragma unroll
-      for (int w2 = 0; w2 < RS_BLOCK / 32; ++w2) tot += warp_cnt[w2][dd];
-      digit_base[dd] += tot;
-    }
-    __syncthreads();
+  for (int q = 0; q < VT; ++q) {
+    const int o = diag + q;
+    if (o >= la + lb) break;
+    bool takeA;
+    if (ia >= la) takeA = false;
+    else if (ib >= lb) takeA = true;
+    else takeA = !lt(sk[la + ib], sv[la + ib], sk[ia], sv[ia]);
+    const int src = takeA ? ia : la + ib;
+    kout[out0 + o] = sk[src];
+    vout[out0 + o] = sv[src];
+    ia += takeA, ib += !takeA;
   }
 }
 
@@ -130,28 +143,32 @@ __global__ void sorted_costs_kernel(const unsigned long long *__restrict__ keys,
   out[i] = __longlong_as_double((long long)b);
 }
 
-int sort_nblocks(int K) { return (K + RS_TILE - 1) / RS_TILE; }
-size_t sort_hist_ints(int K) { return (size_t)256 * sort_nblocks(K); }
+}  // namespace
+
+int sort_launches(int K) {
+  int passes = 0;
+  for (long long L = TILE; L < K; L <<= 1) ++passes;
+  return 2 + passes;
+}
 
 // Sorts costs[0:K]; on return `order` holds the stable ascending permutation (0-based sample ids)
 // and sorted_costs[0:m] the m smallest costs in order. keys_a/keys_b, vals_b: scratch of K entries.
 void launch_sortperm(const double *costs, int K, int m, unsigned long long *keys_a, unsigned long long *keys_b,
-                     int *order, int *vals_b, int *hist, double *sorted_costs, const int *stop, cudaStream_t s) {
-  const int nb = sort_nblocks(K);
-  sort_init_kernel<<<(K + 255) / 256, 256, 0, s>>>(costs, K, keys_a, order, stop);
-  unsigned long long *kin = keys_a, *kout = keys_b;
-  int *vin = order, *vout = vals_b;
-  for (int pass = 0; pass < 8; ++pass) {
-    const int shift = 8 * pass;
-    radix_hist_kernel<<<nb, RS_BLOCK, 0, s>>>(kin, K, shift, nb, hist, stop);
-    radix_scan_kernel<<<1, 1024, 0, s>>>(hist, 256 * nb, stop);
-    radix_scatter_kernel<<<nb, RS_BLOCK, 0, s>>>(kin, vin, K, shift, nb, hist, kout, vout, stop);
+                     int *order, int *vals_b, double *sorted_costs, const int *stop, cudaStream_t s) {
+  const int ntiles = (K + TILE - 1) / TILE;
+  int passes = 0;
+  for (long long L = TILE; L < K; L <<= 1) ++passes;
+  // choose the starting buffer so that the final pass lands in (keys_a, order)
+  unsigned long long *kin = (passes & 1) ? keys_b : keys_a, *kout = (passes & 1) ? keys_a : keys_b;
+  int *vin = (passes & 1) ? vals_b : order, *vout = (passes & 1) ? order : vals_b;
+  tile_sort_kernel<<<ntiles, 1024, 0, s>>>(costs, K, kin, vin, stop);
+  for (long long L = TILE; L < K; L <<= 1) {
+    merge_pass_kernel<<<ntiles, 256, 0, s>>>(kin, vin, K, (int)L, kout, vout, stop);
     unsigned long long *tk = kin;
     kin = kout, kout = tk;
     int *tv = vin;
     vin = vout, vout = tv;
   }
-  // 8 passes = even number of swaps: results are back in keys_a / order
   sorted_costs_kernel<<<(m + 255) / 256, 256, 0, s>>>(kin, m, sorted_costs, stop);
 }
 

@@ -72,8 +72,56 @@ __global__ void __launch_bounds__(1024) weights_kernel(const double *__restrict_
   for (int k = threadIdx.x; k < K; k += blockDim.x) w[k] = w[k] / eta;
 }
 
-void launch_weights(const double *costs, int K, double lambda, double *w, const int *stop, cudaStream_t s) {
-  weights_kernel<<<1, 1024, 0, s>>>(costs, K, lambda, w, stop);
+// Multi-CTA version for large K: (1) per-CTA minima, (2) exp + per-CTA sums, (3) normalise. The partials
+// are combined in a fixed order by every CTA, so the result is deterministic and identical on all ranks.
+constexpr int WG_MAX = 256;
+__global__ void __launch_bounds__(256) weights_min_kernel(const double *__restrict__ costs, int K,
+                                                           double *__restrict__ scratch, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[33];
+  double mn = CUDART_INF;
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < K; k += gridDim.x * 256) mn = fmin(mn, costs[k]);
+  mn = block_reduce<1>(mn, red);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = mn;
+}
+__global__ void __launch_bounds__(256) weights_exp_kernel(const double *__restrict__ costs, int K, double lambda,
+                                                           double *__restrict__ w, double *__restrict__ scratch,
+                                                           const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[33];
+  double mn = threadIdx.x < gridDim.x ? scratch[threadIdx.x] : CUDART_INF;
+  const double rho = block_reduce<1>(mn, red);
+  const double ninv = -1 / lambda;
+  double s = 0.0;
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < K; k += gridDim.x * 256) {
+    const double e = exp(ninv * (costs[k] - rho));
+    w[k] = e;
+    s += e;
+  }
+  s = block_reduce<0>(s, red);
+  if (threadIdx.x == 0) scratch[WG_MAX + blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) weights_norm_kernel(int K, double *__restrict__ w,
+                                                            const double *__restrict__ scratch, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[33];
+  const double part = threadIdx.x < gridDim.x ? scratch[WG_MAX + threadIdx.x] : 0.0;
+  const double eta = block_reduce<0>(part, red);
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < K; k += gridDim.x * 256) w[k] = w[k] / eta;
+}
+
+// scratch: 2 * WG_MAX doubles
+int launch_weights(const double *costs, int K, double lambda, double *w, double *scratch, const int *stop,
+                   cudaStream_t s) {
+  if (K <= 8192 || !scratch) {
+    weights_kernel<<<1, 1024, 0, s>>>(costs, K, lambda, w, stop);
+    return 1;
+  }
+  const int g = min(WG_MAX, (K + 1023) / 1024);
+  weights_min_kernel<<<g, 256, 0, s>>>(costs, K, scratch, stop);
+  weights_exp_kernel<<<g, 256, 0, s>>>(costs, K, lambda, w, scratch, stop);
+  weights_norm_kernel<<<g, 256, 0, s>>>(K, w, scratch, stop);
+  return 3;
 }
 
 // ---- G8 / G5: weighted row sums ---------------------------------------------------------------
@@ -152,52 +200,68 @@ void launch_finalize_mean(const double *sums, int rows, double *mu, double *U, c
 // ---- G5: centred (weighted) scatter matrix ------------------------------------------------------
 // P[c][i][j] = Σ_{k in chunk c} w_k (X[i][k] − μ_i)(X[j][k] − μ_j) for the lower 32x32 tiles.
 // 16x16 threads, 2x2 outputs per thread, 32-sample slabs staged (centred) in shared memory.
-constexpr int SY_T = 32;
+// 64 x 64 output tile per CTA (lower tiles only), 16 x 16 threads with a 4 x 4 register tile each,
+// 16-sample slabs staged sample-major in shared memory: per sample a thread issues four 16-byte
+// shared loads (two of them warp-broadcast) for 16 DFMAs.
+constexpr int SY_T = 64, SY_K = 16;
 __global__ void __launch_bounds__(256) syrk_partial_kernel(const double *__restrict__ X, long long ld, int p,
                                                             int n, const double *__restrict__ w,
                                                             const double *__restrict__ mu, int chunk,
                                                             double *__restrict__ P, const int *stop) {
   if (stop && *stop) return;
-  __shared__ double As[SY_T][SY_T + 1], Bs[SY_T][SY_T + 1];
-  // decode lower-triangular tile index
-  int t = blockIdx.x, bi = 0;
+  __shared__ __align__(16) double As[SY_K][SY_T], Bs[SY_K][SY_T];  // [sample][row]
+  int t = blockIdx.x, bi = 0;  // decode the lower-triangular tile index
   while (t > bi) t -= bi + 1, ++bi;
   const int bj = t;
   const int c = blockIdx.y;
   const int kbeg = c * chunk, kend = min(n, kbeg + chunk);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-  for (int k0 = kbeg; k0 < kend; k0 += SY_T) {
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k0 = kbeg; k0 < kend; k0 += SY_K) {
     __syncthreads();
-    for (int e = threadIdx.x; e < SY_T * SY_T; e += 256) {
-      const int rr = e >> 5, kk = e & 31, k = k0 + kk;
+    for (int e = threadIdx.x; e < SY_T * SY_K; e += 256) {
+      const int rr = e / SY_K, kk = e % SY_K, k = k0 + kk;  // 16 consecutive samples of one row: 128 B
       const int ia = bi * SY_T + rr, ib = bj * SY_T + rr;
       const bool ok = k < kend;
       const double wk = ok ? (w ? w[k] : 1.0) : 0.0;
-      As[rr][kk] = (ok && ia < p) ? wk * (X[(size_t)ia * ld + k] - mu[ia]) : 0.0;
-      Bs[rr][kk] = (ok && ib < p) ? (X[(size_t)ib * ld + k] - mu[ib]) : 0.0;
+      As[kk][rr] = (ok && ia < p) ? wk * (X[(size_t)ia * ld + k] - mu[ia]) : 0.0;
+      Bs[kk][rr] = (ok && ib < p) ? (X[(size_t)ib * ld + k] - mu[ib]) : 0.0;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < SY_T; ++kk) {
-      const double x0 = As[2 * ty][kk], x1 = As[2 * ty + 1][kk];
-      const double y0 = Bs[2 * tx][kk], y1 = Bs[2 * tx + 1][kk];
-      a00 = fma(x0, y0, a00), a01 = fma(x0, y1, a01);
-      a10 = fma(x1, y0, a10), a11 = fma(x1, y1, a11);
+#pragma unroll
+    for (int kk = 0; kk < SY_K; ++kk) {
+      const double2 x01 = *reinterpret_cast<const double2 *>(&As[kk][ty * 4]);
+      const double2 x23 = *reinterpret_cast<const double2 *>(&As[kk][ty * 4 + 2]);
+      const double2 y01 = *reinterpret_cast<const double2 *>(&Bs[kk][tx * 2]);       // columns 2tx, 2tx+1
+      const double2 y23 = *reinterpret_cast<const double2 *>(&Bs[kk][32 + tx * 2]);  // columns 32+2tx, +1
+      const double x[4] = {x01.x, x01.y, x23.x, x23.y}, y[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
     }
   }
   double *Pc = P + (size_t)c * p * p;
-  const int i0 = bi * SY_T + 2 * ty, j0 = bj * SY_T + 2 * tx;
-  if (i0 < p && j0 < p) Pc[(size_t)i0 * p + j0] = a00;
-  if (i0 < p && j0 + 1 < p) Pc[(size_t)i0 * p + j0 + 1] = a01;
-  if (i0 + 1 < p && j0 < p) Pc[(size_t)(i0 + 1) * p + j0] = a10;
-  if (i0 + 1 < p && j0 + 1 < p) Pc[(size_t)(i0 + 1) * p + j0 + 1] = a11;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = bi * SY_T + ty * 4 + a;
+    if (i >= p) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = bj * SY_T + (b >> 1) * 32 + tx * 2 + (b & 1);
+      if (j < p) Pc[(size_t)i * p + j] = acc[a][b];
+    }
+  }
 }
 
 int syrk_chunk(int n) {
-  // aim for <= 64 chunks, multiples of 32 samples
-  int chunk = ((n + 63) / 64 + 31) / 32 * 32;
-  return chunk < 32 ? 32 : chunk;
+  // aim for <= 32 chunks, multiples of 16 samples
+  int chunk = ((n + 31) / 32 + SY_K - 1) / SY_K * SY_K;
+  return chunk < SY_K ? SY_K : chunk;
 }
 int syrk_nchunks(int n) {
   const int ch = syrk_chunk(n);
@@ -239,29 +303,48 @@ __global__ void __launch_bounds__(256) shrink_q_partial_kernel(const double *__r
                                                                 double *__restrict__ partial, const int *stop) {
   if (stop && *stop) return;
   __shared__ double red[33];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  double q = 0.0;
-  if (k < n && (!w || w[k] != 0.0)) {
+  extern __shared__ double dsc[];  // p per-variable scales 1/σ_i (1 for :lw), p means
+  {
     const double cnt = *cnt_dev;  // global number of observations (Σ of ownership weights)
-    double a = 0.0, b = 0.0;
-    for (int i = 0; i < p; ++i) {
-      double z = X[(size_t)i * ld + k] - mu[i];
-      if (standardise) z = z * (1.0 / sqrt(Sraw[(size_t)i * p + i] / cnt));
+    for (int i = threadIdx.x; i < p; i += blockDim.x) {
+      dsc[i] = standardise ? 1.0 / sqrt(Sraw[(size_t)i * p + i] / cnt) : 1.0;
+      dsc[p + i] = mu[i];
+    }
+  }
+  __syncthreads();
+  // 64 samples x 4 row groups per CTA: the rows of a sample are split over 4 threads and recombined
+  __shared__ double sa[4][64], sb[4][64];
+  const int ks = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int k = blockIdx.x * 64 + ks;
+  double a = 0.0, b = 0.0;
+  if (k < n && (!w || w[k] != 0.0)) {
+#pragma unroll 4
+    for (int i = g; i < p; i += 4) {
+      const double z = (X[(size_t)i * ld + k] - dsc[p + i]) * dsc[i];
       const double z2 = z * z;
       a += z2;
       b = fma(z2, z2, b);
     }
-    q = a * a - b;
+  }
+  sa[g][ks] = a, sb[g][ks] = b;
+  __syncthreads();
+  double q = 0.0;
+  if (g == 0) {
+    const double at = (sa[0][ks] + sa[1][ks]) + (sa[2][ks] + sa[3][ks]);
+    const double bt = (sb[0][ks] + sb[1][ks]) + (sb[2][ks] + sb[3][ks]);
+    q = at * at - bt;
   }
   const double t = block_reduce<0>(q, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
+int shrink_q_nblocks(int n) { return (n + 63) / 64; }
+
 void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
                              const double *Sraw, const double *cnt_dev, int standardise, double *partial,
                              const int *stop, cudaStream_t s) {
-  shrink_q_partial_kernel<<<(n + 255) / 256, 256, 0, s>>>(X, ld, p, n, w, mu, Sraw, cnt_dev, standardise, partial,
-                                                          stop);
+  shrink_q_partial_kernel<<<shrink_q_nblocks(n), 256, sizeof(double) * 2 * p, s>>>(X, ld, p, n, w, mu, Sraw, cnt_dev,
+                                                                                   standardise, partial, stop);
 }
 
 // Final covariance: Σ′ = shrink(method, Sraw / denom) + ridge·I, written to Sigma (symmetric, so
