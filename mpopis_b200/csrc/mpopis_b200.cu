@@ -86,7 +86,8 @@ struct mpopis_handle {
   int K = 0, Kloc = 0, T = 0, N = 0, as = 0, cs = 0, ss = 0, m_elite = 0;
   long long k0 = 0, ldk = 0, ldm = 0;
   int dev = 0, world = 1, rank = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, st2 = nullptr;  // main stream; side stream for the next iteration's normals
+  cudaEvent_t ev_z_free = nullptr, ev_z_ready = nullptr;
   ncclComm_t comm = nullptr;
   bool env_set = false, cma_set = false;
   CarEnvArgs car{};
@@ -254,11 +255,23 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       const double *src = Z_host + ((size_t)n * K + h->k0) * cs;
       CU(cudaMemcpyAsync(h->d_stage, src, sizeof(double) * cs * Kloc, cudaMemcpyHostToDevice, st));
       launch_transpose_in(h->d_stage, h->d_Z, cs, Kloc, h->ldk, st);
+    } else if (n == 0) {
+      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, (uint32_t)h->step, 0u, stop, st);
     } else {
-      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, (uint32_t)h->step, (uint32_t)n, stop, st);
+      CU(cudaStreamWaitEvent(st, h->ev_z_ready, 0));  // Z of this iteration was drawn on the side stream
     }
     launch_apply_L(Lt, cs, bs, h->d_Z, h->d_E, h->ldk, Kloc, stop, st);
     h->launches += 2;
+    if (!Z_host && n + 1 < N) {
+      // The next iteration's normals depend on nothing but (seed, step, n+1): draw them on the side stream
+      // as soon as E = L Z has consumed the buffer, so they fill the SMs the latency-bound adaptation
+      // kernels (sort passes, Cholesky, moment finalisation) leave idle.
+      CU(cudaEventRecord(h->ev_z_free, st));
+      CU(cudaStreamWaitEvent(h->st2, h->ev_z_free, 0));
+      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, (uint32_t)h->step, (uint32_t)(n + 1), stop,
+                            h->st2);
+      CU(cudaEventRecord(h->ev_z_ready, h->st2));
+    }
     // --- rollouts (POL:452 -> POL:261-278) ---
     CU(cudaEventRecord(h->ev[2 + 2 * n], st));
     if (int rc = launch_rollouts(h, h->d_U_cur, h->d_U_orig, bvec)) return rc;
@@ -522,7 +535,10 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
     if (int rc_ = (x)) return bail(rc_); \
   } while (0)
   TRY(set_device(h));
-  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_z_free, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_z_ready, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(MPOPIS_ERR_CUDA, "cudaStreamCreate failed"));
   const size_t cs = h->cs, K = h->K, Kloc = h->Kloc, ld = h->ldk;
   TRY(dalloc(&h->d_state, h->ss));
@@ -617,6 +633,9 @@ int mpopis_b200_destroy(mpopis_t *h) {
   if (h->h_flags) cudaFreeHost(h->h_flags);
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
+  if (h->ev_z_free) cudaEventDestroy(h->ev_z_free);
+  if (h->ev_z_ready) cudaEventDestroy(h->ev_z_ready);
+  if (h->st2) cudaStreamSynchronize(h->st2), cudaStreamDestroy(h->st2);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;

@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(256) syrk_partial_kernel(const double *__restr
                                                             const double *__restrict__ mu, int chunk,
                                                             double *__restrict__ P, const int *stop) {
   if (stop && *stop) return;
-  __shared__ __align__(16) double As[SY_K][SY_T], Bs[SY_K][SY_T];  // [sample][row]
+  // [sample][row], row pitch padded by 2 doubles: the transposing stores are 2-way instead of 16-way
+  // bank-conflicted while rows stay 16-byte aligned for the vector reads
+  __shared__ __align__(16) double As[SY_K][SY_T + 2], Bs[SY_K][SY_T + 2];
   int t = blockIdx.x, bi = 0;  // decode the lower-triangular tile index
   while (t > bi) t -= bi + 1, ++bi;
   const int bj = t;
@@ -221,17 +223,28 @@ __global__ void __launch_bounds__(256) syrk_partial_kernel(const double *__restr
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  // each thread stages 4 + 4 elements per slab: rows rr0 + 16 q, sample kk0 (16 consecutive samples of a
+  // row = one 128-byte segment); the NEXT slab is fetched into registers while the current one is consumed
+  const int kk0 = threadIdx.x & 15, rr0 = threadIdx.x >> 4;
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
+    const int k = k0 + kk0;
+    const bool ok = k < kend;
+    const double wk = ok ? (w ? w[k] : 1.0) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ia = bi * SY_T + rr0 + 16 * q, ib = bj * SY_T + rr0 + 16 * q;
+      ra[q] = (ok && ia < p) ? wk * (X[(size_t)ia * ld + k] - mu[ia]) : 0.0;
+      rb[q] = (ok && ib < p) ? (X[(size_t)ib * ld + k] - mu[ib]) : 0.0;
+    }
+  };
+  fetch(kbeg);
   for (int k0 = kbeg; k0 < kend; k0 += SY_K) {
     __syncthreads();
-    for (int e = threadIdx.x; e < SY_T * SY_K; e += 256) {
-      const int rr = e / SY_K, kk = e % SY_K, k = k0 + kk;  // 16 consecutive samples of one row: 128 B
-      const int ia = bi * SY_T + rr, ib = bj * SY_T + rr;
-      const bool ok = k < kend;
-      const double wk = ok ? (w ? w[k] : 1.0) : 0.0;
-      As[kk][rr] = (ok && ia < p) ? wk * (X[(size_t)ia * ld + k] - mu[ia]) : 0.0;
-      Bs[kk][rr] = (ok && ib < p) ? (X[(size_t)ib * ld + k] - mu[ib]) : 0.0;
-    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) As[kk0][rr0 + 16 * q] = ra[q], Bs[kk0][rr0 + 16 * q] = rb[q];
     __syncthreads();
+    if (k0 + SY_K < kend) fetch(k0 + SY_K);
 #pragma unroll
     for (int kk = 0; kk < SY_K; ++kk) {
       const double2 x01 = *reinterpret_cast<const double2 *>(&As[kk][ty * 4]);
@@ -259,8 +272,8 @@ __global__ void __launch_bounds__(256) syrk_partial_kernel(const double *__restr
 }
 
 int syrk_chunk(int n) {
-  // aim for <= 32 chunks, multiples of 16 samples
-  int chunk = ((n + 31) / 32 + SY_K - 1) / SY_K * SY_K;
+  // aim for <= 48 chunks (≈ one CTA per SM for cs = 100: 3 tiles x 48), multiples of 16 samples
+  int chunk = ((n + 47) / 48 + SY_K - 1) / SY_K * SY_K;
   return chunk < SY_K ? SY_K : chunk;
 }
 int syrk_nchunks(int n) {

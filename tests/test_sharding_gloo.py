@@ -1,0 +1,92 @@
+"""N > 1 path on CPU: world_size-2 gloo processes run the numpy emulation of the engine's sharded
+reductions (ownership-masked partial moments -> all-reduce -> finalise) and compare with the unsharded
+oracle. Also the shard arithmetic and the comm-id broadcast plumbing (with a stub id, no NCCL here)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, method, out_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch
+    import torch.distributed as dist
+    from mpopis_b200 import sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def allreduce(x):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).copy())
+        dist.all_reduce(t)
+        return t.numpy()
+
+    rng = np.random.default_rng(123)  # same data on every rank
+    cs, K, m = 20, 96, 24
+    E = rng.standard_normal((cs, K)) * rng.uniform(0.2, 1.5, (cs, 1))
+    costs = np.round(rng.normal(0, 10, K), 1)  # ties on purpose
+    k0, kl = sharding.shard_range(K, rank, world)
+    # all-gather of the local costs
+    parts = [torch.zeros(kl, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(costs[k0:k0 + kl].copy()))
+    gathered = torch.cat(parts).numpy()
+    order = np.argsort(gathered, kind="stable")
+    mu, S, lam = sharding.sharded_elite_moments(E[:, k0:k0 + kl], k0, order, m, allreduce, method)
+    w = np.exp(-(gathered - gathered.min()) / 10.0)
+    w /= w.sum()
+    ws = sharding.sharded_weighted_sum(E[:, k0:k0 + kl], w, k0, allreduce)
+    # comm-id broadcast plumbing (stub id: NCCL itself is not involved on the CPU box)
+    box = [b"x" * 128 if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    np.savez(Path(out_dir) / f"r{rank}.npz", mu=mu, S=S, lam=lam, ws=ws, gathered=gathered, idlen=len(box[0]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("method", ["mle", "ss", "oas"])
+def test_sharded_moments_match_unsharded_oracle(tmp_path, orc, method):
+    from conftest import configure, engine_kwargs, make_env
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), method, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    for k in ("mu", "S", "lam", "ws", "gathered"):
+        assert np.array_equal(r0[k], r1[k]), f"ranks disagree on {k}"  # every rank must reach the same Σ′
+    assert int(r0["idlen"]) == 128
+    # unsharded reference: the oracle's cov(method, elite') on the same elites
+    rng = np.random.default_rng(123)
+    cs, K, m = 20, 96, 24
+    E = rng.standard_normal((cs, K)) * rng.uniform(0.2, 1.5, (cs, 1))
+    costs = np.round(rng.normal(0, 10, K), 1)
+    assert np.array_equal(r0["gathered"], costs)
+    order = orc.sortperm(costs)
+    env = make_env("car")
+    e = configure(orc.engine(**engine_kwargs("cemppi", env, 64, 10)), env, "cemppi")  # cs = 20
+    mu, S = e.cov_estimate(E[:, order[:m]], method)
+    np.testing.assert_allclose(r0["mu"], mu, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(r0["S"], S, rtol=1e-10, atol=1e-13)
+    assert abs(float(r0["lam"]) - e.last_shrinkage()) < 1e-10
+    w = e.weights(costs, 10.0)
+    np.testing.assert_allclose(r0["ws"][:-1], E @ w, rtol=1e-12, atol=1e-14)
+    assert abs(r0["ws"][-1] - 1.0) < 1e-13
+
+
+def test_shard_range():
+    from mpopis_b200.sharding import shard_range
+    assert [shard_range(1 << 20, r, 8) for r in (0, 7)] == [(0, 131072), (7 * 131072, 131072)]
+    with pytest.raises(ValueError):
+        shard_range(150, 0, 8)
+    with pytest.raises(ValueError):
+        shard_range(128, 2, 2)
