@@ -263,12 +263,27 @@ def main():
                              "fp64_instr_per_rollout_step": ipr, "source": "profiles/rollout_kernel_metrics.json (ncu) "
                              "× live CUDA-event launch time; peak = DFMA micro-benchmark in this run"}
 
+    # the one HBM-bound kernel of the path (weighted-noise reduction, POL:226-229) on an operand larger than L2
+    roofline_g8 = None
+    if rank == 0 and world == 1:
+        from mpopis_b200 import _abi
+        from mpopis_b200.engine import Engine
+        g8 = Engine(bound, policy="gmppi", env=_abi.ENV_CAR_RACING, num_samples=1 << 20, horizon=T, lam=LAMBDA,
+                    device=local_rank)
+        ms8, bytes8 = g8.bench_rowsum(20)
+        g8.close()
+        ach8 = bytes8 / (ms8 * 1e-3) / 1e9
+        roofline_g8 = {"kernel": "rowsum_partial_kernel (Σ_k w_k E[r,k], K=2^20, cs=100: 839 MB > L2)", "bound": "hbm",
+                       "achieved": ach8, "peak": hbm_peak, "unit": "GB/s", "frac": ach8 / hbm_peak,
+                       "ms_per_launch": ms8, "peak_source": peak_src}
+
     line = dict(base, value=value, ms_per_step=dev_ms / args.steps,
                 config={"workload": workload, "l2": "flushed between steps (256 MiB memset outside the timed intervals)",
                         "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU"},
                 e2e={"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "ms_per_step": e2e_s / args.steps * 1e3},
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_fp64=roofline_fp64,
+                roofline_g8=roofline_g8,
                 fp64_peak_dfma_per_s=fp64_peak, its_per_step=its_total / args.steps)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

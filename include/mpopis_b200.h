@@ -217,6 +217,10 @@ int mpopis_b200_resident_total_its(mpopis_t *h, int64_t *total_its_out);
  * the roofline denominator of the FP64-bound rollout kernel, which MEASURED_PEAKS.json lacks. */
 int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out);
 
+/* Times the weighted-noise reduction kernel (POL:226-229: weights' * E[r,:] for every row r) alone over this
+ * handle's E operand: CUDA-event ms per launch and the algorithmic bytes per launch (8·cs·K + 8·K). */
+int mpopis_b200_bench_rowsum(mpopis_t *h, int32_t reps, double *ms_per_launch_out, double *bytes_per_launch_out);
+
 /* Timing/introspection: kernels launched by this handle so far, device milliseconds spent in the
  * rollout kernel during the last plan (CUDA events on the handle's stream), the handle's
  * cudaStream_t (as void*). */

@@ -1,0 +1,174 @@
+# MPOPISB200.jl — Julia shim that plugs libmpopis_b200.so into an UNMODIFIED MPOPIS.jl.
+#
+# NOT EXECUTED in this repository's CI: Julia is not installed in the build image (SURVEY.md §0.2). It is
+# the reference-side binding a maintainer adds; tests exercise the same C-ABI calls, in the same order,
+# through the Python ctypes mirror (mpopis_b200/engine.py, policies.py).
+#
+# Mechanism: the same one MPOPIS already uses for its EnvPool backend — more specific methods of the
+# policy functor / simulate_model for concrete env types (mppi_mpopi_policies.jl:148,240; utils.jl:103).
+# Nothing in MPOPIS is edited; `using MPOPISB200` after `using MPOPIS` is enough:
+#
+#     using MPOPIS, MPOPISB200
+#     MPOPISB200.enable!()                       # route CarRacing / MultiCar / MountainCar policies to the GPU
+#     simulate_car_racing(policy_type=:cemppi, num_samples=65536)
+#
+module MPOPISB200
+
+using MPOPIS
+using Random
+import MPOPIS: AbstractGMPPI_Policy, MPPI_Policy, AbstractPathIntegralPolicy, CarRacingEnv, MultiCarRacingEnv,
+               simulate_model
+import ReinforcementLearning: MountainCarEnv
+
+const LIB = Ref{String}(get(ENV, "MPOPIS_B200_LIB", "libmpopis_b200.so"))
+const ABI_VERSION = 1
+
+# ---- include/mpopis_b200.h -------------------------------------------------------------------------------
+struct Cfg                       # mpopis_cfg_t (field order and types must match the header)
+    abi_version::Int32; policy::Int32; env::Int32; n_cars::Int32
+    num_samples::Int64; horizon::Int64; opt_its::Int64
+    lambda::Float64; alpha::Float64; lambda_ais::Float64; ce_elite_threshold::Float64
+    sigma_est::Int32; early_stop::Int32; log_trajectories::Int32
+    device::Int32; rank::Int32; world_size::Int32
+    reserved::NTuple{4,Int32}
+end
+struct Cma                       # mpopis_cma_t
+    sigma::Float64; m_elite::Int64; mu_eff::Float64; c_sigma::Float64; d_sigma::Float64
+    c_Sigma::Float64; c1::Float64; c_mu::Float64; E_norm::Float64
+end
+
+last_error() = unsafe_string(ccall((:mpopis_b200_last_error, LIB[]), Cstring, ()))
+check(rc) = rc == 0 ? nothing : error("mpopis_b200 ($rc): $(last_error())")   # MPOPIS-style error(...)
+
+const POLICY = Dict(MPOPIS.MPPI_Policy => 0, MPOPIS.GMPPI_Policy => 1, MPOPIS.IMPPI_Policy => 2,
+                    MPOPIS.CEMPPI_Policy => 3, MPOPIS.CMAMPPI_Policy => 4, MPOPIS.μAISMPPI_Policy => 5,
+                    MPOPIS.μΣAISMPPI_Policy => 6, MPOPIS.PMCMPPI_Policy => 7)
+policy_code(pol) = POLICY[Base.typename(typeof(pol)).wrapper]
+
+function sigma_est_code(pol)
+    pol isa MPOPIS.CEMPPI_Policy || return Int32(0)
+    m = pol.Σ_estimation_method
+    m isa MPOPIS.SimpleCovariance && return Int32(0)
+    s = m.shrinkage                                   # :lw, :ss, :rblw, :oas (mppi_mpopi_policies.jl:414-426)
+    return Int32(Dict(:lw => 1, :ss => 2, :rblw => 3, :oas => 4)[s])
+end
+
+# ---- handles, one per policy object ------------------------------------------------------------------------
+const HANDLES = IdDict{Any,Ptr{Cvoid}}()
+
+env_code(::CarRacingEnv) = (Int32(0), Int32(1))
+env_code(e::MultiCarRacingEnv) = (Int32(0), Int32(e.N))
+env_code(::MountainCarEnv) = (Int32(1), Int32(0))
+
+car_params(e::CarRacingEnv) = Float64[getfield(e.params, f) for f in fieldnames(typeof(e.params))]  # 18, declaration order
+
+function set_env!(h, e::CarRacingEnv)
+    p = car_params(e); t = e.track
+    check(ccall((:mpopis_b200_set_car_env, LIB[]), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+        h, 1, p, e.dt, e.δt, t.x′, t.y′, t.lane_width′, length(t.x′)))
+end
+function set_env!(h, e::MultiCarRacingEnv)
+    p = reduce(vcat, car_params.(e.envs)); t = e.envs[1].track      # sub-envs share the track file (multi-car_racing.jl:37-45)
+    check(ccall((:mpopis_b200_set_car_env, LIB[]), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+        h, e.N, p, e.dt, e.δt, t.x′, t.y′, t.lane_width′, length(t.x′)))
+end
+function set_env!(h, e::MountainCarEnv)
+    q = e.params
+    p = Float64[q.min_pos, q.max_pos, q.max_speed, q.goal_pos, q.goal_velocity, q.power, q.gravity]
+    check(ccall((:mpopis_b200_set_mountaincar_env, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h, p, q.max_steps))
+end
+
+function handle(pol::AbstractPathIntegralPolicy, env; device=0)
+    get!(HANDLES, pol) do
+        ecode, ncars = env_code(env)
+        P = pol.params
+        cfg = Cfg(ABI_VERSION, policy_code(pol), ecode, ncars, P.num_samples, P.horizon,
+                  hasproperty(pol, :opt_its) ? pol.opt_its : 1, P.λ, P.α,
+                  hasproperty(pol, :λ_ais) ? pol.λ_ais : 20.0,
+                  hasproperty(pol, :ce_elite_threshold) ? pol.ce_elite_threshold : 0.8,
+                  sigma_est_code(pol), 1, P.log ? 1 : 0, device, 0, 1, (Int32(0), Int32(0), Int32(0), Int32(0)))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:mpopis_b200_create, LIB[]), Cint, (Ref{Cfg}, Ref{Ptr{Cvoid}}), cfg, out))
+        h = out[]
+        set_env!(h, env)
+        Σ = Matrix{Float64}(pol.Σ)                   # as x as for :mppi, cs x cs otherwise; column-major as is
+        check(ccall((:mpopis_b200_set_sigma, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h, Σ, size(Σ, 1)))
+        if pol isa MPOPIS.CMAMPPI_Policy
+            cma = Cma(pol.σ, pol.m_elite, pol.μ_eff, pol.cσ, pol.dσ, pol.cΣ, pol.c1, pol.cμ, pol.E)
+            check(ccall((:mpopis_b200_set_cma, LIB[]), Cint, (Ptr{Cvoid}, Ref{Cma}, Ptr{Float64}, Int64),
+                        h, cma, pol.ws, length(pol.ws)))
+        end
+        # Random.seed!(pol, s) seeds pol.rng (MPOPIS.jl:54); draw the engine's Philox key from that stream so
+        # that `seed!(pol, seed + k)` keeps controlling reproducibility.
+        check(ccall((:mpopis_b200_seed, LIB[]), Cint, (Ptr{Cvoid}, UInt64), h, rand(pol.rng, UInt64)))
+        finalizer(_ -> ccall((:mpopis_b200_destroy, LIB[]), Cint, (Ptr{Cvoid},), h), pol)
+        h
+    end
+end
+
+env_t(e) = Int64(hasproperty(e, :t) ? e.t : 0)
+
+# ---- depth (iii): the whole functor, mppi_mpopi_policies.jl:121-146 and 221-238 ------------------------------
+function plan!(pol::AbstractPathIntegralPolicy, env)
+    h = handle(pol, env)
+    control = Vector{Float64}(undef, pol.params.as)
+    its = Ref{Int32}(0)
+    s = Vector{Float64}(env.state)
+    GC.@preserve s control begin
+        check(ccall((:mpopis_b200_plan, LIB[]), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+            h, s, env_t(env), pol.U, control, its))      # pol.U is rolled in place (aliases params.U₀, App. B-2)
+    end
+    if pol.params.log
+        K, T, ss = pol.params.num_samples, pol.params.horizon, pol.params.ss
+        traj = Array{Float64}(undef, T, ss, K)
+        check(ccall((:mpopis_b200_fetch, LIB[]), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, pol.logger.traj_costs, pol.logger.traj_weights, C_NULL, traj))
+        for k in 1:K
+            pol.logger.trajectories[k] .= @view traj[:, :, k]
+        end
+    end
+    # get_model_controls returns a Vector for as == 1 and an as x 1 Matrix otherwise (utils.jl:63-66)
+    return pol.params.as == 1 ? control : reshape(control, :, 1)
+end
+
+# ---- depth (i): simulate_model with Julia's own noise E (exact same-seed drop-in, small K) --------------------
+function simulate_model_b200(pol::AbstractGMPPI_Policy, env, E::Matrix{Float64}, Σ_inv::Matrix{Float64},
+                             U_orig::Vector{Float64})
+    h = handle(pol, env)
+    costs = Vector{Float64}(undef, pol.params.num_samples)
+    s = Vector{Float64}(env.state)
+    check(ccall((:mpopis_b200_rollout_costs, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        h, s, env_t(env), pol.U, U_orig, E, Σ_inv, costs))
+    return costs
+end
+
+# ---- dispatch: enable!() defines the more specific methods -----------------------------------------------------
+"""
+    enable!(; depth = :functor)
+
+`depth = :functor` overrides `(pol)(env)` for CarRacingEnv / MultiCarRacingEnv / MountainCarEnv (whole control step
+on the GPU, engine RNG). `depth = :simulate_model` overrides only `simulate_model` (Julia keeps drawing `E` with
+`pol.rng`: bit-for-bit the same sampling as stock MPOPIS, costs from the GPU).
+"""
+function enable!(; depth::Symbol=:functor)
+    for Env in (CarRacingEnv, MultiCarRacingEnv, MountainCarEnv)
+        if depth == :functor
+            @eval (pol::AbstractGMPPI_Policy)(env::$Env) = plan!(pol, env)
+            @eval (pol::MPPI_Policy)(env::$Env) = plan!(pol, env)
+        elseif depth == :simulate_model
+            @eval MPOPIS.simulate_model(pol::AbstractGMPPI_Policy, env::$Env, E::Matrix{Float64},
+                                        Σ_inv::Matrix{Float64}, U_orig::Vector{Float64}) =
+                simulate_model_b200(pol, env, E, Σ_inv, U_orig)
+        else
+            error("depth must be :functor or :simulate_model")
+        end
+    end
+    nothing
+end
+
+end # module

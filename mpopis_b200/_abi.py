@@ -88,6 +88,7 @@ PRODUCT_ONLY = {
     "resident_total_its": (C.c_int, [_H, _I64]),
     "measure_fp64_peak": (C.c_int, [_H, _D]),
     "sortperm": (C.c_int, [_H, _D, C.c_int64, _I64]),
+    "bench_rowsum": (C.c_int, [_H, C.c_int32, _D, _D]),
     "launch_count": (C.c_int64, [_H]),
     "last_timing": (C.c_int, [_H, _D, _D, _I32]),
     "stream": (C.c_void_p, [_H]),

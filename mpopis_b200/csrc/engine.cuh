@@ -123,7 +123,10 @@ void launch_cma_vec(const double *dw, const double *C, const double *dvec, const
                     double *Sigma, const int *stop, cudaStream_t s);
 // sort.cu
 int sort_launches(int K);
-void launch_sortperm(const double *costs, int K, int m, unsigned long long *keys_a, unsigned long long *keys_b,
-                     int *order, int *vals_b, double *sorted_costs, const int *stop, cudaStream_t s);
+int sort_max_ctas(int num_sms);
+// returns a cudaError_t (cooperative launch); stop_flag != nullptr: also run the elite early-stop test
+int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsigned long long *keys_b, int *order,
+                    int *vals_b, int m, int early_stop, int *stop_flag, const int *stop, int max_ctas,
+                    cudaStream_t s);
 
 }  // namespace mpopis

@@ -95,7 +95,7 @@ struct mpopis_handle {
   double gamma = 0.0;
   uint64_t seed = 0;
   long long step = 0;
-  int rollout_variant = 0, rollout_block = 64, coop_max = 1;
+  int rollout_variant = 0, rollout_block = 64, coop_max = 1, sort_max = 1;
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
   bool L0_valid = false;
   mpopis_cma_t cma{};
@@ -262,20 +262,21 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     }
     launch_apply_L(Lt, cs, bs, h->d_Z, h->d_E, h->ldk, Kloc, stop, st);
     h->launches += 2;
+    // --- rollouts (POL:452 -> POL:261-278) ---
+    CU(cudaEventRecord(h->ev[2 + 2 * n], st));
+    if (int rc = launch_rollouts(h, h->d_U_cur, h->d_U_orig, bvec)) return rc;
+    CU(cudaEventRecord(h->ev[3 + 2 * n], st));
     if (!Z_host && n + 1 < N) {
       // The next iteration's normals depend on nothing but (seed, step, n+1): draw them on the side stream
-      // as soon as E = L Z has consumed the buffer, so they fill the SMs the latency-bound adaptation
-      // kernels (sort passes, Cholesky, moment finalisation) leave idle.
+      // while the latency-bound adaptation kernels (sort passes, Cholesky, moment finalisation) leave most
+      // SMs idle. They are released only AFTER the rollout kernel: both are FP64-issue bound, and letting
+      // them overlap slowed the rollouts by more than the 36 µs it hid (measured, profiles/README.md).
       CU(cudaEventRecord(h->ev_z_free, st));
       CU(cudaStreamWaitEvent(h->st2, h->ev_z_free, 0));
       launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, (uint32_t)h->step, (uint32_t)(n + 1), stop,
                             h->st2);
       CU(cudaEventRecord(h->ev_z_ready, h->st2));
     }
-    // --- rollouts (POL:452 -> POL:261-278) ---
-    CU(cudaEventRecord(h->ev[2 + 2 * n], st));
-    if (int rc = launch_rollouts(h, h->d_U_cur, h->d_U_orig, bvec)) return rc;
-    CU(cudaEventRecord(h->ev[3 + 2 * n], st));
     if (int rc = allgather_costs(h)) return rc;
     if (n == N - 1) break;
     // --- adaptation (the `if n < N` blocks) ---
@@ -305,12 +306,15 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       case MPOPIS_POLICY_CEMPPI:
       case MPOPIS_POLICY_CMAMPPI: {  // POL:455-465, 563-599
         const int m = h->m_elite;
-        launch_sortperm(h->d_costs, K, m, h->d_keys_a, h->d_keys_b, h->d_order, h->d_vals_b,
-                        h->d_sorted, stop, st);
-        launch_elite_stop(h->d_sorted, m, h->cfg.early_stop, stop, st);
+        {  // order = sortperm(costs) + the elite early-stop test (POL:455-461, 563-569)
+          const cudaError_t e = (cudaError_t)launch_sortperm(h->d_costs, K, h->d_keys_a, h->d_keys_b, h->d_order,
+                                                             h->d_vals_b, m, h->cfg.early_stop, stop, stop,
+                                                             h->sort_max, st);
+          if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+        }
         launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, m, h->k0, Kloc, h->d_X, h->ldm,
                            h->world > 1 ? h->d_mask : nullptr, stop, st);
-        h->launches += 2 + sort_launches(K);
+        h->launches += 1 + sort_launches(K);
         if (pol == MPOPIS_POLICY_CEMPPI) {
           if (int rc = moments(h, h->d_X, h->ldm, m, h->world > 1 ? h->d_mask : nullptr, true, 0,
                                h->cfg.sigma_est, 10e-9, true, nullptr, h->d_Sigma))
@@ -568,7 +572,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_sums, cs + 1));
   TRY(dalloc(&h->d_mu, cs));
   TRY(dalloc(&h->d_Sraw, cs * cs));
-  TRY(dalloc(&h->d_P, (size_t)66 * cs * cs));
+  TRY(dalloc(&h->d_P, (size_t)98 * cs * cs));  // <= 96 SYRK chunks (stats.cu: syrk_chunk)
   TRY(dalloc(&h->d_q, 1));
   TRY(dalloc(&h->d_lambda, 1));
   TRY(dalloc(&h->d_ones, 512));  // scratch of the multi-CTA weights kernels
@@ -602,6 +606,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   for (auto &e : h->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MPOPIS_ERR_CUDA, "cudaEventCreate failed"));
   h->coop_max = inv_sqrt_max_ctas(prop.multiProcessorCount);
+  h->sort_max = sort_max_ctas(prop.multiProcessorCount);
   {  // Σ defaults to the identity until set_sigma()
     std::vector<double> I(cs * cs, 0.0);
     for (size_t i = 0; i < cs; ++i) I[i * cs + i] = 1.0;
@@ -882,7 +887,11 @@ int mpopis_b200_sortperm(mpopis_t *h, const double *costs, int64_t K, int64_t *p
   if (int rc = dalloc(&vb, (size_t)K)) return rc;
   if (int rc = dalloc(&hist, 1)) return rc;
   CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
-  launch_sortperm(dc, (int)K, (int)K, ka, kb, ord, vb, ds, nullptr, h->st);
+  {
+    const cudaError_t e = (cudaError_t)launch_sortperm(dc, (int)K, ka, kb, ord, vb, 0, 0, nullptr, nullptr, h->sort_max,
+                                                       h->st);
+    if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  }
   h->launches += sort_launches((int)K);
   std::vector<int> tmp((size_t)K);
   CU(cudaMemcpyAsync(tmp.data(), ord, sizeof(int) * K, cudaMemcpyDeviceToHost, h->st));
@@ -1115,6 +1124,33 @@ int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out) {
   h->launches += 6;
   cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(out);
   *dfma_per_s_out = best;
+  return 0;
+}
+
+// Times the weighted row-sum kernel (G8: Σ_k w_k E[r,k], POL:226-229) alone over this handle's E operand.
+// It is the one HBM-bound kernel of the path; with num_samples = 2^20 the operand (839 MB) exceeds L2.
+int mpopis_b200_bench_rowsum(mpopis_t *h, int32_t reps, double *ms_per_launch_out, double *bytes_per_launch_out) {
+  if (!h || !ms_per_launch_out || reps < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (int rc = set_device(h)) return rc;
+  launch_philox_normals(h->d_E, h->ldk, h->cs, h->Kloc, h->k0, 1234u, 0u, 0u, nullptr, h->st);
+  CU(cudaMemsetAsync(h->d_costs, 0, sizeof(double) * h->K, h->st));
+  h->launches += 1 + launch_weights(h->d_costs, h->K, 1.0, h->d_w, h->d_ones, nullptr, h->st);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; ++i) launch_rowsum_partial(h->d_E, h->ldk, h->cs, h->Kloc, h->d_w + h->k0, h->d_part, nullptr, h->st);
+  CU(cudaEventRecord(e0, h->st));
+  for (int i = 0; i < reps; ++i)
+    launch_rowsum_partial(h->d_E, h->ldk, h->cs, h->Kloc, h->d_w + h->k0, h->d_part, nullptr, h->st);
+  CU(cudaEventRecord(e1, h->st));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  h->launches += reps + 2;
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  *ms_per_launch_out = ms / reps;
+  if (bytes_per_launch_out) *bytes_per_launch_out = 8.0 * h->cs * h->Kloc + 8.0 * h->Kloc;  // E rows + weights
   return 0;
 }
 

@@ -129,9 +129,13 @@ __device__ __forceinline__ bool within_track(const TrackView &tr, double px, dou
   }
   const int m1 = mi == 0 ? tr.n - 1 : mi - 1, p1 = mi == tr.n - 1 ? 0 : mi + 1;  // mod1, TRK:75-76
   const double ax = tr.x[m1] - px, ay = tr.y[m1] - py, bx = tr.x[p1] - px, by = tr.y[p1] - py;
-  const double dm1 = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));  // TRK:77
-  const double dp1 = __dsqrt_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)));  // TRK:78
-  const int m2 = dm1 <= dp1 ? m1 : p1;                                              // TRK:79
+  // TRK:77-79 compares norms: sqrt is monotone and correctly rounded, so the squared distances decide
+  // unless they are within a few ulps of each other — only then are the two square roots taken.
+  const double qa = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+  const double qb = __dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by));
+  int m2;
+  if (USE_LUT && fabs(qa - qb) > 1e-14 * fmax(qa, qb)) m2 = qa < qb ? m1 : p1;
+  else m2 = __dsqrt_rn(qa) <= __dsqrt_rn(qb) ? m1 : p1;
   const double p1x = tr.x[mi], p1y = tr.y[mi];
   const double vx = tr.x[m2] - p1x, vy = tr.y[m2] - p1y, ux = px - p1x, uy = py - p1y;
   const double t = (ux * vx + uy * vy) / (vx * vx + vy * vy);  // TRK:87 (projection on the infinite line)
@@ -170,6 +174,32 @@ __device__ __forceinline__ TireConsts tire_consts(const CarParams &P, double acc
   c.c2_r = (P.C_ar * P.C_ar) / (3 * c.fymax_r);
   c.c3_f = (P.C_af * P.C_af * P.C_af) / (27 * (c.fymax_f * c.fymax_f));
   c.c3_r = (P.C_ar * P.C_ar * P.C_ar) / (27 * (c.fymax_r * c.fymax_r));
+  return c;
+}
+
+// Same constants with one rsqrt per tyre instead of a sqrt and three divisions (fast v3): with
+// v = max((μ fz)² − fx², 1e-8): fy_max = v·rsqrt(v), 1/fy_max = rsqrt(v); divisions by the car's constants
+// become multiplications by their reciprocals (loop-invariant, hoisted by the compiler).
+__device__ __forceinline__ TireConsts tire_consts_fast(const CarParams &P, double accel, double bk,
+                                                       double split, double sgnVx) {
+  TireConsts c;
+  const double fx = accel + bk * sgnVx;  // CAR:310-312
+  c.fxf = split * fx;
+  c.fxr = (1 - split) * fx;
+  const double invL = 1.0 / (P.l_r + P.l_f);
+  const double fzf = (P.m * P.l_r * 9.81 - P.h_cm * fx) * invL;
+  const double fzr = (P.m * P.l_f * 9.81 + P.h_cm * fx) * invL;
+  const double vf = fmax((P.mu_f * fzf) * (P.mu_f * fzf) - c.fxf * c.fxf, 1e-8);
+  const double vr = fmax((P.mu_r * fzr) * (P.mu_r * fzr) - c.fxr * c.fxr, 1e-8);
+  const double rf = rsqrt(vf), rr = rsqrt(vr);
+  c.fymax_f = vf * rf;
+  c.fymax_r = vr * rr;
+  c.thr_f = c.fymax_f * (3.0 / P.C_af);
+  c.thr_r = c.fymax_r * (3.0 / P.C_ar);
+  c.c2_f = (P.C_af * P.C_af / 3.0) * rf;
+  c.c2_r = (P.C_ar * P.C_ar / 3.0) * rr;
+  c.c3_f = (P.C_af * P.C_af * P.C_af / 27.0) * (rf * rf);
+  c.c3_r = (P.C_ar * P.C_ar * P.C_ar / 27.0) * (rr * rr);
   return c;
 }
 
@@ -293,7 +323,7 @@ __device__ __forceinline__ void car_step_fast(const CarParams &P, double dt, dou
   const double split = pedal <= 0.0 ? P.l_brake : P.l_drive;
   const double inv_Izz = 1 / P.Izz, inv_m = 1 / P.m;
   double sg = jl_sign(Vx);
-  TireConsts tc = tire_consts(P, accel, bk, split, sg);
+  TireConsts tc = tire_consts_fast(P, accel, bk, split, sg);
   const double dlt = rate * ddt;
   const bool small = fmax(fabs(delta), fabs(a0 * P.d_max)) <= 0.78;
   double sd, cd, sdl = 0.0, cdl = 1.0;
@@ -326,25 +356,28 @@ __device__ __forceinline__ void car_step_fast(const CarParams &P, double dt, dou
       if (den > 0.0) {
         const double dv = den * Vx;
         double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dv));
-        r = fma(fma(-dv, r, 1.0), r, r);
-        r = fma(fma(-dv, r, 1.0), r, r);
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dv));  // 2^-23 seed
+        const double e = fma(-dv, r, 1.0);
+        r = fma(r, fma(e, e, e), r);                             // r(1 + e + e²): error e³ = 2^-69
         const double ta = (num * Vx) * r;
         ta_r = (yr * den) * r;
-        const double cubic = -P.C_af * ta + tc.c2_f * fabs(ta) * ta - tc.c3_f * (ta * ta * ta);
-        fyf = fabs(ta) < tc.thr_f ? cubic : copysign(tc.fymax_f, -num);  // CAR:255-259
+        // −C t + c2 |t| t − c3 t³ = t·(−C + |t|·(c2 − c3 |t|))   (CAR:256, Horner form)
+        const double at = fabs(ta);
+        const double cubic = ta * fma(at, fma(-tc.c3_f, at, tc.c2_f), -P.C_af);
+        fyf = at < tc.thr_f ? cubic : copysign(tc.fymax_f, -num);  // CAR:255-259
       } else {  // |α_f| >= 90°: saturated
         fyf = copysign(tc.fymax_f, -num);
         ta_r = fast_div(yr, Vx);
       }
-      const double cubic_r = -P.C_ar * ta_r + tc.c2_r * fabs(ta_r) * ta_r - tc.c3_r * (ta_r * ta_r * ta_r);
-      fyr = fabs(ta_r) < tc.thr_r ? cubic_r : copysign(tc.fymax_r, -yr);
+      const double atr = fabs(ta_r);
+      const double cubic_r = ta_r * fma(atr, fma(-tc.c3_r, atr, tc.c2_r), -P.C_ar);
+      fyr = atr < tc.thr_r ? cubic_r : copysign(tc.fymax_r, -yr);
       fx_aero = P.C_D0 + P.C_D1 * Vx;  // CAR:308 with sign(Vx) = 1
     } else {
       const double sg_now = jl_sign(Vx);
       if (sg_now != sg) {  // sign(Vx) flipped: brake force changes direction
         sg = sg_now;
-        if (bk != 0.0) tc = tire_consts(P, accel, bk, split, sg);
+        if (bk != 0.0) tc = tire_consts_fast(P, accel, bk, split, sg);
       }
       if (Vx > 0.0) {
         fyf = tire_fy_ratio<0>(yf * cd - Vx * sd, Vx * cd + yf * sd, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);

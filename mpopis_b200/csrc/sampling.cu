@@ -92,7 +92,11 @@ __global__ void __launch_bounds__(256) apply_L_block_kernel(const double *Lt, in
 // (Lt carries explicit zeros above the diagonal), so the triangle costs ~half a square GEMM.
 // FP64 has no tcgen05 kind and DMMA (mma.sync m8n8k4) has the same peak as the DFMA pipe on B200, so
 // this stays on the FMA pipe.
-constexpr int AL_BM = 32, AL_BN = 128, AL_BJ = 16;
+// Round-1 ncu (profiles/): with the 4 x 4 register tile the kernel is bound by shared-memory wavefronts
+// (67 % of peak, FP64 36 %) because every warp re-reads the Z slab. A 4 x 8 tile (AL_BN = 256) halves the Z
+// wavefronts per FMA but measured SLOWER (153 vs 112 µs: register pressure cuts the resident warps), so the
+// 4 x 4 tile stays.
+constexpr int AL_BM = 32, AL_BN = 128, AL_BJ = 16, AL_NB = AL_BN / 64;  // AL_NB pairs of samples per thread
 __global__ void __launch_bounds__(256) apply_L_dense_kernel(const double *__restrict__ Lt, int cs,
                                                              const double *__restrict__ Z,
                                                              double *__restrict__ E, long long ldk, int K,
@@ -102,11 +106,11 @@ __global__ void __launch_bounds__(256) apply_L_dense_kernel(const double *__rest
   __shared__ __align__(16) double Zs[AL_BJ][AL_BN];  // Zs[j][k]
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty: 0..7
   const int kbase = blockIdx.x * AL_BN, i0 = blockIdx.y * AL_BM;
-  double acc[4][4];
+  double acc[4][2 * AL_NB];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int b = 0; b < 2 * AL_NB; ++b) acc[a][b] = 0.0;
   const int jend = min(i0 + AL_BM, cs);
   for (int jc = 0; jc < jend; jc += AL_BJ) {
     __syncthreads();
@@ -125,14 +129,18 @@ __global__ void __launch_bounds__(256) apply_L_dense_kernel(const double *__rest
     for (int jj = 0; jj < AL_BJ; ++jj) {
       const double2 l01 = *reinterpret_cast<const double2 *>(&Ls[jj][ty * 4]);
       const double2 l23 = *reinterpret_cast<const double2 *>(&Ls[jj][ty * 4 + 2]);
-      // samples {2tx, 2tx+1} and {64+2tx, 64+2tx+1}: consecutive lanes read consecutive 16-byte words
-      const double2 z01 = *reinterpret_cast<const double2 *>(&Zs[jj][tx * 2]);
-      const double2 z23 = *reinterpret_cast<const double2 *>(&Zs[jj][64 + tx * 2]);
-      const double l[4] = {l01.x, l01.y, l23.x, l23.y}, z[4] = {z01.x, z01.y, z23.x, z23.y};
+      // samples {64q + 2tx, 64q + 2tx + 1}: consecutive lanes read consecutive 16-byte words
+      const double l[4] = {l01.x, l01.y, l23.x, l23.y};
+      double z[2 * AL_NB];
+#pragma unroll
+      for (int q = 0; q < AL_NB; ++q) {
+        const double2 zz = *reinterpret_cast<const double2 *>(&Zs[jj][64 * q + tx * 2]);
+        z[2 * q] = zz.x, z[2 * q + 1] = zz.y;
+      }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(l[a], z[b], acc[a][b]);
+        for (int b = 0; b < 2 * AL_NB; ++b) acc[a][b] = fma(l[a], z[b], acc[a][b]);
     }
   }
 #pragma unroll
@@ -140,11 +148,11 @@ __global__ void __launch_bounds__(256) apply_L_dense_kernel(const double *__rest
     const int i = i0 + ty * 4 + a;
     if (i >= cs) continue;
 #pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-      const int k = kbase + 64 * hlf + tx * 2;
+    for (int q = 0; q < AL_NB; ++q) {
+      const int k = kbase + 64 * q + tx * 2;
       double *dst = E + (size_t)i * ldk + k;
-      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[a][2 * hlf], acc[a][2 * hlf + 1]);
-      else if (k < K) dst[0] = acc[a][2 * hlf];
+      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[a][2 * q], acc[a][2 * q + 1]);
+      else if (k < K) dst[0] = acc[a][2 * q];
     }
   }
 }

@@ -8,7 +8,11 @@
 // log2(K/2048) merge-path passes merge runs pairwise with every CTA producing one 2048-key output
 // tile (6 launches at K = 65 536; round 1 started with a 26-launch LSD radix sort — see
 // profiles/README.md for the before/after).
+#include <cooperative_groups.h>
+
 #include "engine.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mpopis {
 
@@ -89,16 +93,12 @@ __device__ __forceinline__ int merge_path_warp(const unsigned long long *ak, con
   return lo;
 }
 
-// One merge pass: sorted runs of length L are merged pairwise; CTA b writes output tile b.
-__global__ void __launch_bounds__(256) merge_pass_kernel(const unsigned long long *__restrict__ kin,
-                                                          const int *__restrict__ vin, int n, int L,
-                                                          unsigned long long *__restrict__ kout,
-                                                          int *__restrict__ vout, const int *stop) {
-  if (stop && *stop) return;
-  __shared__ unsigned long long sk[TILE];
-  __shared__ int sv[TILE];
-  __shared__ int sa[2];
-  const int out0 = blockIdx.x * TILE;
+// Merges the pair of sorted runs (length L) that contains output tile `tile` and writes that tile.
+__device__ __forceinline__ void merge_tile(const unsigned long long *__restrict__ kin, const int *__restrict__ vin,
+                                           int n, int L, unsigned long long *__restrict__ kout,
+                                           int *__restrict__ vout, int tile, unsigned long long *sk, int *sv,
+                                           int *sa) {
+  const int out0 = tile * TILE;
   const int pair_base = (out0 / (2 * L)) * (2 * L);
   const int na = min(L, n - pair_base), nb = max(0, min(L, n - pair_base - L));
   const unsigned long long *ak = kin + pair_base, *bk = kin + pair_base + L;
@@ -133,28 +133,60 @@ __global__ void __launch_bounds__(256) merge_pass_kernel(const unsigned long lon
   }
 }
 
-__global__ void sorted_costs_kernel(const unsigned long long *__restrict__ keys, int m, double *__restrict__ out,
-                                    const int *stop) {
-  if (stop && *stop) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  unsigned long long b = keys[i];
+__device__ __forceinline__ double cost_of(unsigned long long b) {
   b = (b >> 63) ? (b & 0x7fffffffffffffffULL) : ~b;
-  out[i] = __longlong_as_double((long long)b);
+  return __longlong_as_double((long long)b);
+}
+
+// All merge passes in ONE cooperative kernel (grid-wide barrier between passes) followed by the elite
+// early-stop test maximum(abs.(diff(elite_traj_cost))) < 10e-3 (POL:458-461, 566-569) on the sorted keys:
+// K = 65 536 needs 5 passes, which as separate launches cost 5 x 12 µs of mostly launch/drain latency.
+__global__ void __launch_bounds__(256) merge_all_kernel(unsigned long long *kin, int *vin, unsigned long long *kout,
+                                                         int *vout, int n, int m, int early_stop, int *stop_flag,
+                                                         const int *stop) {
+  if (stop && *stop) return;  // grid-uniform
+  cg::grid_group grid = cg::this_grid();
+  __shared__ unsigned long long sk[TILE];
+  __shared__ int sv[TILE];
+  __shared__ int sa[2];
+  __shared__ double red[8];
+  const int ntiles = (n + TILE - 1) / TILE;
+  for (long long L = TILE; L < n; L <<= 1) {
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      __syncthreads();
+      merge_tile(kin, vin, n, (int)L, kout, vout, t, sk, sv, sa);
+    }
+    grid.sync();
+    unsigned long long *tk = kin;
+    kin = kout, kout = tk;
+    int *tv = vin;
+    vin = vout, vout = tv;
+  }
+  if (blockIdx.x == 0 && stop_flag && m > 1) {
+    double mx = -1.0;
+    for (int j = threadIdx.x; j + 1 < m; j += 256) mx = fmax(mx, fabs(cost_of(kin[j + 1]) - cost_of(kin[j])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+      if (early_stop && mx < 10e-3) *stop_flag = 1;
+    }
+  }
 }
 
 }  // namespace
 
-int sort_launches(int K) {
-  int passes = 0;
-  for (long long L = TILE; L < K; L <<= 1) ++passes;
-  return 2 + passes;
-}
+int sort_launches(int K) { return 2; }
 
-// Sorts costs[0:K]; on return `order` holds the stable ascending permutation (0-based sample ids)
-// and sorted_costs[0:m] the m smallest costs in order. keys_a/keys_b, vals_b: scratch of K entries.
-void launch_sortperm(const double *costs, int K, int m, unsigned long long *keys_a, unsigned long long *keys_b,
-                     int *order, int *vals_b, double *sorted_costs, const int *stop, cudaStream_t s) {
+// Sorts costs[0:K]; on return `order` holds the stable ascending permutation (0-based sample ids).
+// keys_a/keys_b, vals_b: scratch of K entries. With stop_flag != nullptr the kernel also evaluates the elite
+// early-stop test on the m smallest costs and raises *stop_flag. max_ctas: co-resident CTA budget of the
+// cooperative merge kernel. Returns a cudaError_t.
+int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsigned long long *keys_b, int *order,
+                    int *vals_b, int m, int early_stop, int *stop_flag, const int *stop, int max_ctas,
+                    cudaStream_t s) {
   const int ntiles = (K + TILE - 1) / TILE;
   int passes = 0;
   for (long long L = TILE; L < K; L <<= 1) ++passes;
@@ -162,14 +194,18 @@ void launch_sortperm(const double *costs, int K, int m, unsigned long long *keys
   unsigned long long *kin = (passes & 1) ? keys_b : keys_a, *kout = (passes & 1) ? keys_a : keys_b;
   int *vin = (passes & 1) ? vals_b : order, *vout = (passes & 1) ? order : vals_b;
   tile_sort_kernel<<<ntiles, 1024, 0, s>>>(costs, K, kin, vin, stop);
-  for (long long L = TILE; L < K; L <<= 1) {
-    merge_pass_kernel<<<ntiles, 256, 0, s>>>(kin, vin, K, (int)L, kout, vout, stop);
-    unsigned long long *tk = kin;
-    kin = kout, kout = tk;
-    int *tv = vin;
-    vin = vout, vout = tv;
-  }
-  sorted_costs_kernel<<<(m + 255) / 256, 256, 0, s>>>(kin, m, sorted_costs, stop);
+  int grid = ntiles < max_ctas ? ntiles : max_ctas;
+  if (grid < 1) grid = 1;
+  void *args[] = {(void *)&kin, (void *)&vin, (void *)&kout, (void *)&vout, (void *)&K,
+                  (void *)&m,   (void *)&early_stop, (void *)&stop_flag, (void *)&stop};
+  return (int)cudaLaunchCooperativeKernel((const void *)merge_all_kernel, dim3(grid), dim3(256), args, 0, s);
+}
+
+int sort_max_ctas(int num_sms) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_all_kernel, 256, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  return per_sm * num_sms;
 }
 
 }  // namespace mpopis

@@ -245,6 +245,11 @@ class Engine:
         self._chk(self.b.measure_fp64_peak(self.h, C.byref(v)))
         return v.value
 
+    def bench_rowsum(self, reps=20):
+        ms, nbytes = C.c_double(0.0), C.c_double(0.0)
+        self._chk(self.b.bench_rowsum(self.h, int(reps), C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value
+
     def sortperm(self, costs):
         c = _f64(costs)
         out = np.zeros(c.size, dtype=np.int64)
