@@ -213,6 +213,8 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   cudaStream_t st = h->st;
   if (!h->env_set) return fail(MPOPIS_ERR_BAD_ARG, "environment not set");
   if (pol == MPOPIS_POLICY_CMAMPPI && !h->cma_set) return fail(MPOPIS_ERR_BAD_ARG, "CMA constants not set");
+  if (pol == MPOPIS_POLICY_CMAMPPI && N > 1 && (long long)cs * h->m_elite < K)  // δs[order[ii]] out of bounds
+    return fail(MPOPIS_ERR_BAD_ARG, "BoundsError: CMA linear index exceeds cs*m_elite (POL:593)");
   if (pol == MPOPIS_POLICY_PMCMPPI && N > 1 && Z_host && !u_host)
     return fail(MPOPIS_ERR_BAD_ARG, "pmcmppi with injected noise needs resample_u");
   CU(cudaEventRecord(h->ev[0], st));
@@ -744,8 +746,6 @@ int mpopis_b200_set_cma(mpopis_t *h, const mpopis_cma_t *cma, const double *ws, 
   if (h->cfg.policy != MPOPIS_POLICY_CMAMPPI) return fail(MPOPIS_ERR_BAD_ARG, "not a :cmamppi handle");
   if (n_ws != h->K) return fail(MPOPIS_ERR_BAD_ARG, "ws must have num_samples entries");
   if (h->N > 1 && (cma->m_elite < 2 || cma->m_elite > h->K)) return fail(MPOPIS_ERR_BAD_ARG, "m_elite out of range");
-  if (h->N > 1 && (long long)h->cs * cma->m_elite < h->K)
-    return fail(MPOPIS_ERR_BAD_ARG, "BoundsError: CMA linear index exceeds cs*m_elite (POL:593)");
   if (int rc = set_device(h)) return rc;
   h->cma = *cma;
   h->m_elite = (int)cma->m_elite;

@@ -7,6 +7,8 @@
 // purpose<<24, control-step counter), Box–Muller in FP64. Because the counter is the GLOBAL
 // sample index, the draws are independent of how K is sharded across GPUs. oracle/ restates the
 // same generator (tests compare them to ~1e-15).
+#include <cstdlib>
+
 #include "engine.cuh"
 
 namespace mpopis {
@@ -157,11 +159,91 @@ __global__ void __launch_bounds__(256) apply_L_dense_kernel(const double *__rest
   }
 }
 
+// The same contraction on the FP64 tensor cores: mma.sync.m8n8k4.f64 (SASS: DMMA). FP64 has no tcgen05
+// kind, so this warp-level MMA is the tensor path that exists for doubles; on B200 its peak is ~1.3x the
+// DFMA pipe, and — what matters here — one instruction performs 256 FMAs from 2+2 register operands per
+// lane, i.e. 8x less shared-memory traffic per FMA than the 4x4 register tile above (which ncu showed bound
+// by shared-memory wavefronts). CTA = 4 warps, tile = 32 rows x 128 samples (32 samples per warp, 4 x 4
+// accumulator fragments); row fragments beyond cs are skipped, so the triangle is followed at 8-row
+// granularity. Fragment layouts (PTX ISA, m8n8k4 .f64): A[g][t], B[t][g], C[g][2t..2t+1] with g = lane/4,
+// t = lane%4. Shared pitches 20 and 136 doubles make every fragment load 2 wavefronts (the minimum).
+constexpr int DM_BM = 32, DM_BN = 128, DM_BJ = 16, DM_LP = 20, DM_ZP = 136;
+__global__ void __launch_bounds__(128) apply_L_dmma_kernel(const double *__restrict__ Lt, int cs,
+                                                            const double *__restrict__ Z, double *__restrict__ E,
+                                                            long long ldk, int K, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double Ls[DM_BM][DM_LP];
+  __shared__ double Zs[DM_BJ][DM_ZP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int kbase = blockIdx.x * DM_BN, i0 = blockIdx.y * DM_BM;
+  const int nrf = min(4, (cs - i0 + 7) / 8);  // row fragments that contain rows < cs
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int jend = min(i0 + DM_BM, cs);
+  for (int jc = 0; jc < jend; jc += DM_BJ) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < DM_BM * DM_BJ; e += 128) {
+      const int ii = e / DM_BJ, jj = e % DM_BJ;
+      const int i = i0 + ii, j = jc + jj;
+      Ls[ii][jj] = (i < cs && j < cs) ? __ldg(Lt + (size_t)i * cs + j) : 0.0;
+    }
+    for (int e = threadIdx.x; e < DM_BJ * DM_BN; e += 128) {
+      const int jj = e / DM_BN, kk = e % DM_BN;
+      const int j = jc + jj, kg = kbase + kk;
+      Zs[jj][kk] = (j < cs && kg < K) ? Z[(size_t)j * ldk + kg] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j4 = 0; j4 < DM_BJ; j4 += 4) {
+      double bf[4];
+#pragma unroll
+      for (int cf = 0; cf < 4; ++cf) bf[cf] = Zs[j4 + t][w * 32 + cf * 8 + g];
+#pragma unroll
+      for (int rf = 0; rf < 4; ++rf) {
+        if (rf >= nrf) break;
+        const double af = Ls[rf * 8 + g][j4 + t];
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[rf][cf][0]), "+d"(acc[rf][cf][1])
+                       : "d"(af), "d"(bf[cf]));
+      }
+    }
+  }
+#pragma unroll
+  for (int rf = 0; rf < 4; ++rf) {
+    const int i = i0 + rf * 8 + g;
+    if (rf >= nrf || i >= cs) continue;
+#pragma unroll
+    for (int cf = 0; cf < 4; ++cf) {
+      const int k = kbase + w * 32 + cf * 8 + 2 * t;
+      double *dst = E + (size_t)i * ldk + k;
+      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[rf][cf][0], acc[rf][cf][1]);
+      else if (k < K) dst[0] = acc[rf][cf][0];
+    }
+  }
+}
+
+static int apply_L_path() {  // MPOPIS_APPLY_L=fma selects the DFMA kernel (A/B evidence, profiles/)
+  static int path = -1;
+  if (path < 0) {
+    const char *e = getenv("MPOPIS_APPLY_L");
+    path = (e && e[0] == 'f') ? 0 : 1;
+  }
+  return path;
+}
+
 void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E, long long ldk, int K,
                     const int *stop, cudaStream_t s) {
   if (bs < cs) {
     dim3 grid((K + 255) / 256, cs);
     apply_L_block_kernel<<<grid, 256, 0, s>>>(Lt, cs, bs, Z, E, ldk, K, stop);
+  } else if (apply_L_path() == 1) {
+    dim3 grid((K + DM_BN - 1) / DM_BN, (cs + DM_BM - 1) / DM_BM);
+    apply_L_dmma_kernel<<<grid, 128, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);
   } else {
     dim3 grid((K + AL_BN - 1) / AL_BN, (cs + AL_BM - 1) / AL_BM);
     apply_L_dense_kernel<<<grid, 256, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);

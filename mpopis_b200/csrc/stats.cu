@@ -14,6 +14,8 @@
 // inside a control step.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "engine.cuh"
 
 namespace mpopis {
@@ -282,11 +284,96 @@ int syrk_nchunks(int n) {
   return (n + ch - 1) / ch;
 }
 
+// The same scatter tile on the FP64 tensor cores (mma.sync.m8n8k4.f64 -> SASS DMMA): the Σ outer-product
+// update is the contraction BASELINE.json's north star reserves the tensor cores for. 4 warps per CTA, each
+// owning a 32 x 32 quadrant of the 64 x 64 tile as 4 x 4 accumulator fragments; slabs of 16 samples are
+// staged row-major with a pitch of 20 doubles, so the A fragment As[g][t] and the B fragment Bs[g][t]
+// (B is "column-major k x j", i.e. the row-major centred data itself) load conflict-free.
+constexpr int SD_P = 20;
+__global__ void __launch_bounds__(128) syrk_dmma_kernel(const double *__restrict__ X, long long ld, int p, int n,
+                                                         const double *__restrict__ w,
+                                                         const double *__restrict__ mu, int chunk,
+                                                         double *__restrict__ P, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double As[SY_T][SD_P], Bs[SY_T][SD_P];  // [row][sample]
+  int tt = blockIdx.x, bi = 0;  // decode the lower-triangular tile index
+  while (tt > bi) tt -= bi + 1, ++bi;
+  const int bj = tt;
+  const int c = blockIdx.y;
+  const int kbeg = c * chunk, kend = min(n, kbeg + chunk);
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int wi = (wq >> 1) * 32, wj = (wq & 1) * 32;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  // staging: thread -> sample kk0 = tid % 16 and rows rr0 + 8 q (q < 8); next slab prefetched into registers
+  const int kk0 = threadIdx.x & 15, rr0 = threadIdx.x >> 4;
+  double ra[8], rb[8];
+  auto fetch = [&](int k0) {
+    const int k = k0 + kk0;
+    const bool ok = k < kend;
+    const double wk = ok ? (w ? w[k] : 1.0) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ia = bi * SY_T + rr0 + 8 * q, ib = bj * SY_T + rr0 + 8 * q;
+      ra[q] = (ok && ia < p) ? wk * (X[(size_t)ia * ld + k] - mu[ia]) : 0.0;
+      rb[q] = (ok && ib < p) ? (X[(size_t)ib * ld + k] - mu[ib]) : 0.0;
+    }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += SY_K) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) As[rr0 + 8 * q][kk0] = ra[q], Bs[rr0 + 8 * q][kk0] = rb[q];
+    __syncthreads();
+    if (k0 + SY_K < kend) fetch(k0 + SY_K);
+#pragma unroll
+    for (int k4 = 0; k4 < SY_K; k4 += 4) {
+      double bf[4];
+#pragma unroll
+      for (int cf = 0; cf < 4; ++cf) bf[cf] = Bs[wj + cf * 8 + g][k4 + t];
+#pragma unroll
+      for (int rf = 0; rf < 4; ++rf) {
+        const double af = As[wi + rf * 8 + g][k4 + t];
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[rf][cf][0]), "+d"(acc[rf][cf][1])
+                       : "d"(af), "d"(bf[cf]));
+      }
+    }
+  }
+  double *Pc = P + (size_t)c * p * p;
+#pragma unroll
+  for (int rf = 0; rf < 4; ++rf) {
+    const int i = bi * SY_T + wi + rf * 8 + g;
+    if (i >= p) continue;
+#pragma unroll
+    for (int cf = 0; cf < 4; ++cf) {
+      const int j = bj * SY_T + wj + cf * 8 + 2 * t;
+      if (j < p) Pc[(size_t)i * p + j] = acc[rf][cf][0];
+      if (j + 1 < p) Pc[(size_t)i * p + j + 1] = acc[rf][cf][1];
+    }
+  }
+}
+
+static int syrk_path() {  // MPOPIS_SYRK=fma selects the DFMA kernel (A/B evidence, profiles/)
+  static int path = -1;
+  if (path < 0) {
+    const char *e = getenv("MPOPIS_SYRK");
+    path = (e && e[0] == 'f') ? 0 : 1;
+  }
+  return path;
+}
+
 void launch_syrk_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
                          double *P, const int *stop, cudaStream_t s) {
   const int nt = (p + SY_T - 1) / SY_T;
   dim3 grid(nt * (nt + 1) / 2, syrk_nchunks(n));
-  syrk_partial_kernel<<<grid, 256, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop);
+  if (syrk_path() == 1) syrk_dmma_kernel<<<grid, 128, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop);
+  else syrk_partial_kernel<<<grid, 256, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop);
 }
 
 // S[i][j] (lower, i >= j) = Σ_c P[c][i][j] in chunk order; raw scatter sums, mirrored to full storage.
