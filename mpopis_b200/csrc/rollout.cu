@@ -338,6 +338,9 @@ __device__ __forceinline__ void car_step_fast(const CarParams &P, double dt, dou
   }
   double sp, cp;
   sincos_pi(psi, &sp, &cp);
+  // ncu: the dominant stall is "wait" (fixed-latency FP64 dependencies) at ~3 warps per scheduler; unrolling
+  // by two lets the scheduler overlap the position/heading tail of one sub-step with the next tyre chain.
+#pragma unroll 2
   for (int i = 0; i < nsub; ++i) {
     delta += dlt;  // CAR:301
     if (small) {
@@ -475,12 +478,22 @@ __global__ void __launch_bounds__(128) rollout_car_kernel(const __grid_constant_
   for (int q = 0; q < SS; ++q) s[q] = __ldg(a.state0 + q);
   const double *Ek = a.E + k;
   double cost = 0.0, cc = 0.0;
+  // the noise of step t+1 is fetched while step t integrates (ncu: long-scoreboard stalls on these loads)
+  double e_next[AS];
+#pragma unroll
+  for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)r * a.ldk];
   for (int t = 0; t < a.T; ++t) {
-    double act[AS];
+    double act[AS], e_cur[AS];
+#pragma unroll
+    for (int r = 0; r < AS; ++r) e_cur[r] = e_next[r];
+    if (t + 1 < a.T) {
+#pragma unroll
+      for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)((t + 1) * AS + r) * a.ldk];
+    }
 #pragma unroll
     for (int r = 0; r < AS; ++r) {
       const int row = t * AS + r;
-      const double v = __ldg(a.U + row) + Ek[(size_t)row * a.ldk];  // Vₖ = pol.U + E[:,k], POL:271
+      const double v = __ldg(a.U + row) + e_cur[r];  // Vₖ = pol.U + E[:,k], POL:271
       if (a.bvec) cc += __ldg(a.bvec + row) * (v - __ldg(a.U_orig + row));  // POL:272
       act[r] = clamp1(v);                                                   // UTL:55-67
     }

@@ -480,12 +480,16 @@ __global__ void __launch_bounds__(1024) cov_finalize_kernel(const double *__rest
     double q = 0.0, r2 = 0.0;
     for (int c = threadIdx.x; c < nq; c += blockDim.x) q += qpart[c];
     q = block_reduce<0>(q, red);
-    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
-      const int i = e / p, j = e % p;
-      if (i == j) continue;
-      double v = Sraw[e] * inv;
-      if (ss) v = v * (1.0 / sqrt(Sraw[(size_t)i * p + i] * inv)) * (1.0 / sqrt(Sraw[(size_t)j * p + j] * inv));
-      r2 = fma(v, v, r2);
+    extern __shared__ double dinv[];  // p entries: 1/σ_i (:ss) or 1 (:lw)
+    for (int i = threadIdx.x; i < p; i += blockDim.x) dinv[i] = ss ? 1.0 / sqrt(Sraw[(size_t)i * p + i] * inv) : 1.0;
+    __syncthreads();
+    for (int i = threadIdx.x >> 5; i < p; i += blockDim.x >> 5) {  // one warp per row: no integer divisions
+      const double di = dinv[i] * inv;
+      for (int j = threadIdx.x & 31; j < p; j += 32) {
+        if (i == j) continue;
+        const double v = Sraw[(size_t)i * p + j] * di * dinv[j];
+        r2 = fma(v, v, r2);
+      }
     }
     r2 = block_reduce<0>(r2, red);
     const double n = cnt;
@@ -512,19 +516,19 @@ __global__ void __launch_bounds__(1024) cov_finalize_kernel(const double *__rest
     if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
     return;
   }
-  for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
-    const bool dg = e / p == e % p;
-    const double v = Sraw[e] * inv;
-    Sigma[e] = dg ? v + ridge : (1.0 - lam) * v;
-  }
+  for (int i = threadIdx.x >> 5; i < p; i += blockDim.x >> 5)
+    for (int j = threadIdx.x & 31; j < p; j += 32) {
+      const double v = Sraw[(size_t)i * p + j] * inv;
+      Sigma[(size_t)i * p + j] = i == j ? v + ridge : (1.0 - lam) * v;
+    }
   if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
 }
 
 void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int corrected, int method,
                          const double *qpart, int nq, double ridge, double *Sigma, double *lambda_out,
                          const int *stop, cudaStream_t s) {
-  cov_finalize_kernel<<<1, 1024, 0, s>>>(Sraw, p, cnt_dev, corrected, method, qpart, nq, ridge, Sigma,
-                                         lambda_out, stop);
+  cov_finalize_kernel<<<1, 1024, sizeof(double) * p, s>>>(Sraw, p, cnt_dev, corrected, method, qpart, nq, ridge,
+                                                          Sigma, lambda_out, stop);
 }
 
 // ---- G4: elite gather + early-stop test ---------------------------------------------------------
