@@ -80,24 +80,26 @@ void launch_transpose_out(const double *dev, double *colmajor, int cs, int K, lo
 int launch_weights(const double *costs, int K, double lambda, double *w, double *scratch, const int *stop,
                    cudaStream_t s);
 int rowsum_nchunks(int n);
+// n_dev (nullable): device-side column count, n_eff = min(n, *n_dev); grids are sized for n
 void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
-                           const int *stop, cudaStream_t s);
+                           const int *stop, cudaStream_t s, const int *n_dev = nullptr);
 void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop, cudaStream_t s);
 void launch_finalize_mean(const double *sums, int rows, double *mu, double *U, const double *scale_dev,
                           const int *stop, cudaStream_t s);
 int syrk_nchunks(int n);
 void launch_syrk_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu, double *P,
-                         const int *stop, cudaStream_t s);
+                         const int *stop, cudaStream_t s, const int *n_dev = nullptr);
 void launch_scatter_reduce(const double *P, int nchunks, int p, double *S, const int *stop, cudaStream_t s);
 int shrink_q_nblocks(int n);
 void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
                              const double *Sraw, const double *cnt_dev, int standardise, double *partial,
-                             const int *stop, cudaStream_t s);
+                             const int *stop, cudaStream_t s, const int *n_dev = nullptr);
 void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int corrected, int method,
                          const double *qpart, int nq, double ridge, double *Sigma, double *lambda_out,
                          const int *stop, cudaStream_t s);
 void launch_gather_cols(const double *E, long long ldk, int cs, const int *order, int m, long long k0, int Kloc,
-                        double *X, long long ldx, double *mask, const int *stop, cudaStream_t s);
+                        double *X, long long ldx, double *mask, const int *stop, cudaStream_t s,
+                        const int *m_dev = nullptr);
 void launch_elite_stop(const double *sorted_costs, int m, int enabled, int *stop, cudaStream_t s);
 void launch_iter_begin(const int *stop, int *its, int *total_its, cudaStream_t s);
 void launch_pmc_counts(const double *wglobal, int K, const double *u, double *cdf, int *counts, long long k0,
@@ -124,6 +126,9 @@ void launch_cma_vec(const double *dw, const double *C, const double *dvec, const
 // sort.cu
 int sort_launches(int K);
 int sort_max_ctas(int num_sms);
+void launch_global_rank(const unsigned long long *runs_k, const int *runs_v, int G, int me, int Kloc, int m,
+                        double *gap_partial, double *gap_out, int *m_loc, const int *stop, cudaStream_t s);
+void launch_stop_decide(const double *gap, int early_stop, int *stop, cudaStream_t s);
 // returns a cudaError_t (cooperative launch); stop_flag != nullptr: also run the elite early-stop test
 int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsigned long long *keys_b, int *order,
                     int *vals_b, int m, int early_stop, int *stop_flag, const int *stop, int max_ctas,

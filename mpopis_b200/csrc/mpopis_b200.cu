@@ -115,6 +115,9 @@ struct mpopis_handle {
   int *d_order = nullptr, *d_vals_b = nullptr, *d_hist = nullptr, *d_counts = nullptr, *d_flags = nullptr;
   unsigned char *d_done = nullptr;
   uint4 *d_lut = nullptr;
+  unsigned long long *d_runs_k = nullptr;  // sharded :cemppi: all-gathered sorted runs
+  int *d_runs_v = nullptr, *d_mloc = nullptr;
+  double *d_gap = nullptr;
   size_t part_doubles = 0;
   // d_flags: [0] stop, [1] its, [2] info
   int *stop() { return d_flags; }
@@ -157,18 +160,19 @@ int allgather_costs(mpopis_t *h) {
 // (weighted) mean [+ covariance] of the columns of X ([cs][ld], n local columns) — G5.
 // w: per-local-column weights or nullptr. Adds the mean to U_cur when update_U (scaled by *scale_dev).
 int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, bool want_cov, int corrected,
-            int method, double ridge, bool update_U, const double *scale_dev, double *Sigma_out) {
+            int method, double ridge, bool update_U, const double *scale_dev, double *Sigma_out,
+            const int *n_dev = nullptr) {
   const int cs = h->cs;
   const int *stop = h->stop();
   const int nch = rowsum_nchunks(n);
-  launch_rowsum_partial(X, ld, cs, n, w, h->d_part, stop, h->st);
+  launch_rowsum_partial(X, ld, cs, n, w, h->d_part, stop, h->st, n_dev);
   launch_reduce_partials(h->d_part, nch, cs + 1, h->d_sums, stop, h->st);
   h->launches += 2;
   if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
   launch_finalize_mean(h->d_sums, cs, h->d_mu, update_U ? h->d_U_cur : nullptr, scale_dev, stop, h->st);
   h->launches += 1;
   if (!want_cov) return 0;
-  launch_syrk_partial(X, ld, cs, n, w, h->d_mu, h->d_P, stop, h->st);
+  launch_syrk_partial(X, ld, cs, n, w, h->d_mu, h->d_P, stop, h->st, n_dev);
   launch_scatter_reduce(h->d_P, syrk_nchunks(n), cs, h->d_Sraw, stop, h->st);
   h->launches += 2;
   if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs)) return rc;
@@ -176,7 +180,7 @@ int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, 
   if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
     const int nb = shrink_q_nblocks(n);
     launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS,
-                            h->d_qpart, stop, h->st);
+                            h->d_qpart, stop, h->st, n_dev);
     launch_reduce_partials(h->d_qpart, nb, 1, h->d_q, stop, h->st);
     h->launches += 2;
     if (int rc = allreduce_sum(h, h->d_q, 1)) return rc;
@@ -185,6 +189,28 @@ int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, 
   launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, corrected, method, h->d_q, nq, ridge, Sigma_out, h->d_lambda,
                       stop, h->st);
   h->launches += 1;
+  return 0;
+}
+
+// Sharded :cemppi selection (sort.cu: global_rank_kernel): local sort, all-gather of the sorted runs,
+// global positions by binary search, early-stop statistic by all-reduce(max), local elites gathered into X.
+// On return *d_mloc holds this rank's elite count (a prefix of its sorted run).
+int sharded_ce_select(mpopis_t *h, int m) {
+  const int Kloc = h->Kloc, cs = h->cs;
+  int *stop = h->stop();
+  cudaStream_t st = h->st;
+  const cudaError_t e = (cudaError_t)launch_sortperm(h->d_costs + h->k0, Kloc, h->d_keys_a, h->d_keys_b, h->d_order,
+                                                     h->d_vals_b, 0, 0, nullptr, stop, h->sort_max, st);
+  if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  NC(g_nccl.AllGather(h->d_keys_a, h->d_runs_k, (size_t)Kloc, ncclUint64, h->comm, st));
+  NC(g_nccl.AllGather(h->d_order, h->d_runs_v, (size_t)Kloc, ncclInt32, h->comm, st));
+  CU(cudaMemsetAsync(h->d_mloc, 0, sizeof(int), st));
+  launch_global_rank(h->d_runs_k, h->d_runs_v, h->world, h->rank, Kloc, m, h->d_qpart, h->d_gap, h->d_mloc, stop, st);
+  NC(g_nccl.AllReduce(h->d_gap, h->d_gap, 1, ncclFloat64, ncclMax, h->comm, st));
+  launch_stop_decide(h->d_gap, h->cfg.early_stop, stop, st);
+  const int mmax = m < Kloc ? m : Kloc;
+  launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, mmax, 0, Kloc, h->d_X, h->ldm, nullptr, stop, st, h->d_mloc);
+  h->launches += sort_launches(Kloc) + 4;
   return 0;
 }
 
@@ -279,7 +305,9 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
                             h->st2);
       CU(cudaEventRecord(h->ev_z_ready, h->st2));
     }
-    if (int rc = allgather_costs(h)) return rc;
+    const bool local_select = h->world > 1 && pol == MPOPIS_POLICY_CEMPPI;  // no global cost vector needed
+    if (!local_select)
+      if (int rc = allgather_costs(h)) return rc;
     if (n == N - 1) break;
     // --- adaptation (the `if n < N` blocks) ---
     switch (pol) {
@@ -308,6 +336,13 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       case MPOPIS_POLICY_CEMPPI:
       case MPOPIS_POLICY_CMAMPPI: {  // POL:455-465, 563-599
         const int m = h->m_elite;
+        if (h->world > 1 && pol == MPOPIS_POLICY_CEMPPI) {
+          if (int rc = sharded_ce_select(h, m)) return rc;
+          if (int rc = moments(h, h->d_X, h->ldm, m < Kloc ? m : Kloc, nullptr, true, 0, h->cfg.sigma_est, 10e-9, true,
+                               nullptr, h->d_Sigma, h->d_mloc))
+            return rc;
+          break;
+        }
         {  // order = sortperm(costs) + the elite early-stop test (POL:455-461, 563-569)
           const cudaError_t e = (cudaError_t)launch_sortperm(h->d_costs, K, h->d_keys_a, h->d_keys_b, h->d_order,
                                                              h->d_vals_b, m, h->cfg.early_stop, stop, stop,
@@ -330,6 +365,8 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     }
   }
   h->last_its_launched = N;
+  if (h->world > 1 && pol == MPOPIS_POLICY_CEMPPI)  // costs of the last executed iteration, for the final weights
+    if (int rc = allgather_costs(h)) return rc;
   // --- final weights (always λ: POL:313,367,470,604,665,736,811), weighted noise, control, roll ---
   h->launches += launch_weights(h->d_costs, K, h->cfg.lambda, h->d_w, h->d_ones, nullptr, st);
   launch_rowsum_partial(h->d_E, h->ldk, cs, Kloc, h->d_w + h->k0, h->d_part, nullptr, st);
@@ -585,6 +622,12 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_part, h->part_doubles));
   TRY(dalloc(&h->d_qpart, (size_t)shrink_q_nblocks((int)nmax) + 1));
   if (cfg->policy == MPOPIS_POLICY_CEMPPI) TRY(ensure_elite_capacity(h, h->m_elite));
+  TRY(dalloc(&h->d_mloc, 1));
+  TRY(dalloc(&h->d_gap, 1));
+  if (cfg->policy == MPOPIS_POLICY_CEMPPI && world > 1) {
+    TRY(dalloc(&h->d_runs_k, K));
+    TRY(dalloc(&h->d_runs_v, K));
+  }
   if (cfg->policy == MPOPIS_POLICY_PMCMPPI || cfg->policy == MPOPIS_POLICY_CMAMPPI) {
     TRY(dalloc(&h->d_u, K));
     TRY(dalloc(&h->d_cdf, K));
@@ -632,7 +675,7 @@ int mpopis_b200_destroy(mpopis_t *h) {
                   h->d_traj,   h->d_u,     h->d_cdf,    h->d_wcnt,   h->d_ws,     h->d_sigma,   h->d_psig,
                   h->d_pSig,   h->d_C,     h->d_ns,     h->d_reward, h->d_env_t,  h->d_keys_a,  h->d_keys_b,
                   h->d_order,  h->d_vals_b, h->d_hist,  h->d_counts, h->d_flags,  h->d_done,   h->d_lut,
-                  h->d_ones};
+                  h->d_ones,   h->d_runs_k, h->d_runs_v, h->d_mloc,  h->d_gap};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->h_in) cudaFreeHost(h->h_in);

@@ -201,6 +201,90 @@ int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsi
   return (int)cudaLaunchCooperativeKernel((const void *)merge_all_kernel, dim3(grid), dim3(256), args, 0, s);
 }
 
+// ---- sharded elite selection (one rank of a K-sharded :cemppi policy) -----------------------------------
+// Every rank sorts only its own costs; the sorted runs (key, local index) are all-gathered. For element j of
+// this rank's run, its position in the GLOBAL stable order is j + Σ_{r != me} #{elements of run r below it}
+// (binary searches; the composite (key, global index) is unique). Elites (position < m) are therefore a
+// PREFIX of the local run (length *m_loc), and the early-stop statistic max|Δ sorted elite costs| is the
+// maximum over elites of (successor cost − own cost), the successor being the smallest element above it
+// over all runs. No global sort, no moment work on other ranks' elites.
+__global__ void __launch_bounds__(256) global_rank_kernel(const unsigned long long *__restrict__ runs_k,
+                                                           const int *__restrict__ runs_v, int G, int me, int Kloc,
+                                                           int m, double *__restrict__ gap_partial, int *m_loc,
+                                                           const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[8];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  double gap = -1.0;
+  if (j < Kloc) {
+    const unsigned long long *mk = runs_k + (size_t)me * Kloc;
+    const int *mv = runs_v + (size_t)me * Kloc;
+    const unsigned long long key = mk[j];
+    const int gid = mv[j] + me * Kloc;  // global sample id
+    long long pos = j;
+    unsigned long long sk = KEY_PAD;
+    int sv = 0x7fffffff;
+    if (j + 1 < Kloc) sk = mk[j + 1], sv = mv[j + 1] + me * Kloc;
+    for (int r = 0; r < G; ++r) {
+      if (r == me) continue;
+      const unsigned long long *rk = runs_k + (size_t)r * Kloc;
+      const int *rv = runs_v + (size_t)r * Kloc;
+      int lo = 0, hi = Kloc;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lt(rk[mid], rv[mid] + r * Kloc, key, gid)) lo = mid + 1;
+        else hi = mid;
+      }
+      pos += lo;
+      if (lo < Kloc && lt(rk[lo], rv[lo] + r * Kloc, sk, sv)) sk = rk[lo], sv = rv[lo] + r * Kloc;
+    }
+    if (pos < m) {
+      atomicMax(m_loc, j + 1);
+      if (pos + 1 < m) gap = fabs(cost_of(sk) - cost_of(key));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gap = fmax(gap, __shfl_xor_sync(0xffffffffu, gap, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gap;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) gap = fmax(gap, red[w]);
+    gap_partial[blockIdx.x] = gap;
+  }
+}
+
+__global__ void __launch_bounds__(256) gap_finish_kernel(const double *__restrict__ part, int n, double *out,
+                                                          const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[8];
+  double g = -1.0;
+  for (int i = threadIdx.x; i < n; i += 256) g = fmax(g, part[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) g = fmax(g, __shfl_xor_sync(0xffffffffu, g, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = g;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) g = fmax(g, red[w]);
+    *out = g;
+  }
+}
+
+// after the all-reduce(max) of the gap: maximum(abs.(diff(elite_traj_cost))) < 10e-3 -> break (POL:458-461)
+__global__ void stop_decide_kernel(const double *gap, int early_stop, int *stop) {
+  if (!*stop && early_stop && *gap < 10e-3) *stop = 1;
+}
+
+void launch_global_rank(const unsigned long long *runs_k, const int *runs_v, int G, int me, int Kloc, int m,
+                        double *gap_partial, double *gap_out, int *m_loc, const int *stop, cudaStream_t s) {
+  const int nb = (Kloc + 255) / 256;
+  global_rank_kernel<<<nb, 256, 0, s>>>(runs_k, runs_v, G, me, Kloc, m, gap_partial, m_loc, stop);
+  gap_finish_kernel<<<1, 256, 0, s>>>(gap_partial, nb, gap_out, stop);
+}
+
+void launch_stop_decide(const double *gap, int early_stop, int *stop, cudaStream_t s) {
+  stop_decide_kernel<<<1, 1, 0, s>>>(gap, early_stop, stop);
+}
+
 int sort_max_ctas(int num_sms) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_all_kernel, 256, 0) != cudaSuccess || per_sm < 1)

@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(RS_THREADS) rowsum_partial_kernel(const double
                                                                      int rows, int n,
                                                                      const double *__restrict__ w,
                                                                      double *__restrict__ partial,
-                                                                     const int *stop) {
+                                                                     const int *stop, const int *n_dev) {
   if (stop && *stop) return;
+  if (n_dev) n = min(n, *n_dev);  // device-side column count (sharded elite sets); chunks beyond it write zeros
   __shared__ double red[33];
   const int c = blockIdx.x, r0 = blockIdx.y * RS_ROWS;
   const int kbeg = c * RS_CHUNK, kend = min(n, kbeg + RS_CHUNK);
@@ -162,9 +163,9 @@ __global__ void __launch_bounds__(RS_THREADS) rowsum_partial_kernel(const double
 int rowsum_nchunks(int n) { return (n + RS_CHUNK - 1) / RS_CHUNK; }
 
 void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
-                           const int *stop, cudaStream_t s) {
+                           const int *stop, cudaStream_t s, const int *n_dev) {
   dim3 grid(rowsum_nchunks(n), (rows + 1 + RS_ROWS - 1) / RS_ROWS);
-  rowsum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop);
+  rowsum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop, n_dev);
 }
 
 // out[i] = Σ_c partial[c][i] in chunk order (deterministic)
@@ -209,8 +210,10 @@ constexpr int SY_T = 64, SY_K = 16;
 __global__ void __launch_bounds__(256) syrk_partial_kernel(const double *__restrict__ X, long long ld, int p,
                                                             int n, const double *__restrict__ w,
                                                             const double *__restrict__ mu, int chunk,
-                                                            double *__restrict__ P, const int *stop) {
+                                                            double *__restrict__ P, const int *stop,
+                                                            const int *n_dev) {
   if (stop && *stop) return;
+  if (n_dev) n = min(n, *n_dev);
   // [sample][row], row pitch padded by 2 doubles: the transposing stores are 2-way instead of 16-way
   // bank-conflicted while rows stay 16-byte aligned for the vector reads
   __shared__ __align__(16) double As[SY_K][SY_T + 2], Bs[SY_K][SY_T + 2];
@@ -293,8 +296,10 @@ constexpr int SD_P = 20;
 __global__ void __launch_bounds__(128) syrk_dmma_kernel(const double *__restrict__ X, long long ld, int p, int n,
                                                          const double *__restrict__ w,
                                                          const double *__restrict__ mu, int chunk,
-                                                         double *__restrict__ P, const int *stop) {
+                                                         double *__restrict__ P, const int *stop,
+                                                         const int *n_dev) {
   if (stop && *stop) return;
+  if (n_dev) n = min(n, *n_dev);
   __shared__ double As[SY_T][SD_P], Bs[SY_T][SD_P];  // [row][sample]
   int tt = blockIdx.x, bi = 0;  // decode the lower-triangular tile index
   while (tt > bi) tt -= bi + 1, ++bi;
@@ -369,11 +374,11 @@ static int syrk_path() {  // MPOPIS_SYRK=fma selects the DFMA kernel (A/B eviden
 }
 
 void launch_syrk_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
-                         double *P, const int *stop, cudaStream_t s) {
+                         double *P, const int *stop, cudaStream_t s, const int *n_dev) {
   const int nt = (p + SY_T - 1) / SY_T;
   dim3 grid(nt * (nt + 1) / 2, syrk_nchunks(n));
-  if (syrk_path() == 1) syrk_dmma_kernel<<<grid, 128, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop);
-  else syrk_partial_kernel<<<grid, 256, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop);
+  if (syrk_path() == 1) syrk_dmma_kernel<<<grid, 128, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop, n_dev);
+  else syrk_partial_kernel<<<grid, 256, 0, s>>>(X, ld, p, n, w, mu, syrk_chunk(n), P, stop, n_dev);
 }
 
 // S[i][j] (lower, i >= j) = Σ_c P[c][i][j] in chunk order; raw scatter sums, mirrored to full storage.
@@ -413,8 +418,10 @@ __global__ void __launch_bounds__(256) shrink_q_partial_kernel(const double *__r
                                                                 const double *__restrict__ mu,
                                                                 const double *__restrict__ Sraw,
                                                                 const double *cnt_dev, int standardise,
-                                                                double *__restrict__ partial, const int *stop) {
+                                                                double *__restrict__ partial, const int *stop,
+                                                                const int *n_dev) {
   if (stop && *stop) return;
+  if (n_dev) n = min(n, *n_dev);
   __shared__ double red[33];
   extern __shared__ double dsc[];  // p per-variable scales 1/σ_i (1 for :lw), p means
   {
@@ -455,9 +462,9 @@ int shrink_q_nblocks(int n) { return (n + 63) / 64; }
 
 void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
                              const double *Sraw, const double *cnt_dev, int standardise, double *partial,
-                             const int *stop, cudaStream_t s) {
+                             const int *stop, cudaStream_t s, const int *n_dev) {
   shrink_q_partial_kernel<<<shrink_q_nblocks(n), 256, sizeof(double) * 2 * p, s>>>(X, ld, p, n, w, mu, Sraw, cnt_dev,
-                                                                                   standardise, partial, stop);
+                                                                                   standardise, partial, stop, n_dev);
 }
 
 // Final covariance: Σ′ = shrink(method, Sraw / denom) + ridge·I, written to Sigma (symmetric, so
@@ -536,8 +543,9 @@ void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int c
 // elites owned by other shards contribute zeros (they are summed in by the all-reduce).
 __global__ void gather_cols_kernel(const double *__restrict__ E, long long ldk, int cs, const int *__restrict__ order,
                                    int m, long long k0, int Kloc, double *__restrict__ X, long long ldx,
-                                   double *__restrict__ mask, const int *stop) {
+                                   double *__restrict__ mask, const int *stop, const int *m_dev) {
   if (stop && *stop) return;
+  if (m_dev) m = min(m, *m_dev);
   const int j = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (j >= m) return;
   const long long k = (long long)order[j] - k0;
@@ -547,9 +555,10 @@ __global__ void gather_cols_kernel(const double *__restrict__ E, long long ldk, 
 }
 
 void launch_gather_cols(const double *E, long long ldk, int cs, const int *order, int m, long long k0, int Kloc,
-                        double *X, long long ldx, double *mask, const int *stop, cudaStream_t s) {
+                        double *X, long long ldx, double *mask, const int *stop, cudaStream_t s,
+                        const int *m_dev) {
   dim3 grid((m + 255) / 256, cs);
-  gather_cols_kernel<<<grid, 256, 0, s>>>(E, ldk, cs, order, m, k0, Kloc, X, ldx, mask, stop);
+  gather_cols_kernel<<<grid, 256, 0, s>>>(E, ldk, cs, order, m, k0, Kloc, X, ldx, mask, stop, m_dev);
 }
 
 // maximum(abs.(diff(elite_traj_cost))) < 10e-3 -> break (POL:458-461, 566-569). Sets *stop.
