@@ -52,6 +52,16 @@ struct RolloutArgs {
   int T;                // horizon
 };
 
+// Peer-memory mailboxes of a sharded policy (peer.cu): data[r] / flag[r] point into rank r's mailbox
+// (own memory for r == rank, cudaIpcOpenMemHandle mappings otherwise).
+struct PeerMailboxes {
+  double *data[64];             // 2 slots x capacity doubles each
+  unsigned long long *flag[64]; // 2 sequence flags each
+  unsigned int *arrive;         // 2 local CTA-arrival counters
+  long long capacity;
+  int rank, world;
+};
+
 // ---- launchers (host). Every kernel of the AIS loop takes the device-side `stop` flag ----------
 // rollout.cu  (variant 0 = fast math-equivalent formulation, 1 = literal libm call sequence)
 void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, const int *stop,
@@ -82,8 +92,11 @@ int launch_weights(const double *costs, int K, double lambda, double *w, double 
 int rowsum_nchunks(int n);
 // n_dev (nullable): device-side column count, n_eff = min(n, *n_dev); grids are sized for n
 void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
-                           const int *stop, cudaStream_t s, const int *n_dev = nullptr);
-void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop, cudaStream_t s);
+                           const int *stop, cudaStream_t s, const int *n_dev = nullptr, int sq = 0);
+void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop, cudaStream_t s,
+                            int stride = 0);
+void launch_dinv_from_moments(const double *sum1, const double *sum2, const double *cnt, int p, int standardise,
+                              double *dinv, const int *stop, cudaStream_t s);
 void launch_finalize_mean(const double *sums, int rows, double *mu, double *U, const double *scale_dev,
                           const int *stop, cudaStream_t s);
 int syrk_nchunks(int n);
@@ -93,7 +106,8 @@ void launch_scatter_reduce(const double *P, int nchunks, int p, double *S, const
 int shrink_q_nblocks(int n);
 void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
                              const double *Sraw, const double *cnt_dev, int standardise, double *partial,
-                             const int *stop, cudaStream_t s, const int *n_dev = nullptr);
+                             const int *stop, cudaStream_t s, const int *n_dev = nullptr,
+                             const double *dinv_ext = nullptr);
 void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int corrected, int method,
                          const double *qpart, int nq, double ridge, double *Sigma, double *lambda_out,
                          const int *stop, cudaStream_t s);
@@ -123,12 +137,15 @@ void launch_cma_lin_gather(const double *X, long long ldx, int cs, const int *or
 void launch_cma_vec(const double *dw, const double *C, const double *dvec, const double *ws, int K, int cs,
                     int n_iter, const mpopis_cma_t &c, double *psig, double *pSig, double *sigma_dev, double *U,
                     double *Sigma, const int *stop, cudaStream_t s);
+// peer.cu
+void launch_peer_allreduce(const PeerMailboxes &pm, double *buf, int n, unsigned long long seq, int *info,
+                           const int *stop, cudaStream_t s);
 // sort.cu
 int sort_launches(int K);
 int sort_max_ctas(int num_sms);
 void launch_global_rank(const unsigned long long *runs_k, const int *runs_v, int G, int me, int Kloc, int m,
                         double *gap_partial, double *gap_out, int *m_loc, const int *stop, cudaStream_t s);
-void launch_stop_decide(const double *gap, int early_stop, int *stop, cudaStream_t s);
+void launch_stop_decide(const double *gaps, int G, int early_stop, int *stop, cudaStream_t s);
 // returns a cudaError_t (cooperative launch); stop_flag != nullptr: also run the elite early-stop test
 int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsigned long long *keys_b, int *order,
                     int *vals_b, int m, int early_stop, int *stop_flag, const int *stop, int max_ctas,

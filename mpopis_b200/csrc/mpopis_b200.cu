@@ -48,6 +48,8 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   bool load() {
     if (lib) return true;
     lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -60,8 +62,10 @@ struct NcclApi {
     SYM(AllReduce, "ncclAllReduce");
     SYM(AllGather, "ncclAllGather");
     SYM(GetErrorString, "ncclGetErrorString");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
 #undef SYM
-    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GroupStart && GroupEnd;
   }
 } g_nccl;
 
@@ -117,7 +121,13 @@ struct mpopis_handle {
   uint4 *d_lut = nullptr;
   unsigned long long *d_runs_k = nullptr;  // sharded :cemppi: all-gathered sorted runs
   int *d_runs_v = nullptr, *d_mloc = nullptr;
-  double *d_gap = nullptr;
+  double *d_gap = nullptr, *d_bvec2 = nullptr;  // d_bvec2: 1/σ_i of the sharded shrinkage
+  // peer-memory all-reduce (peer.cu)
+  bool peer_ok = false;
+  PeerMailboxes pm{};
+  void *d_mailbox = nullptr;
+  void *peer_base[64] = {};
+  unsigned long long peer_seq = 0;
   size_t part_doubles = 0;
   // d_flags: [0] stop, [1] its, [2] info
   int *stop() { return d_flags; }
@@ -131,9 +141,43 @@ struct mpopis_handle {
   int last_its_launched = 0;
   double last_rollout_ms = 0, last_total_ms = 0;
   bool timing_valid = false;
+  // optional phase tracer (MPOPIS_TRACE=1): CUDA events at phase boundaries of the last plan, printed to stderr
+  bool trace = false;
+  std::vector<std::pair<const char *, cudaEvent_t>> marks;
+  std::vector<cudaEvent_t> mark_pool;
 };
 
 namespace {
+
+void mark(mpopis_t *h, const char *name) {
+  if (!h->trace) return;
+  cudaEvent_t e;
+  if (h->marks.size() < h->mark_pool.size()) e = h->mark_pool[h->marks.size()];
+  else {
+    cudaEventCreate(&e);
+    h->mark_pool.push_back(e);
+  }
+  cudaEventRecord(e, h->st);
+  h->marks.emplace_back(name, e);
+}
+
+void dump_marks(mpopis_t *h) {
+  if (!h->trace || h->marks.size() < 2) return;
+  std::vector<std::pair<std::string, double>> agg;
+  double tot = 0;
+  for (size_t i = 1; i < h->marks.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->marks[i - 1].second, h->marks[i].second);
+    tot += ms;
+    bool found = false;
+    for (auto &a : agg)
+      if (a.first == h->marks[i].first) a.second += ms, found = true;
+    if (!found) agg.emplace_back(h->marks[i].first, ms);
+  }
+  fprintf(stderr, "[mpopis trace rank %d] total %.3f ms:", h->rank, tot);
+  for (auto &a : agg) fprintf(stderr, " %s=%.3f", a.first.c_str(), a.second);
+  fprintf(stderr, "\n");
+}
 
 int set_device(mpopis_t *h) {
   CU(cudaSetDevice(h->dev));
@@ -148,7 +192,79 @@ bool adapts_sigma(int pol) {
 
 int allreduce_sum(mpopis_t *h, double *buf, size_t n) {
   if (h->world == 1) return 0;
+  if (h->peer_ok && (long long)n <= h->pm.capacity) {  // one-shot sum over NVLink peer memory (peer.cu)
+    launch_peer_allreduce(h->pm, buf, (int)n, ++h->peer_seq, h->info(), h->stop(), h->st);
+    h->launches += 1;
+    return 0;
+  }
   NC(g_nccl.AllReduce(buf, buf, n, ncclFloat64, ncclSum, h->comm, h->st));
+  return 0;
+}
+
+// Exports this rank's mailbox with CUDA IPC, exchanges the handles over the (already initialised) NCCL
+// communicator and maps every peer's mailbox. All ranks agree (all-reduce min) on whether the peer path is
+// usable; otherwise ncclAllReduce keeps being used.
+int setup_peer_mailboxes(mpopis_t *h) {
+  // Opt-in (MPOPIS_PEER_ALLREDUCE=1): at 2 GPUs the first version measured no faster than ncclAllReduce for
+  // these sizes (profiles/README.md), so NCCL stays the default until it wins.
+  const char *env = getenv("MPOPIS_PEER_ALLREDUCE");
+  int want = env && env[0] == '1';
+  const int G = h->world;
+  const long long cap = (long long)h->cs * h->cs + 256;
+  const size_t bytes = sizeof(double) * 2 * cap + 64;
+  int ok = want;
+  cudaIpcMemHandle_t mine{};
+  if (ok && cudaMalloc(&h->d_mailbox, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaMemset(h->d_mailbox, 0, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, h->d_mailbox) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // exchange handles (64 bytes each) + per-rank ok flags through NCCL
+  unsigned char *d_x = nullptr;
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  std::vector<unsigned char> host(rec * G, 0);
+  memcpy(host.data() + rec * h->rank, &mine, sizeof mine);
+  host[rec * h->rank + sizeof mine] = (unsigned char)ok;
+  CU(cudaMalloc((void **)&d_x, rec * G));
+  CU(cudaMemcpy(d_x, host.data(), rec * G, cudaMemcpyHostToDevice));
+  NC(g_nccl.AllGather(d_x + rec * h->rank, d_x, rec, ncclChar, h->comm, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaMemcpy(host.data(), d_x, rec * G, cudaMemcpyDeviceToHost));
+  cudaFree(d_x);
+  for (int r = 0; r < G; ++r) ok = ok && host[rec * r + sizeof mine];
+  if (ok) {
+    for (int r = 0; r < G && ok; ++r) {
+      if (r == h->rank) {
+        h->peer_base[r] = h->d_mailbox;
+        continue;
+      }
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, host.data() + rec * r, sizeof hd);
+      if (cudaIpcOpenMemHandle(&h->peer_base[r], hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        h->peer_base[r] = nullptr;
+        ok = 0;
+      }
+    }
+  }
+  // second agreement round: did every rank manage to map every peer?
+  double *d_ok = nullptr;
+  double v = ok ? 1.0 : 0.0;
+  CU(cudaMalloc((void **)&d_ok, sizeof(double)));
+  CU(cudaMemcpy(d_ok, &v, sizeof v, cudaMemcpyHostToDevice));
+  NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclFloat64, ncclMin, h->comm, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaMemcpy(&v, d_ok, sizeof v, cudaMemcpyDeviceToHost));
+  cudaFree(d_ok);
+  if (h->trace) fprintf(stderr, "[mpopis trace rank %d] peer-memory all-reduce: want=%d agreed=%d\n", h->rank, want, v >= 1.0);
+  if (v < 1.0) return 0;  // NCCL path stays in use
+  h->pm.capacity = cap, h->pm.rank = h->rank, h->pm.world = G;
+  for (int r = 0; r < G; ++r) {
+    unsigned char *base = (unsigned char *)h->peer_base[r];
+    h->pm.data[r] = (double *)base;
+    h->pm.flag[r] = (unsigned long long *)(base + sizeof(double) * 2 * cap);
+  }
+  h->pm.arrive = (unsigned int *)((unsigned char *)h->d_mailbox + sizeof(double) * 2 * cap + 16);
+  h->peer_ok = true;
   return 0;
 }
 int allgather_costs(mpopis_t *h) {
@@ -161,34 +277,65 @@ int allgather_costs(mpopis_t *h) {
 // w: per-local-column weights or nullptr. Adds the mean to U_cur when update_U (scaled by *scale_dev).
 int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, bool want_cov, int corrected,
             int method, double ridge, bool update_U, const double *scale_dev, double *Sigma_out,
-            const int *n_dev = nullptr) {
+            const int *n_dev = nullptr, bool sharded_stop = false) {
   const int cs = h->cs;
   const int *stop = h->stop();
   const int nch = rowsum_nchunks(n);
-  launch_rowsum_partial(X, ld, cs, n, w, h->d_part, stop, h->st, n_dev);
-  launch_reduce_partials(h->d_part, nch, cs + 1, h->d_sums, stop, h->st);
+  const bool shrink = want_cov && (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS);
+  // Sharded shrinkage: the first all-reduce also carries Σx² so that the standardisation of the shrinkage
+  // statistic needs no collective of its own, and that statistic rides on the scatter-matrix all-reduce:
+  // 2 collectives per iteration instead of 3. d_sums = [Σx (cs) | n | per-rank stop statistics (64) | Σx² (cs)].
+  const bool fused = h->world > 1 && shrink;
+  const int width = fused ? 2 * cs + 1 : cs + 1;
+  launch_rowsum_partial(X, ld, cs, n, w, h->d_part, stop, h->st, n_dev, fused);
+  launch_reduce_partials(h->d_part, nch, cs + 1, h->d_sums, stop, h->st, width);
   h->launches += 2;
-  if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
+  if (fused) {
+    launch_reduce_partials(h->d_part + cs + 1, nch, cs, h->d_sums + cs + 1 + 64, stop, h->st, width);
+    h->launches += 1;
+  }
+  mark(h, "mean.local");
+  if (int rc = allreduce_sum(h, h->d_sums, cs + 1 + ((sharded_stop || fused) ? 64 : 0) + (fused ? cs : 0))) return rc;
+  mark(h, "mean.coll");
+  if (sharded_stop) {  // POL:458-461 on the all-reduced per-rank statistics, before anything is updated
+    launch_stop_decide(h->d_sums + cs + 1, h->world, h->cfg.early_stop, h->stop(), h->st);
+    h->launches += 1;
+  }
   launch_finalize_mean(h->d_sums, cs, h->d_mu, update_U ? h->d_U_cur : nullptr, scale_dev, stop, h->st);
   h->launches += 1;
+  mark(h, "mean");
   if (!want_cov) return 0;
   launch_syrk_partial(X, ld, cs, n, w, h->d_mu, h->d_P, stop, h->st, n_dev);
   launch_scatter_reduce(h->d_P, syrk_nchunks(n), cs, h->d_Sraw, stop, h->st);
   h->launches += 2;
-  if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs)) return rc;
-  int nq = 0;
-  if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
-    const int nb = shrink_q_nblocks(n);
+  double *qdst = h->d_q;
+  if (fused) {
+    qdst = h->d_Sraw + (size_t)cs * cs;  // travels with the scatter matrix
+    launch_dinv_from_moments(h->d_sums, h->d_sums + cs + 1 + 64, h->d_sums + cs, cs, method == MPOPIS_SIGMA_SS,
+                             h->d_bvec2, stop, h->st);
     launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS,
-                            h->d_qpart, stop, h->st, n_dev);
-    launch_reduce_partials(h->d_qpart, nb, 1, h->d_q, stop, h->st);
-    h->launches += 2;
-    if (int rc = allreduce_sum(h, h->d_q, 1)) return rc;
-    nq = 1;
+                            h->d_qpart, stop, h->st, n_dev, h->d_bvec2);
+    launch_reduce_partials(h->d_qpart, shrink_q_nblocks(n), 1, qdst, stop, h->st);
+    h->launches += 3;
   }
-  launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, corrected, method, h->d_q, nq, ridge, Sigma_out, h->d_lambda,
+  mark(h, "scatter.local");
+  if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs + (fused ? 1 : 0))) return rc;
+  mark(h, "scatter.coll");
+  int nq = 0;
+  if (shrink) {
+    if (!fused) {
+      launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS,
+                              h->d_qpart, stop, h->st, n_dev);
+      launch_reduce_partials(h->d_qpart, shrink_q_nblocks(n), 1, h->d_q, stop, h->st);
+      h->launches += 2;
+    }
+    nq = 1;
+    mark(h, "shrinkq");
+  }
+  launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, corrected, method, qdst, nq, ridge, Sigma_out, h->d_lambda,
                       stop, h->st);
   h->launches += 1;
+  mark(h, "covfin");
   return 0;
 }
 
@@ -202,12 +349,19 @@ int sharded_ce_select(mpopis_t *h, int m) {
   const cudaError_t e = (cudaError_t)launch_sortperm(h->d_costs + h->k0, Kloc, h->d_keys_a, h->d_keys_b, h->d_order,
                                                      h->d_vals_b, 0, 0, nullptr, stop, h->sort_max, st);
   if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  mark(h, "sel.sort");
+  NC(g_nccl.GroupStart());  // one fused NCCL launch for keys + indices
   NC(g_nccl.AllGather(h->d_keys_a, h->d_runs_k, (size_t)Kloc, ncclUint64, h->comm, st));
   NC(g_nccl.AllGather(h->d_order, h->d_runs_v, (size_t)Kloc, ncclInt32, h->comm, st));
+  NC(g_nccl.GroupEnd());
+  mark(h, "sel.allgather");
   CU(cudaMemsetAsync(h->d_mloc, 0, sizeof(int), st));
-  launch_global_rank(h->d_runs_k, h->d_runs_v, h->world, h->rank, Kloc, m, h->d_qpart, h->d_gap, h->d_mloc, stop, st);
-  NC(g_nccl.AllReduce(h->d_gap, h->d_gap, 1, ncclFloat64, ncclMax, h->comm, st));
-  launch_stop_decide(h->d_gap, h->cfg.early_stop, stop, st);
+  // this rank's early-stop statistic goes into slot `rank` of the (zeroed) tail of d_sums and rides on the
+  // all-reduce(sum) of the elite row sums (moments()): one collective less per iteration
+  CU(cudaMemsetAsync(h->d_sums + cs + 1, 0, sizeof(double) * h->world, st));
+  launch_global_rank(h->d_runs_k, h->d_runs_v, h->world, h->rank, Kloc, m, h->d_qpart, h->d_sums + cs + 1 + h->rank,
+                     h->d_mloc, stop, st);
+  mark(h, "sel.rank");
   const int mmax = m < Kloc ? m : Kloc;
   launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, mmax, 0, Kloc, h->d_X, h->ldm, nullptr, stop, st, h->d_mloc);
   h->launches += sort_launches(Kloc) + 4;
@@ -244,6 +398,8 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   if (pol == MPOPIS_POLICY_PMCMPPI && N > 1 && Z_host && !u_host)
     return fail(MPOPIS_ERR_BAD_ARG, "pmcmppi with injected noise needs resample_u");
   CU(cudaEventRecord(h->ev[0], st));
+  h->marks.clear();
+  mark(h, "begin");
   CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 2, st));  // stop, its (info is sticky until read)
   CU(cudaMemcpyAsync(h->d_U_cur, h->d_U_orig, sizeof(double) * cs, cudaMemcpyDeviceToDevice, st));
   const bool adapt = adapts_sigma(pol) && N > 1;
@@ -278,6 +434,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       h->launches += 1;
       bvec = h->d_bvec;
     }
+    mark(h, "chol");
     // --- Z, E = L Z (POL:448) ---
     if (Z_host) {
       const double *src = Z_host + ((size_t)n * K + h->k0) * cs;
@@ -290,6 +447,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     }
     launch_apply_L(Lt, cs, bs, h->d_Z, h->d_E, h->ldk, Kloc, stop, st);
     h->launches += 2;
+    mark(h, "sample");
     // --- rollouts (POL:452 -> POL:261-278) ---
     CU(cudaEventRecord(h->ev[2 + 2 * n], st));
     if (int rc = launch_rollouts(h, h->d_U_cur, h->d_U_orig, bvec)) return rc;
@@ -309,6 +467,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     if (!local_select)
       if (int rc = allgather_costs(h)) return rc;
     if (n == N - 1) break;
+    mark(h, "rollout+gather");
     // --- adaptation (the `if n < N` blocks) ---
     switch (pol) {
       case MPOPIS_POLICY_IMPPI:
@@ -338,8 +497,9 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
         const int m = h->m_elite;
         if (h->world > 1 && pol == MPOPIS_POLICY_CEMPPI) {
           if (int rc = sharded_ce_select(h, m)) return rc;
+          mark(h, "select");
           if (int rc = moments(h, h->d_X, h->ldm, m < Kloc ? m : Kloc, nullptr, true, 0, h->cfg.sigma_est, 10e-9, true,
-                               nullptr, h->d_Sigma, h->d_mloc))
+                               nullptr, h->d_Sigma, h->d_mloc, true))
             return rc;
           break;
         }
@@ -352,6 +512,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
         launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, m, h->k0, Kloc, h->d_X, h->ldm,
                            h->world > 1 ? h->d_mask : nullptr, stop, st);
         h->launches += 1 + sort_launches(K);
+        mark(h, "select");
         if (pol == MPOPIS_POLICY_CEMPPI) {
           if (int rc = moments(h, h->d_X, h->ldm, m, h->world > 1 ? h->d_mask : nullptr, true, 0,
                                h->cfg.sigma_est, 10e-9, true, nullptr, h->d_Sigma))
@@ -375,6 +536,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
   launch_finalize_control(h->d_sums, h->d_U_orig, h->d_U_cur, cs, h->as, h->T, h->d_U_next, h->d_control, st);
   h->launches += 1;
+  mark(h, "final");
   CU(cudaEventRecord(h->ev[1], st));
   CU(cudaGetLastError());
   h->step += 1;
@@ -393,10 +555,12 @@ int finish_timing(mpopis_t *h) {
   }
   h->last_rollout_ms = r;
   h->timing_valid = true;
+  dump_marks(h);
   return 0;
 }
 
 int check_info(mpopis_t *h, int info) {
+  if (info == 3000) return fail(MPOPIS_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank");
   if (info != 0)
     return fail(MPOPIS_ERR_NOT_PD, "PosDefException: matrix is not positive definite; Cholesky factorization failed (%s)",
                 info >= 1000 ? "initial Σ" : (std::string("AIS iteration ") + std::to_string(info)).c_str());
@@ -534,6 +698,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
                 prop.major, prop.minor);
   const int world = cfg->world_size < 1 ? 1 : cfg->world_size;
   if (cfg->rank < 0 || cfg->rank >= world) return fail(MPOPIS_ERR_BAD_ARG, "rank out of range");
+  if (world > 64) return fail(MPOPIS_ERR_BAD_ARG, "world_size must be <= 64");
   if (cfg->num_samples % world) return fail(MPOPIS_ERR_BAD_ARG, "num_samples must be divisible by world_size");
 
   mpopis_t *h = new mpopis_handle();
@@ -565,6 +730,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
       return fail(MPOPIS_ERR_BAD_ARG, "m_elite = %d out of range", h->m_elite);
     }
   }
+  if (const char *e = getenv("MPOPIS_TRACE")) h->trace = atoi(e) != 0;
   if (const char *e = getenv("MPOPIS_ROLLOUT_VARIANT")) h->rollout_variant = atoi(e);
   if (const char *e = getenv("MPOPIS_ROLLOUT_BLOCK")) h->rollout_block = atoi(e);
   if (h->rollout_block < 32 || h->rollout_block > 128 || h->rollout_block % 32) h->rollout_block = 64;
@@ -608,9 +774,10 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_vals_b, K));
   TRY(dalloc(&h->d_hist, 1));
   TRY(dalloc(&h->d_flags, 4));
-  TRY(dalloc(&h->d_sums, cs + 1));
+  TRY(dalloc(&h->d_sums, 2 * cs + 1 + 64));
+  TRY(dalloc(&h->d_bvec2, cs));  // [Σx (cs) | count | per-rank early-stop statistics (<= 64 ranks)]
   TRY(dalloc(&h->d_mu, cs));
-  TRY(dalloc(&h->d_Sraw, cs * cs));
+  TRY(dalloc(&h->d_Sraw, cs * cs + 1));
   TRY(dalloc(&h->d_P, (size_t)98 * cs * cs));  // <= 96 SYRK chunks (stats.cu: syrk_chunk)
   TRY(dalloc(&h->d_q, 1));
   TRY(dalloc(&h->d_lambda, 1));
@@ -618,7 +785,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_reward, 1));
   TRY(dalloc(&h->d_done, 1));
   const size_t nmax = K;  // moments may run over Kloc samples or up to K elites
-  h->part_doubles = (size_t)(rowsum_nchunks((int)nmax) + 1) * (cs + 1);
+  h->part_doubles = (size_t)(rowsum_nchunks((int)nmax) + 1) * (2 * cs + 1);
   TRY(dalloc(&h->d_part, h->part_doubles));
   TRY(dalloc(&h->d_qpart, (size_t)shrink_q_nblocks((int)nmax) + 1));
   if (cfg->policy == MPOPIS_POLICY_CEMPPI) TRY(ensure_elite_capacity(h, h->m_elite));
@@ -667,6 +834,9 @@ int mpopis_b200_destroy(mpopis_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->dev);
   if (h->st) cudaStreamSynchronize(h->st);
+  for (int r = 0; r < 64; ++r)
+    if (h->peer_base[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_base[r]);
+  if (h->d_mailbox) cudaFree(h->d_mailbox);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->d_trk,    h->d_state, h->d_U_orig, h->d_U_cur,  h->d_U_next, h->d_control, h->d_Sigma0,
                   h->d_Sigma,  h->d_Lt,    h->d_Lt0,    h->d_cholW,  h->d_bvec,   h->d_Z,       h->d_E,
@@ -675,7 +845,8 @@ int mpopis_b200_destroy(mpopis_t *h) {
                   h->d_traj,   h->d_u,     h->d_cdf,    h->d_wcnt,   h->d_ws,     h->d_sigma,   h->d_psig,
                   h->d_pSig,   h->d_C,     h->d_ns,     h->d_reward, h->d_env_t,  h->d_keys_a,  h->d_keys_b,
                   h->d_order,  h->d_vals_b, h->d_hist,  h->d_counts, h->d_flags,  h->d_done,   h->d_lut,
-                  h->d_ones,   h->d_runs_k, h->d_runs_v, h->d_mloc,  h->d_gap};
+                  h->d_ones,   h->d_runs_k, h->d_runs_v, h->d_mloc,  h->d_gap,
+                  h->d_bvec2};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->h_in) cudaFreeHost(h->h_in);
@@ -683,6 +854,7 @@ int mpopis_b200_destroy(mpopis_t *h) {
   if (h->h_flags) cudaFreeHost(h->h_flags);
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto &e : h->mark_pool) cudaEventDestroy(e);
   if (h->ev_z_free) cudaEventDestroy(h->ev_z_free);
   if (h->ev_z_ready) cudaEventDestroy(h->ev_z_ready);
   if (h->st2) cudaStreamSynchronize(h->st2), cudaStreamDestroy(h->st2);
@@ -709,7 +881,7 @@ int mpopis_b200_comm_init(mpopis_t *h, const void *id128) {
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   NC(g_nccl.CommInitRank(&h->comm, h->world, id, h->rank));
-  return 0;
+  return setup_peer_mailboxes(h);
 }
 
 int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params, double dt, double ddt,

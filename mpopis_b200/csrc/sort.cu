@@ -270,8 +270,10 @@ __global__ void __launch_bounds__(256) gap_finish_kernel(const double *__restric
 }
 
 // after the all-reduce(max) of the gap: maximum(abs.(diff(elite_traj_cost))) < 10e-3 -> break (POL:458-461)
-__global__ void stop_decide_kernel(const double *gap, int early_stop, int *stop) {
-  if (!*stop && early_stop && *gap < 10e-3) *stop = 1;
+__global__ void stop_decide_kernel(const double *gaps, int G, int early_stop, int *stop) {
+  double g = gaps[0];
+  for (int r = 1; r < G; ++r) g = fmax(g, gaps[r]);
+  if (!*stop && early_stop && g < 10e-3) *stop = 1;
 }
 
 void launch_global_rank(const unsigned long long *runs_k, const int *runs_v, int G, int me, int Kloc, int m,
@@ -281,8 +283,8 @@ void launch_global_rank(const unsigned long long *runs_k, const int *runs_v, int
   gap_finish_kernel<<<1, 256, 0, s>>>(gap_partial, nb, gap_out, stop);
 }
 
-void launch_stop_decide(const double *gap, int early_stop, int *stop, cudaStream_t s) {
-  stop_decide_kernel<<<1, 1, 0, s>>>(gap, early_stop, stop);
+void launch_stop_decide(const double *gaps, int G, int early_stop, int *stop, cudaStream_t s) {
+  stop_decide_kernel<<<1, 1, 0, s>>>(gaps, G, early_stop, stop);
 }
 
 int sort_max_ctas(int num_sms) {

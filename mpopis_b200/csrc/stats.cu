@@ -135,53 +135,79 @@ __global__ void __launch_bounds__(RS_THREADS) rowsum_partial_kernel(const double
                                                                      int rows, int n,
                                                                      const double *__restrict__ w,
                                                                      double *__restrict__ partial,
-                                                                     const int *stop, const int *n_dev) {
+                                                                     const int *stop, const int *n_dev, int sq) {
   if (stop && *stop) return;
   if (n_dev) n = min(n, *n_dev);  // device-side column count (sharded elite sets); chunks beyond it write zeros
   __shared__ double red[33];
   const int c = blockIdx.x, r0 = blockIdx.y * RS_ROWS;
   const int kbeg = c * RS_CHUNK, kend = min(n, kbeg + RS_CHUNK);
-  double acc[RS_ROWS];
+  const int width = sq ? 2 * rows + 1 : rows + 1;  // sq: also Σ_k w_k X[r][k]² at column rows + 1 + r
+  double acc[RS_ROWS], acc2[RS_ROWS];
 #pragma unroll
-  for (int q = 0; q < RS_ROWS; ++q) acc[q] = 0.0;
+  for (int q = 0; q < RS_ROWS; ++q) acc[q] = acc2[q] = 0.0;
   for (int k = kbeg + threadIdx.x; k < kend; k += RS_THREADS) {
     const double wk = w ? w[k] : 1.0;
 #pragma unroll
     for (int q = 0; q < RS_ROWS; ++q) {
       const int r = r0 + q;
-      if (r < rows) acc[q] = fma(wk, X[(size_t)r * ld + k], acc[q]);
-      else if (r == rows) acc[q] += wk;
+      if (r < rows) {
+        const double x = X[(size_t)r * ld + k];
+        acc[q] = fma(wk, x, acc[q]);
+        if (sq) acc2[q] = fma(wk * x, x, acc2[q]);
+      } else if (r == rows) acc[q] += wk;
     }
   }
 #pragma unroll
   for (int q = 0; q < RS_ROWS; ++q) {
     const double t = block_reduce<0>(acc[q], red);
-    if (threadIdx.x == 0 && r0 + q <= rows) partial[(size_t)c * (rows + 1) + r0 + q] = t;
+    if (threadIdx.x == 0 && r0 + q <= rows) partial[(size_t)c * width + r0 + q] = t;
+    if (sq) {
+      const double t2 = block_reduce<0>(acc2[q], red);
+      if (threadIdx.x == 0 && r0 + q < rows) partial[(size_t)c * width + rows + 1 + r0 + q] = t2;
+    }
   }
 }
 
 int rowsum_nchunks(int n) { return (n + RS_CHUNK - 1) / RS_CHUNK; }
 
 void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
-                           const int *stop, cudaStream_t s, const int *n_dev) {
+                           const int *stop, cudaStream_t s, const int *n_dev, int sq) {
   dim3 grid(rowsum_nchunks(n), (rows + 1 + RS_ROWS - 1) / RS_ROWS);
-  rowsum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop, n_dev);
+  rowsum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop, n_dev, sq);
 }
 
 // out[i] = Σ_c partial[c][i] in chunk order (deterministic)
-__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int n,
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int n, int stride,
                                        double *__restrict__ out, const int *stop) {
   if (stop && *stop) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
-  for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * n + i];
+  for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * stride + i];
   out[i] = s;
 }
 
+// stride = row pitch of `partial` (0: n)
 void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop,
-                            cudaStream_t s) {
-  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, nchunks, n, out, stop);
+                            cudaStream_t s, int stride) {
+  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, nchunks, n, stride ? stride : n, out, stop);
+}
+
+// 1/σ_i from the all-reduced first and second raw moments (sharded shrinkage: one collective fewer):
+// σ_i² = Σx_i²/n − μ_i². The elites' noise mean is a fraction of their spread, so the cancellation costs at
+// most a few ulps; it only feeds the standardisation inside the shrinkage intensity λ̂.
+__global__ void dinv_from_moments_kernel(const double *__restrict__ sum1, const double *__restrict__ sum2,
+                                         const double *cnt, int p, int standardise, double *__restrict__ dinv,
+                                         const int *stop) {
+  if (stop && *stop) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p) return;
+  const double n = *cnt, mu = sum1[i] / n;
+  dinv[i] = standardise ? 1.0 / sqrt(sum2[i] / n - mu * mu) : 1.0;
+}
+void launch_dinv_from_moments(const double *sum1, const double *sum2, const double *cnt, int p, int standardise,
+                              double *dinv, const int *stop, cudaStream_t s) {
+  dinv_from_moments_kernel<<<(p + 127) / 128, 128, 0, s>>>(sum1, sum2, cnt, p, standardise, dinv, stop);
 }
 
 // μ = sums[0:rows] / sums[rows]; optionally U += scale * μ  (pol.U = pol.U + vec(μ′), POL:365,465,...)
@@ -213,7 +239,10 @@ __global__ void __launch_bounds__(256) syrk_partial_kernel(const double *__restr
                                                             double *__restrict__ P, const int *stop,
                                                             const int *n_dev) {
   if (stop && *stop) return;
-  if (n_dev) n = min(n, *n_dev);
+  if (n_dev) {  // device-side column count: re-balance the chunks over the grid (all CTAs stay busy)
+    n = min(n, *n_dev);
+    chunk = max(SY_K, (((n + (int)gridDim.y - 1) / (int)gridDim.y + SY_K - 1) / SY_K) * SY_K);
+  }
   // [sample][row], row pitch padded by 2 doubles: the transposing stores are 2-way instead of 16-way
   // bank-conflicted while rows stay 16-byte aligned for the vector reads
   __shared__ __align__(16) double As[SY_K][SY_T + 2], Bs[SY_K][SY_T + 2];
@@ -299,7 +328,10 @@ __global__ void __launch_bounds__(128) syrk_dmma_kernel(const double *__restrict
                                                          double *__restrict__ P, const int *stop,
                                                          const int *n_dev) {
   if (stop && *stop) return;
-  if (n_dev) n = min(n, *n_dev);
+  if (n_dev) {  // device-side column count: re-balance the chunks over the grid (all CTAs stay busy)
+    n = min(n, *n_dev);
+    chunk = max(SY_K, (((n + (int)gridDim.y - 1) / (int)gridDim.y + SY_K - 1) / SY_K) * SY_K);
+  }
   __shared__ double As[SY_T][SD_P], Bs[SY_T][SD_P];  // [row][sample]
   int tt = blockIdx.x, bi = 0;  // decode the lower-triangular tile index
   while (tt > bi) tt -= bi + 1, ++bi;
@@ -419,7 +451,8 @@ __global__ void __launch_bounds__(256) shrink_q_partial_kernel(const double *__r
                                                                 const double *__restrict__ Sraw,
                                                                 const double *cnt_dev, int standardise,
                                                                 double *__restrict__ partial, const int *stop,
-                                                                const int *n_dev) {
+                                                                const int *n_dev,
+                                                                const double *__restrict__ dinv_ext) {
   if (stop && *stop) return;
   if (n_dev) n = min(n, *n_dev);
   __shared__ double red[33];
@@ -427,7 +460,7 @@ __global__ void __launch_bounds__(256) shrink_q_partial_kernel(const double *__r
   {
     const double cnt = *cnt_dev;  // global number of observations (Σ of ownership weights)
     for (int i = threadIdx.x; i < p; i += blockDim.x) {
-      dsc[i] = standardise ? 1.0 / sqrt(Sraw[(size_t)i * p + i] / cnt) : 1.0;
+      dsc[i] = dinv_ext ? dinv_ext[i] : (standardise ? 1.0 / sqrt(Sraw[(size_t)i * p + i] / cnt) : 1.0);
       dsc[p + i] = mu[i];
     }
   }
@@ -462,9 +495,9 @@ int shrink_q_nblocks(int n) { return (n + 63) / 64; }
 
 void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const double *w, const double *mu,
                              const double *Sraw, const double *cnt_dev, int standardise, double *partial,
-                             const int *stop, cudaStream_t s, const int *n_dev) {
-  shrink_q_partial_kernel<<<shrink_q_nblocks(n), 256, sizeof(double) * 2 * p, s>>>(X, ld, p, n, w, mu, Sraw, cnt_dev,
-                                                                                   standardise, partial, stop, n_dev);
+                             const int *stop, cudaStream_t s, const int *n_dev, const double *dinv_ext) {
+  shrink_q_partial_kernel<<<shrink_q_nblocks(n), 256, sizeof(double) * 2 * p, s>>>(
+      X, ld, p, n, w, mu, Sraw, cnt_dev, standardise, partial, stop, n_dev, dinv_ext);
 }
 
 // Final covariance: Σ′ = shrink(method, Sraw / denom) + ridge·I, written to Sigma (symmetric, so
