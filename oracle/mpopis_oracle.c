@@ -26,6 +26,9 @@
 #endif
 
 static __thread char g_err[512] = "";
+/* threads for the embarrassingly parallel helpers (normal draws, L·Z): the reference gets these from
+ * multithreaded BLAS / a fast native RNG, so the CPU baseline should not be charged for them serially */
+static int g_threads = 1;
 const char *orc_last_error(void) { return g_err; }
 #define FAIL(code, ...)                         \
   do {                                          \
@@ -199,6 +202,7 @@ static void philox_u2(uint64_t seed, uint32_t k, uint32_t j, uint32_t it, uint32
 
 static void philox_normals(uint64_t seed, int64_t step, int64_t it, int64_t cs, int64_t K, int64_t k0,
                            double *Z /* cs x K, column k holds global sample k0+k */) {
+#pragma omp parallel for schedule(static) num_threads(g_threads)
   for (int64_t k = 0; k < K; ++k)
     for (int64_t j = 0; 2 * j < cs; ++j) {
       double u1, u2;
@@ -598,6 +602,7 @@ int orc_destroy(orc_t *h) {
 
 int orc_set_threads(orc_t *h, int nthreads) {
   h->nthreads = nthreads < 1 ? 1 : nthreads;
+  g_threads = h->nthreads;
   return 0;
 }
 
@@ -659,6 +664,7 @@ int orc_seed(orc_t *h, uint64_t seed) {
 
 /* E = L * Z (Z cs x K), MvNormal sampling, SURVEY App. A-1 */
 static void apply_L(const double *L, int64_t n, const double *Z, int64_t K, double *E) {
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (K > 64)
   for (int64_t k = 0; k < K; ++k)
     for (int64_t i = 0; i < n; ++i) {
       double s = 0.0;
