@@ -401,6 +401,7 @@ __device__ __forceinline__ void car_step_fast(const CarParams &P, double dt, dou
     psi += dpsi;  // CAR:329 (wrapped once per step below)
     double sdp, cdp;
     if (fabs(dpsi) <= 0.03) sincos_tiny(dpsi, &sdp, &cdp);
+    else if (fabs(dpsi) <= 0.8) sincos_kernel(dpsi, &sdp, &cdp);  // spinning car: still no libdevice call
     else sincos(dpsi, &sdp, &cdp);
     const double nsp = fma(sp, cdp, cp * sdp);
     cp = fma(cp, cdp, -(sp * sdp));

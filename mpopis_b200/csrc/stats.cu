@@ -131,11 +131,13 @@ int launch_weights(const double *costs, int K, double lambda, double *w, double 
 // (w == nullptr: w_k = 1). X is [rows][ld] with the sample index contiguous, so every warp streams
 // 256-byte row segments: this is the one genuinely HBM-bound kernel of the path (8·cs·K bytes).
 constexpr int RS_THREADS = 256, RS_ROWS = 4, RS_CHUNK = 4096;
+template <bool SQ>  // SQ: also the second raw moment (sharded shrinkage); the plain instance is the G8 kernel
 __global__ void __launch_bounds__(RS_THREADS) rowsum_partial_kernel(const double *__restrict__ X, long long ld,
                                                                      int rows, int n,
                                                                      const double *__restrict__ w,
                                                                      double *__restrict__ partial,
-                                                                     const int *stop, const int *n_dev, int sq) {
+                                                                     const int *stop, const int *n_dev) {
+  constexpr bool sq = SQ;
   if (stop && *stop) return;
   if (n_dev) n = min(n, *n_dev);  // device-side column count (sharded elite sets); chunks beyond it write zeros
   __shared__ double red[33];
@@ -173,7 +175,8 @@ int rowsum_nchunks(int n) { return (n + RS_CHUNK - 1) / RS_CHUNK; }
 void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const double *w, double *partial,
                            const int *stop, cudaStream_t s, const int *n_dev, int sq) {
   dim3 grid(rowsum_nchunks(n), (rows + 1 + RS_ROWS - 1) / RS_ROWS);
-  rowsum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop, n_dev, sq);
+  if (sq) rowsum_partial_kernel<true><<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop, n_dev);
+  else rowsum_partial_kernel<false><<<grid, RS_THREADS, 0, s>>>(X, ld, rows, n, w, partial, stop, n_dev);
 }
 
 // out[i] = Σ_c partial[c][i] in chunk order (deterministic)
