@@ -199,8 +199,9 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
 
 /* λ̂ of the last shrinkage covariance estimate (:lw/:ss/:rblw/:oas), for parity tests. */
 int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out);
-/* Tuning knobs, not part of the reference API: "rollout_variant" (0 = fast formulation, 1 = literal
- * libm call sequence of CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel). */
+/* Tuning knobs, not part of the reference API: "rollout_variant" (3 = default, speculative straight-line
+ * step with repair; 0 = branchy fast formulation; 2 = first fast cut; 1 = literal libm call sequence of
+ * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128). */
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value);
 
 /* Device-resident control loop used by bench.py's `value` leg: state and U stay in HBM, the

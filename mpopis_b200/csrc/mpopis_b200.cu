@@ -99,7 +99,7 @@ struct mpopis_handle {
   double gamma = 0.0;
   uint64_t seed = 0;
   long long step = 0;
-  int rollout_variant = 0, rollout_block = 64, coop_max = 1, sort_max = 1;
+  int rollout_variant = 3, rollout_block = 64, coop_max = 1, sort_max = 1;
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
   bool L0_valid = false;
   mpopis_cma_t cma{};
@@ -980,7 +980,8 @@ int mpopis_b200_seed(mpopis_t *h, uint64_t seed) {
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
   if (!h || !key) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (!strcmp(key, "rollout_variant")) {
-    if (value != 0.0 && value != 1.0 && value != 2.0) return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1 or 2");
+    if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
+      return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1, 2 or 3");
     h->rollout_variant = (int)value;
   }
   else if (!strcmp(key, "rollout_block")) {
@@ -1131,7 +1132,7 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
   if (int rc = dalloc(&dj, (size_t)n)) return rc;
   if (int rc = dalloc(&dw, (size_t)n)) return rc;
   CU(cudaMemcpyAsync(dp, pos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->st));
-  launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->rollout_variant == 0, h->st);
+  launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->rollout_variant == 0 || h->rollout_variant == 3, h->st);
   h->launches += 1;
   if (idx_out) CU(cudaMemcpyAsync(idx_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));
   if (idx2_out) CU(cudaMemcpyAsync(idx2_out, dj, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));

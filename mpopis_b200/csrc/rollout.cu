@@ -31,415 +31,35 @@
 // indices equal the reference's Float64 evaluation bit for bit.
 #include <math_constants.h>
 
+#include "car_model.cuh"
 #include "engine.cuh"
 
 namespace mpopis {
-
-// fdlibm __kernel_sin / __kernel_cos minimax coefficients (|x| <= π/4, error < 2^-57)
-__constant__ double kSinCos[12] = {
-    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
-    2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10,
-    4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
-    -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
-
-__device__ __forceinline__ double jl_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
-__device__ __forceinline__ double clamp1(double v) { return fmin(fmax(v, -1.0), 1.0); }
-
-// sin/cos on |x| <= ~π/4 (no range reduction)
-__device__ __forceinline__ void sincos_kernel(double x, double *s, double *c) {
-  const double z = x * x;
-  double ps = fma(z, kSinCos[5], kSinCos[4]);
-  ps = fma(z, ps, kSinCos[3]);
-  ps = fma(z, ps, kSinCos[2]);
-  ps = fma(z, ps, kSinCos[1]);
-  ps = fma(z, ps, kSinCos[0]);
-  *s = fma(x * z, ps, x);
-  double pc = fma(z, kSinCos[11], kSinCos[10]);
-  pc = fma(z, pc, kSinCos[9]);
-  pc = fma(z, pc, kSinCos[8]);
-  pc = fma(z, pc, kSinCos[7]);
-  pc = fma(z, pc, kSinCos[6]);
-  *c = fma(z * z, pc, fma(-0.5, z, 1.0));
-}
-
-// sin/cos for |x| <= π(1+ε): quadrant reduction with a two-term π/2, then the kernels
-__device__ __forceinline__ void sincos_pi(double x, double *s, double *c) {
-  const double kf = rint(x * 0.63661977236758138);
-  double r = fma(-kf, 1.5707963267948966, x);
-  r = fma(-kf, 6.123233995736766e-17, r);
-  const int k = (int)kf;
-  double sr, cr;
-  sincos_kernel(r, &sr, &cr);
-  const double s1 = (k & 1) ? cr : sr, c1 = (k & 1) ? -sr : cr;
-  *s = (k & 2) ? -s1 : s1;
-  *c = (k & 2) ? -c1 : c1;
-}
-
-// n/d without the IEEE slow path: reciprocal seed (2^-23), two Newton steps, one residual correction
-__device__ __forceinline__ double fast_div(double n, double d) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  r = fma(fma(-d, r, 1.0), r, r);
-  r = fma(fma(-d, r, 1.0), r, r);
-  const double q = n * r;
-  return fma(fma(-d, q, n), r, q);
-}
-
-struct TrackView {
-  const double *x, *y, *w;
-  int n;
-  // exact pruning table (nullptr = always scan): cell -> {count, up to 7 candidate indices} as 8 x u16
-  const uint4 *lut;
-  double x0, y0, inv_c;
-  int nx, ny;
-};
-
-// within_track(track, pos) TRK:68-92. Integer-exact: distances use un-fused mul/add.
-template <bool USE_LUT>
-__device__ __forceinline__ bool within_track(const TrackView &tr, double px, double py, int *idx_out,
-                                             int *idx2_out, double *dist_out) {
-  int mi = 0;
-  double best = CUDART_INF;
-  bool done = false;
-  if (USE_LUT && tr.lut) {
-    const double fx = (px - tr.x0) * tr.inv_c, fy = (py - tr.y0) * tr.inv_c;
-    if (fx >= 0.0 && fy >= 0.0 && fx < (double)tr.nx && fy < (double)tr.ny) {
-      const uint4 cell = __ldg(tr.lut + (int)fy * tr.nx + (int)fx);
-      const unsigned cnt = cell.x & 0xffffu;
-      if (cnt <= 7u) {
-        const unsigned long long w0 = ((unsigned long long)cell.y << 32) | cell.x;
-        const unsigned long long w1 = ((unsigned long long)cell.w << 32) | cell.z;
-        for (unsigned q = 0; q < cnt; ++q) {  // candidates are stored in ascending index order
-          const int i = (int)(((q < 3u) ? (w0 >> (16u * q + 16u)) : (w1 >> (16u * (q - 3u)))) & 0xffffu);
-          const double dx = tr.x[i] - px, dy = tr.y[i] - py;
-          const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-          if (d < best) best = d, mi = i;
-        }
-        done = true;
-      }
-    }
-  }
-  if (!done) {
-#pragma unroll 4
-    for (int i = 0; i < tr.n; ++i) {  // TRK:71,73 (findmin -> FIRST minimum: strict <)
-      const double dx = tr.x[i] - px, dy = tr.y[i] - py;
-      const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      if (d < best) best = d, mi = i;
-    }
-  }
-  const int m1 = mi == 0 ? tr.n - 1 : mi - 1, p1 = mi == tr.n - 1 ? 0 : mi + 1;  // mod1, TRK:75-76
-  const double ax = tr.x[m1] - px, ay = tr.y[m1] - py, bx = tr.x[p1] - px, by = tr.y[p1] - py;
-  // TRK:77-79 compares norms: sqrt is monotone and correctly rounded, so the squared distances decide
-  // unless they are within a few ulps of each other — only then are the two square roots taken.
-  const double qa = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
-  const double qb = __dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by));
-  int m2;
-  if (USE_LUT && fabs(qa - qb) > 1e-14 * fmax(qa, qb)) m2 = qa < qb ? m1 : p1;
-  else m2 = __dsqrt_rn(qa) <= __dsqrt_rn(qb) ? m1 : p1;
-  const double p1x = tr.x[mi], p1y = tr.y[mi];
-  const double vx = tr.x[m2] - p1x, vy = tr.y[m2] - p1y, ux = px - p1x, uy = py - p1y;
-  const double t = (ux * vx + uy * vy) / (vx * vx + vy * vy);  // TRK:87 (projection on the infinite line)
-  const double ex = p1x + t * vx - px, ey = p1y + t * vy - py; // TRK:88
-  const double dist = sqrt(ex * ex + ey * ey);                 // TRK:89
-  if (idx_out) *idx_out = mi;
-  if (idx2_out) *idx2_out = m2;
-  *dist_out = dist;
-  return dist < tr.w[mi];  // TRK:90
-}
-
-// Tyre-force constants that depend only on (pedal, sign(Vx)); CAR:310-318 + the invariant part
-// of calc_tire_fy CAR:252-260.
-struct TireConsts {
-  double fxf, fxr;           // longitudinal split, CAR:315-316
-  double fymax_f, fymax_r;   // sqrt(max((μ fz)² − fx², 1e-8)), CAR:253
-  double thr_f, thr_r;       // 3 fy_max / C  (tan of the sliding angle), CAR:255
-  double c2_f, c2_r;         // C² / (3 fy_max)
-  double c3_f, c3_r;         // C³ / (27 fy_max²)
-};
-
-__device__ __forceinline__ TireConsts tire_consts(const CarParams &P, double accel, double bk,
-                                                  double split, double sgnVx) {
-  TireConsts c;
-  const double fx = accel + bk * sgnVx;  // CAR:310-312
-  c.fxf = split * fx;
-  c.fxr = (1 - split) * fx;
-  const double L = P.l_r + P.l_f;
-  const double fzf = (P.m * P.l_r * 9.81 - P.h_cm * fx) / L;  // calc_tire_fz 'f', CAR:262-272
-  const double fzr = (P.m * P.l_f * 9.81 + P.h_cm * fx) / L;  // calc_tire_fz 'r'
-  c.fymax_f = sqrt(fmax((P.mu_f * fzf) * (P.mu_f * fzf) - c.fxf * c.fxf, 1e-8));
-  c.fymax_r = sqrt(fmax((P.mu_r * fzr) * (P.mu_r * fzr) - c.fxr * c.fxr, 1e-8));
-  c.thr_f = 3 * c.fymax_f / P.C_af;
-  c.thr_r = 3 * c.fymax_r / P.C_ar;
-  c.c2_f = (P.C_af * P.C_af) / (3 * c.fymax_f);
-  c.c2_r = (P.C_ar * P.C_ar) / (3 * c.fymax_r);
-  c.c3_f = (P.C_af * P.C_af * P.C_af) / (27 * (c.fymax_f * c.fymax_f));
-  c.c3_r = (P.C_ar * P.C_ar * P.C_ar) / (27 * (c.fymax_r * c.fymax_r));
-  return c;
-}
-
-// Same constants with one rsqrt per tyre instead of a sqrt and three divisions (fast v3): with
-// v = max((μ fz)² − fx², 1e-8): fy_max = v·rsqrt(v), 1/fy_max = rsqrt(v); divisions by the car's constants
-// become multiplications by their reciprocals (loop-invariant, hoisted by the compiler).
-__device__ __forceinline__ TireConsts tire_consts_fast(const CarParams &P, double accel, double bk,
-                                                       double split, double sgnVx) {
-  TireConsts c;
-  const double fx = accel + bk * sgnVx;  // CAR:310-312
-  c.fxf = split * fx;
-  c.fxr = (1 - split) * fx;
-  const double invL = 1.0 / (P.l_r + P.l_f);
-  const double fzf = (P.m * P.l_r * 9.81 - P.h_cm * fx) * invL;
-  const double fzr = (P.m * P.l_f * 9.81 + P.h_cm * fx) * invL;
-  const double vf = fmax((P.mu_f * fzf) * (P.mu_f * fzf) - c.fxf * c.fxf, 1e-8);
-  const double vr = fmax((P.mu_r * fzr) * (P.mu_r * fzr) - c.fxr * c.fxr, 1e-8);
-  const double rf = rsqrt(vf), rr = rsqrt(vr);
-  c.fymax_f = vf * rf;
-  c.fymax_r = vr * rr;
-  c.thr_f = c.fymax_f * (3.0 / P.C_af);
-  c.thr_r = c.fymax_r * (3.0 / P.C_ar);
-  c.c2_f = (P.C_af * P.C_af / 3.0) * rf;
-  c.c2_r = (P.C_ar * P.C_ar / 3.0) * rr;
-  c.c3_f = (P.C_af * P.C_af * P.C_af / 27.0) * (rf * rf);
-  c.c3_r = (P.C_ar * P.C_ar * P.C_ar / 27.0) * (rr * rr);
-  return c;
-}
-
-// brush-tyre lateral force from tan α = num/den with |α| < π (fast paths, Vx > 0)
-template <int MODE>
-__device__ __forceinline__ double tire_fy_ratio(double num, double den, double C, double c2, double c3,
-                                                double thr, double fymax) {
-  const double ta = MODE == 0 ? fast_div(num, den) : num / den;
-  const double cubic = -C * ta + c2 * fabs(ta) * ta - c3 * (ta * ta * ta);
-  const double sat = -fymax * jl_sign(num);
-  return (den > 0.0 && fabs(ta) < thr) ? cubic : sat;
-}
-
-// literal calc_tire_fy, CAR:252-260
-__device__ __forceinline__ double tire_fy_literal(double alpha, double C, double c2, double c3,
-                                                  double thr, double fymax) {
-  const double ta = tan(alpha);
-  if (fabs(alpha) < atan(thr)) return -C * ta + c2 * fabs(ta) * ta - c3 * (ta * ta * ta);
-  return -fymax * jl_sign(alpha);
-}
-
-// _step!(env::CarRacingEnv, a), CAR:282-344. s = [x, y, Ψ, Vx, Vy, Ψ̇, δ, pedal].
-__device__ __forceinline__ void car_step_fast(const CarParams &P, double dt, double ddt, int nsub, double *s,
-                                              double a0, double a1);
-
-template <int MODE>
-__device__ __forceinline__ void car_step(const CarParams &P, double dt, double ddt, int nsub, double *s,
-                                         double a0, double a1) {
-  if constexpr (MODE == 0) {
-    car_step_fast(P, dt, ddt, nsub, s, a0, a1);
-    return;
-  }
-  constexpr bool FAST = MODE != 1;
-  double x = s[0], y = s[1], psi = s[2], Vx = s[3], Vy = s[4], psid = s[5], delta = s[6];
-  const double tgt = a0 * P.d_max - delta;
-  const double rate = fmin(fabs(tgt) / dt, P.dd_max) * jl_sign(tgt);  // CAR:295-296
-  const double pedal = a1;                                           // CAR:297
-  const double accel = P.Fx_max * fmax(pedal, 0.0);                  // CAR:310
-  const double bk = P.Fx_min * fmin(pedal, 0.0);                     // CAR:311 without sign(Vx)
-  const double split = pedal <= 0.0 ? P.l_brake : P.l_drive;
-  const double inv_Izz = 1 / P.Izz, inv_m = 1 / P.m;                 // CAR:322-324 multiply by (1/·)
-  double sg = jl_sign(Vx);
-  TireConsts tc = tire_consts(P, accel, bk, split, sg);
-  for (int i = 0; i < nsub; ++i) {
-    delta += rate * ddt;  // CAR:301
-    const double sg_now = jl_sign(Vx);
-    if (sg_now != sg) {  // sign(Vx) flipped: brake force changes direction (rare)
-      sg = sg_now;
-      if (bk != 0.0) tc = tire_consts(P, accel, bk, split, sg);
-    }
-    double sd, cd;
-    if (MODE == 0 && fabs(delta) <= 0.8) sincos_kernel(delta, &sd, &cd);
-    else sincos(delta, &sd, &cd);
-    const double yf = Vy + P.l_f * psid, yr = Vy - P.l_r * psid;
-    double fyf, fyr;
-    if (FAST && Vx > 0.0) {
-      // tan(atan(yf, Vx) − δ) = (yf cδ − Vx sδ)/(Vx cδ + yf sδ); rear: tan α_r = yr / Vx
-      fyf = tire_fy_ratio<MODE>(yf * cd - Vx * sd, Vx * cd + yf * sd, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f,
-                                tc.fymax_f);
-      fyr = tire_fy_ratio<MODE>(yr, Vx, P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
-    } else {
-      const double a_f = atan2(yf, Vx) - delta;  // CAR:304
-      const double a_r = atan2(yr, Vx);          // CAR:305
-      fyf = tire_fy_literal(a_f, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
-      fyr = tire_fy_literal(a_r, P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
-    }
-    const double fx_aero = (P.C_D0 + P.C_D1 * fabs(Vx)) * sg;  // CAR:308
-    const double psidd = inv_Izz * (P.l_f * (tc.fxf * sd + fyf * cd) - P.l_r * fyr);        // CAR:322
-    const double Vy_dot = inv_m * (fyf * cd + tc.fxf * sd + fyr) - psid * Vx;               // CAR:323
-    const double Vx_dot = inv_m * (tc.fxf * cd - fyf * sd + tc.fxr - fx_aero) + psid * Vy;  // CAR:324
-    psid += psidd * ddt;  // CAR:326
-    Vx += Vx_dot * ddt;   // CAR:327
-    Vy += Vy_dot * ddt;   // CAR:328
-    psi += psid * ddt;    // CAR:329
-    double sp, cp;
-    if (FAST) {  // CAR:330: atan(sin Ψ, cos Ψ) == Ψ on (−π, π], otherwise Ψ − 2π·round(Ψ/2π)
-      if (fabs(psi) > CUDART_PI) {
-        const double k = rint(psi * 0.15915494309189535);
-        psi = fma(-k, 6.283185307179586, psi);
-        psi = fma(-k, 2.4492935982947064e-16, psi);
-      }
-      if (MODE == 0) sincos_pi(psi, &sp, &cp);
-      else sincos(psi, &sp, &cp);
-    } else {
-      sincos(psi, &sp, &cp);
-      psi = atan2(sp, cp);
-      sincos(psi, &sp, &cp);
-    }
-    x += (Vx * cp - Vy * sp) * ddt;  // CAR:331
-    y += (Vx * sp + Vy * cp) * ddt;  // CAR:332
-  }
-  s[0] = x, s[1] = y, s[2] = psi, s[3] = Vx, s[4] = Vy, s[5] = psid, s[6] = delta, s[7] = pedal;
-}
-
-// Short sin/cos for a small rotation increment (|x| <= 0.03: truncation error < 1e-18 relative)
-__device__ __forceinline__ void sincos_tiny(double x, double *s, double *c) {
-  const double z = x * x;
-  double ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);
-  ps = fma(z, ps, -1.6666666666666666e-01);
-  *s = fma(x * z, ps, x);
-  const double pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);
-  *c = fma(z * z, pc, fma(-0.5, z, 1.0));
-}
-
-// MODE 0 ("fast v3") implementation of _step! (CAR:282-344). On top of the v1/v2 reformulations:
-//   * sin/cos of δ by the angle-addition recurrence (δ advances by the constant rate·δt inside a control
-//     step and never overshoots its target, so |δ| <= max(|δ₀|, |a₁ δ_max|));
-//   * sin/cos of Ψ by rotating (sin Ψ, cos Ψ) with the per-sub-step increment Ψ̇·δt; both recurrences are
-//     re-synchronised with a full evaluation at every control step, so drift is bounded by nsub roundings;
-//     Ψ itself is accumulated and wrapped once per step (the wrap is the identity modulo 2π);
-//   * forward motion (Vx > 0, the case for every realistic rollout) needs no sign bookkeeping and shares
-//     ONE reciprocal between the front and rear slip ratios; anything else takes the general path.
-__device__ __forceinline__ void car_step_fast(const CarParams &P, double dt, double ddt, int nsub, double *s,
-                                              double a0, double a1) {
-  double x = s[0], y = s[1], psi = s[2], Vx = s[3], Vy = s[4], psid = s[5], delta = s[6];
-  const double tgt = a0 * P.d_max - delta;
-  const double rate = fmin(fabs(tgt) / dt, P.dd_max) * jl_sign(tgt);  // CAR:295-296
-  const double pedal = a1;                                           // CAR:297
-  const double accel = P.Fx_max * fmax(pedal, 0.0);                  // CAR:310
-  const double bk = P.Fx_min * fmin(pedal, 0.0);                     // CAR:311 without sign(Vx)
-  const double split = pedal <= 0.0 ? P.l_brake : P.l_drive;
-  const double inv_Izz = 1 / P.Izz, inv_m = 1 / P.m;
-  double sg = jl_sign(Vx);
-  TireConsts tc = tire_consts_fast(P, accel, bk, split, sg);
-  const double dlt = rate * ddt;
-  const bool small = fmax(fabs(delta), fabs(a0 * P.d_max)) <= 0.78;
-  double sd, cd, sdl = 0.0, cdl = 1.0;
-  if (small) {
-    sincos_kernel(delta, &sd, &cd);
-    sincos_kernel(dlt, &sdl, &cdl);
-  }
-  if (fabs(psi) > CUDART_PI) {  // callers may hand in any heading; CAR:330 keeps it in (−π, π] afterwards
-    const double k = rint(psi * 0.15915494309189535);
-    psi = fma(-k, 6.283185307179586, psi);
-    psi = fma(-k, 2.4492935982947064e-16, psi);
-  }
-  double sp, cp;
-  sincos_pi(psi, &sp, &cp);
-  // ncu: the dominant stall is "wait" (fixed-latency FP64 dependencies) at ~3 warps per scheduler; unrolling
-  // by two lets the scheduler overlap the position/heading tail of one sub-step with the next tyre chain.
-#pragma unroll 2
-  for (int i = 0; i < nsub; ++i) {
-    delta += dlt;  // CAR:301
-    if (small) {
-      const double ns = fma(sd, cdl, cd * sdl);
-      cd = fma(cd, cdl, -(sd * sdl));
-      sd = ns;
-    } else {
-      sincos(delta, &sd, &cd);
-    }
-    const double yf = Vy + P.l_f * psid, yr = Vy - P.l_r * psid;
-    double fyf, fyr, fx_aero;
-    if (Vx > 0.0 && sg > 0.0) {
-      // tan(atan(yf, Vx) − δ) = num/den, tan α_r = yr / Vx (CAR:304-305 without atan/tan)
-      const double num = yf * cd - Vx * sd, den = Vx * cd + yf * sd;
-      double ta_r;
-      if (den > 0.0) {
-        const double dv = den * Vx;
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dv));  // 2^-23 seed
-        const double e = fma(-dv, r, 1.0);
-        r = fma(r, fma(e, e, e), r);                             // r(1 + e + e²): error e³ = 2^-69
-        const double ta = (num * Vx) * r;
-        ta_r = (yr * den) * r;
-        // −C t + c2 |t| t − c3 t³ = t·(−C + |t|·(c2 − c3 |t|))   (CAR:256, Horner form)
-        const double at = fabs(ta);
-        const double cubic = ta * fma(at, fma(-tc.c3_f, at, tc.c2_f), -P.C_af);
-        fyf = at < tc.thr_f ? cubic : copysign(tc.fymax_f, -num);  // CAR:255-259
-      } else {  // |α_f| >= 90°: saturated
-        fyf = copysign(tc.fymax_f, -num);
-        ta_r = fast_div(yr, Vx);
-      }
-      const double atr = fabs(ta_r);
-      const double cubic_r = ta_r * fma(atr, fma(-tc.c3_r, atr, tc.c2_r), -P.C_ar);
-      fyr = atr < tc.thr_r ? cubic_r : copysign(tc.fymax_r, -yr);
-      fx_aero = P.C_D0 + P.C_D1 * Vx;  // CAR:308 with sign(Vx) = 1
-    } else {
-      const double sg_now = jl_sign(Vx);
-      if (sg_now != sg) {  // sign(Vx) flipped: brake force changes direction
-        sg = sg_now;
-        if (bk != 0.0) tc = tire_consts_fast(P, accel, bk, split, sg);
-      }
-      if (Vx > 0.0) {
-        fyf = tire_fy_ratio<0>(yf * cd - Vx * sd, Vx * cd + yf * sd, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
-        fyr = tire_fy_ratio<0>(yr, Vx, P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
-      } else {  // reversing / standstill: the un-wrapped slip angle matters, keep the libm sequence
-        fyf = tire_fy_literal(atan2(yf, Vx) - delta, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
-        fyr = tire_fy_literal(atan2(yr, Vx), P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
-      }
-      fx_aero = (P.C_D0 + P.C_D1 * fabs(Vx)) * sg;
-    }
-    const double psidd = inv_Izz * (P.l_f * (tc.fxf * sd + fyf * cd) - P.l_r * fyr);        // CAR:322
-    const double Vy_dot = inv_m * (fyf * cd + tc.fxf * sd + fyr) - psid * Vx;               // CAR:323
-    const double Vx_dot = inv_m * (tc.fxf * cd - fyf * sd + tc.fxr - fx_aero) + psid * Vy;  // CAR:324
-    psid += psidd * ddt;  // CAR:326
-    Vx += Vx_dot * ddt;   // CAR:327
-    Vy += Vy_dot * ddt;   // CAR:328
-    const double dpsi = psid * ddt;
-    psi += dpsi;  // CAR:329 (wrapped once per step below)
-    double sdp, cdp;
-    if (fabs(dpsi) <= 0.03) sincos_tiny(dpsi, &sdp, &cdp);
-    else if (fabs(dpsi) <= 0.8) sincos_kernel(dpsi, &sdp, &cdp);  // spinning car: still no libdevice call
-    else sincos(dpsi, &sdp, &cdp);
-    const double nsp = fma(sp, cdp, cp * sdp);
-    cp = fma(cp, cdp, -(sp * sdp));
-    sp = nsp;
-    x += (Vx * cp - Vy * sp) * ddt;  // CAR:331
-    y += (Vx * sp + Vy * cp) * ddt;  // CAR:332
-  }
-  if (fabs(psi) > CUDART_PI) {  // CAR:330
-    const double k = rint(psi * 0.15915494309189535);
-    psi = fma(-k, 6.283185307179586, psi);
-    psi = fma(-k, 2.4492935982947064e-16, psi);
-  }
-  s[0] = x, s[1] = y, s[2] = psi, s[3] = Vx, s[4] = Vy, s[5] = psid, s[6] = delta, s[7] = pedal;
-}
-
-// reward(env::CarRacingEnv), CAR:201-213
-template <int MODE>
-__device__ __forceinline__ double car_reward(const CarParams &P, double cos_bl, const TrackView &tr,
-                                             const double *s) {
-  double dist;
-  const bool within = within_track<MODE == 0>(tr, s[0], s[1], nullptr, nullptr, &dist);
-  const double speed = sqrt(s[3] * s[3] + s[4] * s[4]);
-  const bool exceed = MODE != 1 ? (s[3] < cos_bl * speed) : (fabs(atan2(s[4], s[3])) > P.b_limit);  // CAR:181-189
-  double rew = 0.0;
-  if (!within) rew += -1000000.0;
-  if (exceed) rew += -5000.0;
-  rew += -dist;
-  rew += 2.0 * speed;
-  return rew;
-}
 
 // (env)(a) + reward(env) for 1..N cars: CAR:238-241 / MCR:200-207, MCR:145-158
 template <int NCARS, int MODE>
 __device__ __forceinline__ double cars_step_reward(const CarEnvArgs &env, const TrackView &tr, double *s,
                                                    const double *a) {
+  if constexpr (MODE == 3) {  // every car's straight-line step first (independent chains), then the rare repairs
+    double o[8 * NCARS];
+    bool ok[NCARS];
 #pragma unroll
-  for (int c = 0; c < NCARS; ++c)
-    car_step<MODE>(env.car[c], env.dt, env.ddt, env.nsub, s + 8 * c, a[2 * c], a[2 * c + 1]);
+    for (int c = 0; c < NCARS; ++c)
+      ok[c] = car_step_spec(env.car[c], env.dt, env.ddt, env.nsub, s + 8 * c, o + 8 * c, a[2 * c], a[2 * c + 1]);
+#pragma unroll
+    for (int c = 0; c < NCARS; ++c) {
+      if (ok[c]) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[8 * c + q] = o[8 * c + q];
+      } else {
+        car_step_fast(env.car[c], env.dt, env.ddt, env.nsub, s + 8 * c, a[2 * c], a[2 * c + 1]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCARS; ++c)
+      car_step<MODE>(env.car[c], env.dt, env.ddt, env.nsub, s + 8 * c, a[2 * c], a[2 * c + 1]);
+  }
   double rew = 0.0;
 #pragma unroll
   for (int c = 0; c < NCARS; ++c) {
@@ -465,7 +85,7 @@ __device__ __forceinline__ TrackView stage_track(const CarEnvArgs &env, double *
 }
 
 template <int NCARS, int MODE>
-__global__ void __launch_bounds__(128) rollout_car_kernel(const __grid_constant__ CarEnvArgs env,
+__global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(const __grid_constant__ CarEnvArgs env,
                                                           const __grid_constant__ RolloutArgs a,
                                                           const int *stop) {
   extern __shared__ double smem[];
@@ -565,7 +185,7 @@ static void launch_rollout_car_v(const CarEnvArgs &env, const RolloutArgs &a, in
     MPOPIS_LAUNCH(3)
     MPOPIS_LAUNCH(4)
   }
-  if constexpr (MODE == 0) {  // 5..8 cars: only the default variant is instantiated (build time)
+  if constexpr (MODE == 0 || MODE == 3) {  // 5..8 cars: only the production variants are instantiated (build time)
     switch (env.n_cars) {
       MPOPIS_LAUNCH(5)
       MPOPIS_LAUNCH(6)
@@ -578,7 +198,8 @@ static void launch_rollout_car_v(const CarEnvArgs &env, const RolloutArgs &a, in
 
 void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, const int *stop,
                         cudaStream_t st) {
-  if (variant == 0 || env.n_cars > 4) launch_rollout_car_v<0>(env, a, block, stop, st);
+  if (variant == 3) launch_rollout_car_v<3>(env, a, block, stop, st);
+  else if (variant == 0 || env.n_cars > 4) launch_rollout_car_v<0>(env, a, block, stop, st);
   else if (variant == 1) launch_rollout_car_v<1>(env, a, block, stop, st);
   else launch_rollout_car_v<2>(env, a, block, stop, st);
 }
@@ -649,7 +270,7 @@ void launch_env_step_car(const CarEnvArgs &env, double *state, const double *act
       cudaFuncSetAttribute(env_step_car_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     env_step_car_kernel<M><<<1, 32, smem, st>>>(env, state, action, env_t, reward);                          \
   }
-  if (variant == 0) MPOPIS_ES(0) else if (variant == 1) MPOPIS_ES(1) else MPOPIS_ES(2)
+  if (variant == 0) MPOPIS_ES(0) else if (variant == 1) MPOPIS_ES(1) else if (variant == 3) MPOPIS_ES(3) else MPOPIS_ES(2)
 #undef MPOPIS_ES
 }
 
@@ -681,7 +302,7 @@ void launch_env_reward_car(const CarEnvArgs &env, const double *state, double *r
       cudaFuncSetAttribute(env_reward_car_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     env_reward_car_kernel<M><<<1, 32, smem, st>>>(env, state, reward);                                       \
   }
-  if (variant == 0) MPOPIS_ER(0) else if (variant == 1) MPOPIS_ER(1) else MPOPIS_ER(2)
+  if (variant == 0) MPOPIS_ER(0) else if (variant == 1) MPOPIS_ER(1) else if (variant == 3) MPOPIS_ER(3) else MPOPIS_ER(2)
 #undef MPOPIS_ER
 }
 

@@ -33,9 +33,10 @@ def assert_costs_close(got, ref, max_flip_frac=2e-3):
     return flips
 
 
-def pair(gpu_bound, orc, policy, env, K, T, N=10, variant=0, **kw):
+def pair(gpu_bound, orc, policy, env, K, T, N=10, variant=None, **kw):
     g = configure(Engine(gpu_bound, **engine_kwargs(policy, env, K, T, N, **kw)), env, policy)
-    g.set_option("rollout_variant", variant)
+    if variant is not None:  # otherwise the engine's default (or MPOPIS_ROLLOUT_VARIANT)
+        g.set_option("rollout_variant", variant)
     c = configure(orc.engine(nthreads=8, **engine_kwargs(policy, env, K, T, N, **kw)), env, policy)
     return g, c
 
@@ -43,7 +44,7 @@ def pair(gpu_bound, orc, policy, env, K, T, N=10, variant=0, **kw):
 # ---------------------------------------------------------------------------------------------------
 # 1. golden fixtures
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_golden_rollout_costs(gpu_bound, variant):
     env = make_env("car")
     g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, 64, 50)), env, "gmppi")
@@ -92,7 +93,7 @@ def test_golden_control_step(gpu_bound, policy, envname):
 # ---------------------------------------------------------------------------------------------------
 # 2. live oracle, same seeded inputs
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 @pytest.mark.parametrize("n_cars", [1, 2, 3])
 def test_rollout_costs_vs_oracle(gpu_bound, orc, variant, n_cars):
     env = make_env("car", n_cars)
@@ -108,11 +109,13 @@ def test_rollout_costs_vs_oracle(gpu_bound, orc, variant, n_cars):
     print(f"threshold flips: {flips} of {K * len(states)}")
 
 
-def test_rollout_costs_reversing_car_and_wrap(gpu_bound, orc):
-    """Vx <= 0 takes the literal slip-angle path; |Ψ| crosses π (heading wrap)."""
+@pytest.mark.parametrize("variant", [0, 3])
+def test_rollout_costs_reversing_car_and_wrap(gpu_bound, orc, variant):
+    """Vx <= 0 takes the literal slip-angle path (variant 0) or the quadrant-aware ratio form (variant 3, with
+    the v3 repair when Vx changes sign while braking); |Ψ| crosses π (heading wrap)."""
     env = make_env("car")
     K, T = 512, 30
-    g, c = pair(gpu_bound, orc, "gmppi", env, K, T, 1)
+    g, c = pair(gpu_bound, orc, "gmppi", env, K, T, 1, variant)
     rng = np.random.default_rng(5)
     E = rng.standard_normal((g.cs, K)) * 0.5
     U = np.tile([0.8, -1.0], T)  # hard braking while steering
