@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples-per-gpu", type=int, default=K_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the K = 150 / 4096 / 2^20 side measurements")
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -277,6 +278,37 @@ def main():
                        "achieved": ach8, "peak": hbm_peak, "unit": "GB/s", "frac": ach8 / hbm_peak,
                        "ms_per_launch": ms8, "peak_source": peak_src}
 
+    # the other sizes the north star names (K ∈ {150 … 2^20}, T = 50): short device-resident runs, same timing rules
+    k_sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        k_sweep = []
+        for Ks in (150, 4096, 1 << 20):
+            env_s, eng_s = make_engine(bound, Ks, 0, 1, local_rank)
+            st_s = torch.cuda.ExternalStream(eng_s.b.stream(eng_s.h), device=torch.device("cuda", local_rank))
+            eng_s.resident_reset(state0, 0, np.zeros(eng_s.cs))
+            for _ in range(3):
+                eng_s.resident_plan(True)
+            eng_s.resident_read()
+            eng_s.resident_reset(state0, 0, np.zeros(eng_s.cs))
+            n_s = 10 if Ks <= 4096 else 4
+            ev_s = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_s)]
+            torch.cuda.synchronize()
+            with torch.cuda.stream(st_s):
+                for a, b in ev_s:
+                    flush.zero_()
+                    a.record(st_s)
+                    eng_s.resident_plan(True)
+                    b.record(st_s)
+            torch.cuda.synchronize()
+            ms_s = sum(a.elapsed_time(b) for a, b in ev_s)
+            its_s = eng_s.resident_total_its()
+            eng_s.resident_read()  # synchronises and completes the engine's own CUDA-event timings
+            tm_s = eng_s.last_timing()
+            k_sweep.append({"K": Ks, "ms_per_step": ms_s / n_s, "its_per_step": its_s / n_s,
+                            "rollout_steps_per_s": Ks * T * its_s / (ms_s * 1e-3),
+                            "rollout_ms_per_launch": tm_s["rollout_ms"] / max(tm_s["rollout_launches"], 1)})
+            eng_s.close()
+
     line = dict(base, value=value, ms_per_step=dev_ms / args.steps,
                 config={"workload": workload, "l2": "flushed between steps (256 MiB memset outside the timed intervals)",
                         "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU"},
@@ -284,7 +316,7 @@ def main():
                      "ms_per_step": e2e_s / args.steps * 1e3},
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_fp64=roofline_fp64,
                 roofline_g8=roofline_g8,
-                fp64_peak_dfma_per_s=fp64_peak, its_per_step=its_total / args.steps)
+                fp64_peak_dfma_per_s=fp64_peak, its_per_step=its_total / args.steps, k_sweep=k_sweep)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         K_cpu = 8192

@@ -61,7 +61,9 @@ typedef enum {
 
 typedef enum {
   MPOPIS_ENV_CAR_RACING = 0,  /* CarRacingEnv (n_cars = 1, CAR) or MultiCarRacingEnv (n_cars > 1, MCR) */
-  MPOPIS_ENV_MOUNTAIN_CAR = 1 /* RLEnvs MountainCarEnv(continuous=true) + EXM:4-22 */
+  MPOPIS_ENV_MOUNTAIN_CAR = 1, /* RLEnvs MountainCarEnv(continuous=true) + EXM:4-22 */
+  MPOPIS_ENV_EXTERNAL = 2      /* the caller's own batched simulator behind the EnvpoolEnv seam (POL:148,240; UTL:103):
+                                  the engine samples / adapts / weights, a callback rolls the K controls out */
 } mpopis_env_t;
 
 /* CEMPPI_Policy Σ_est, POL:414-426 */
@@ -93,7 +95,8 @@ typedef struct mpopis_cfg {
   int32_t device;             /* CUDA device ordinal */
   int32_t rank;               /* shard index of this handle, 0 <= rank < world_size */
   int32_t world_size;         /* number of handles sharing the K samples (1 = unsharded) */
-  int32_t reserved[4];
+  int32_t ext_action_size;    /* MPOPIS_ENV_EXTERNAL only: as = action_space_size(action_space(env)), UTL:2-7 */
+  int32_t reserved[3];
 } mpopis_cfg_t;
 
 /* CMA-ES constants computed by the CMAMPPI_Policy constructor (POL:513-525). The host side
@@ -134,6 +137,10 @@ int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params18_
  * and max_steps. */
 int mpopis_b200_set_mountaincar_env(mpopis_t *h, const double *params7, int64_t max_steps);
 
+/* MPOPIS_ENV_EXTERNAL: the action bounds leftendpoint/rightendpoint(action_space(env)) (as doubles each) that
+ * get_model_controls clamps to (UTL:31-32,42-43). */
+int mpopis_b200_set_external_env(mpopis_t *h, const double *action_lo, const double *action_hi);
+
 /* pol.Σ: n = as (expanded with block_diagm over the horizon, UTL:9-21, POL:76-78) or n = cs. */
 int mpopis_b200_set_sigma(mpopis_t *h, const double *Sigma, int64_t n);
 /* pol.ws (K doubles) and the scalar CMA constants (POL:478-496). */
@@ -154,6 +161,22 @@ int mpopis_b200_plan(mpopis_t *h, const double *state, int64_t env_t, double *U_
 int mpopis_b200_plan_with_noise(mpopis_t *h, const double *state, int64_t env_t, double *U_inout,
                                 const double *Z, const double *resample_u, double *control_out,
                                 int32_t *its_run_out);
+/* The EnvpoolEnv seam. `rollout` replaces rollout_model(env::EnvpoolEnv, T, model_controls, pol) UTL:103-121: it
+ * receives the clamped model controls of all K samples exactly as get_model_controls(action_space, Vₖ, T) UTL:42-53
+ * shapes them — a K x as x T column-major array, controls[k + K*(r + as*t)] — steps its own batched simulator
+ * from the current real state, writes traj_cost[k] = −Σ_t reward (UTL:110-111), restores the simulator
+ * (reset!(env; restore=true), UTL:119) and returns 0 (non-zero aborts the plan with MPOPIS_ERR_BAD_ARG).
+ * It is called on the calling thread, once per executed AIS iteration, between device phases. */
+typedef int (*mpopis_rollout_fn)(void *user, const double *controls, int64_t K, int64_t as, int64_t T,
+                                 double *traj_cost_out);
+/* pol(env::EnvpoolEnv): simulate_model(pol, env::EnvpoolEnv, E, Σ_inv, U_orig) POL:240-259 (and the :mppi method
+ * POL:148-184) inside the policy's calculate_trajectory_costs, then the weighted update and get_controls_roll_U!.
+ * Sampling, the control cost γ U_origᵀ Σ⁻¹ (Vₖ − U_orig) (POL:248), adaptation, weights and the control run on
+ * the device; only the K x cs controls (D2H) and the K costs (H2D) cross per iteration. Z / resample_u as in
+ * plan_with_noise (NULL = the engine's Philox stream). Handle must have been created with MPOPIS_ENV_EXTERNAL. */
+int mpopis_b200_plan_external(mpopis_t *h, double *U_inout, mpopis_rollout_fn rollout, void *user, const double *Z,
+                              const double *resample_u, double *control_out, int32_t *its_run_out);
+
 /* Results of the last plan(): trajectory_cost (K), weights (K), E (cs x K, shifted as in POL:468),
  * logger trajectories (K matrices T x ss, column-major, sample k at offset k*T*ss; needs
  * cfg.log_trajectories). Any pointer may be NULL. With world_size > 1 only this rank's shard
@@ -201,7 +224,8 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
 int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out);
 /* Tuning knobs, not part of the reference API: "rollout_variant" (3 = default, speculative straight-line
  * step with repair; 0 = branchy fast formulation; 2 = first fast cut; 1 = literal libm call sequence of
- * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128). */
+ * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128), "apply_l" (E = L·Z kernel,
+ * process-wide: 0 = DFMA register tile, 1 = DMMA 32-row blocks, 2 = DMMA column tiles with cp.async). */
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value);
 
 /* Device-resident control loop used by bench.py's `value` leg: state and U stay in HBM, the

@@ -8,7 +8,7 @@ side — the same constructors, symbols and entry points a Julia user of MPOPIS.
 There is no CPU path: constructing/calling a policy without the built library and a B200 raises.
 """
 from ._abi import ABI_VERSION
-from .envs import (CarRacingEnv, CarRacingEnvParams, MountainCarEnv, MountainCarEnvParams, MultiCarRacingEnv,
+from .envs import (CarRacingEnv, CarRacingEnvParams, ExternalEnv, MountainCarEnv, MountainCarEnvParams, MultiCarRacingEnv,
                    calculate_β, exceed_β, reward, state, within_track)
 from .examples import quantile_ci, simulate_car_racing, simulate_mountaincar
 from .policies import (CEMPPI_Policy, CMAMPPI_Policy, GMPPI_Policy, IMPPI_Policy, MPPI_Policy, PMCMPPI_Policy,
@@ -19,7 +19,7 @@ from .tracks import Track
 __all__ = [
     "ABI_VERSION", "MPPI_Policy", "GMPPI_Policy", "IMPPI_Policy", "CEMPPI_Policy", "CMAMPPI_Policy",
     "μAISMPPI_Policy", "μΣAISMPPI_Policy", "PMCMPPI_Policy", "Track", "CarRacingEnv", "CarRacingEnvParams",
-    "MultiCarRacingEnv", "MountainCarEnv", "MountainCarEnvParams", "within_track", "calculate_β", "exceed_β",
+    "MultiCarRacingEnv", "ExternalEnv", "MountainCarEnv", "MountainCarEnvParams", "within_track", "calculate_β", "exceed_β",
     "block_diagm", "action_space_size", "reward", "state", "get_policy", "seed_b", "cma_constants",
     "simulate_car_racing", "simulate_mountaincar", "quantile_ci",
 ]

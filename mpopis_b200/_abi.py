@@ -21,7 +21,7 @@ POLICY = {
     # ASCII aliases for the Unicode symbols of example_utils.jl:87,100
     "muaismppi": 5, "musigmaaismppi": 6,
 }
-ENV_CAR_RACING, ENV_MOUNTAIN_CAR = 0, 1
+ENV_CAR_RACING, ENV_MOUNTAIN_CAR, ENV_EXTERNAL = 0, 1, 2
 SIGMA_EST = {"mle": 0, "lw": 1, "ss": 2, "rblw": 3, "oas": 4}
 
 
@@ -33,7 +33,7 @@ class Cfg(C.Structure):
         ("ce_elite_threshold", C.c_double),
         ("sigma_est", C.c_int32), ("early_stop", C.c_int32), ("log_trajectories", C.c_int32),
         ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("ext_action_size", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -50,6 +50,8 @@ _I32 = C.POINTER(C.c_int32)
 _I64 = C.POINTER(C.c_int64)
 _U8 = C.POINTER(C.c_uint8)
 _H = C.c_void_p
+# mpopis_rollout_fn: int (*)(void *user, const double *controls, int64 K, int64 as, int64 T, double *traj_cost_out)
+ROLLOUT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _D, C.c_int64, C.c_int64, C.c_int64, _D)
 
 # name -> (restype, argtypes). `h` = opaque handle.
 SIGNATURES = {
@@ -58,6 +60,8 @@ SIGNATURES = {
     "destroy": (C.c_int, [_H]),
     "set_car_env": (C.c_int, [_H, C.c_int32, _D, C.c_double, C.c_double, _D, _D, _D, C.c_int64]),
     "set_mountaincar_env": (C.c_int, [_H, _D, C.c_int64]),
+    "set_external_env": (C.c_int, [_H, _D, _D]),
+    "plan_external": (C.c_int, [_H, _D, ROLLOUT_FN, C.c_void_p, _D, _D, _D, _I32]),
     "set_sigma": (C.c_int, [_H, _D, C.c_int64]),
     "set_cma": (C.c_int, [_H, C.POINTER(Cma), _D, C.c_int64]),
     "seed": (C.c_int, [_H, C.c_uint64]),

@@ -4,6 +4,7 @@
 // without a GPU. See rollout.cu for the description of the variants (MODE 0..3).
 #pragma once
 #include <math.h>
+#include <string.h>
 #include <math_constants.h>
 
 #include "engine.cuh"
@@ -34,6 +35,7 @@ MPOPIS_HD double add_rn(double a, double b) { return add_rn(a, b); }
 MPOPIS_HD double sqrt_rn(double a) { return sqrt_rn(a); }
 MPOPIS_HD double rsqrt_f64(double a) { return rsqrt(a); }
 MPOPIS_HD uint4 ldg_u4(const uint4 *p) { return __ldg(p); }
+MPOPIS_HD double inf_f64() { return CUDART_INF; }
 #else
 #define MPOPIS_SC(i) kSinCosHost[i]
 MPOPIS_HD double rcp_seed(double d) { return (double)(float)(1.0 / d); }
@@ -42,6 +44,7 @@ MPOPIS_HD double add_rn(double a, double b) { return a + b; }
 MPOPIS_HD double sqrt_rn(double a) { return sqrt(a); }
 MPOPIS_HD double rsqrt_f64(double a) { return 1.0 / sqrt(a); }
 MPOPIS_HD uint4 ldg_u4(const uint4 *p) { return *p; }
+MPOPIS_HD double inf_f64() { return HUGE_VAL; }
 #endif
 
 MPOPIS_HD double jl_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
@@ -100,7 +103,7 @@ template <bool USE_LUT>
 MPOPIS_HD bool within_track(const TrackView &tr, double px, double py, int *idx_out,
                                              int *idx2_out, double *dist_out) {
   int mi = 0;
-  double best = INFINITY;
+  double best = inf_f64();
   bool done = false;
   if (USE_LUT && tr.lut) {
     const double fx = (px - tr.x0) * tr.inv_c, fy = (py - tr.y0) * tr.inv_c;
@@ -204,6 +207,29 @@ MPOPIS_HD TireConsts tire_consts_fast(const CarParams &P, double accel, double b
   return c;
 }
 
+// tire_consts_fast with the car-only factors taken from CarDerived (constant bank)
+MPOPIS_HD TireConsts tire_consts_der(const CarParams &P, const CarDerived &D, double accel, double bk, double split,
+                                     double sgnVx) {
+  TireConsts c;
+  const double fx = accel + bk * sgnVx;  // CAR:310-312
+  c.fxf = split * fx;
+  c.fxr = (1 - split) * fx;
+  const double fzf = (D.wf - P.h_cm * fx) * D.inv_L;
+  const double fzr = (D.wr + P.h_cm * fx) * D.inv_L;
+  const double vf = fmax((P.mu_f * fzf) * (P.mu_f * fzf) - c.fxf * c.fxf, 1e-8);
+  const double vr = fmax((P.mu_r * fzr) * (P.mu_r * fzr) - c.fxr * c.fxr, 1e-8);
+  const double rf = rsqrt_f64(vf), rr = rsqrt_f64(vr);
+  c.fymax_f = vf * rf;
+  c.fymax_r = vr * rr;
+  c.thr_f = c.fymax_f * D.thrC_f;
+  c.thr_r = c.fymax_r * D.thrC_r;
+  c.c2_f = D.c2C_f * rf;
+  c.c2_r = D.c2C_r * rr;
+  c.c3_f = D.c3C_f * (rf * rf);
+  c.c3_r = D.c3C_r * (rr * rr);
+  return c;
+}
+
 // brush-tyre lateral force from tan α = num/den with |α| < π (fast paths, Vx > 0)
 template <int MODE>
 MPOPIS_HD double tire_fy_ratio(double num, double den, double C, double c2, double c3,
@@ -225,8 +251,8 @@ MPOPIS_HD double tire_fy_literal(double alpha, double C, double c2, double c3,
 // _step!(env::CarRacingEnv, a), CAR:282-344. s = [x, y, Ψ, Vx, Vy, Ψ̇, δ, pedal].
 MPOPIS_HD void car_step_fast(const CarParams &P, double dt, double ddt, int nsub, double *s,
                                               double a0, double a1);
-MPOPIS_HD bool car_step_spec(const CarParams &P, double dt, double ddt, int nsub, const double *s,
-                                              double *o, double a0, double a1);
+MPOPIS_HD bool car_step_spec(const CarParams &P, const CarDerived &D, double dt, double ddt, int nsub,
+                             const double *s, double *o, double a0, double a1);
 
 template <int MODE>
 MPOPIS_HD void car_step(const CarParams &P, double dt, double ddt, int nsub, double *s,
@@ -237,7 +263,8 @@ MPOPIS_HD void car_step(const CarParams &P, double dt, double ddt, int nsub, dou
   }
   if constexpr (MODE == 3) {
     double o[8];
-    if (car_step_spec(P, dt, ddt, nsub, s, o, a0, a1)) {
+    const CarDerived D = derive_car(P, ddt);  // env_step / host checker; the rollout kernel passes env.der[c]
+    if (car_step_spec(P, D, dt, ddt, nsub, s, o, a0, a1)) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) s[q] = o[q];
     } else {
@@ -429,37 +456,65 @@ MPOPIS_HD void car_step_fast(const CarParams &P, double dt, double ddt, int nsub
   s[0] = x, s[1] = y, s[2] = psi, s[3] = Vx, s[4] = Vy, s[5] = psid, s[6] = delta, s[7] = pedal;
 }
 
-// MODE 3 ("fast v4"): the v3 arithmetic as straight-line code. ncu's opcode mix of v3 shows ≈10 BRA and 6 BSSY/BSYNC
-// pairs per sub-step: the data-dependent branches (Vx > 0, den > 0, |Ψ̇ δt| <= 0.03, sign flips) cut the sub-step
-// into basic blocks the scheduler cannot overlap, and at ~3.5 warps per scheduler the kernel then waits on
-// FP64 dependency chains. Here one control step is integrated SPECULATIVELY without any branch:
-//   * the brush-tyre force is written for every Vx != 0 (not only Vx > 0): tan α is the rotated ratio for any
+// MODE 3 ("fast v4"): one control step integrated SPECULATIVELY as straight-line code, repaired by v3 when invalid.
+//
+// What the profiles said (profiles/README.md, round 1): v3 executes ≈10 BRA and 6 BSSY/BSYNC pairs per sub-step, yet
+// removing them alone changed nothing (305 vs 297 µs): at K = 65 536 the four SM sub-partitions hold {4,4,3,3} warps
+// and the loaded ones run the FP64 pipe at ≈80-90 % — the kernel is bound by the NUMBER OF FP64-PIPE INSTRUCTIONS
+// (DFMA/DMUL/DADD and DSETP alike, 2 issue cycles each). So this variant spends its effort there:
+//   * the brush-tyre force is written for every Vx != 0 (not only Vx > 0): tan α is the rotated ratio in any
 //     quadrant (tan has period π); |α| < atan(thr) <=> cos α > 0 and |tan α| < thr, with cos α_f ∝ den,
 //     cos α_r ∝ Vx (|δ| <= 0.78 keeps the un-wrapped α_f inside (−3π/2, 3π/2)); in saturation sign(α) is
-//     sign(sin α) for Vx > 0 and the sign bit of the numerator of atan2 for Vx < 0 (atan2 ∈ ±(π/2, π]);
-//   * aero drag is copysign(C_D0 + C_D1 |Vx|, Vx);
-//   * the conditions under which this is NOT the reference's arithmetic — Vx or den exactly 0, a sign change of
-//     Vx while braking (the tyre constants hold sign(Vx), CAR:311), a yaw increment beyond the short sincos
-//     polynomial, |δ| > 0.78 — are accumulated in a predicate; the caller then discards the speculative state and
-//     integrates that control step again with car_step_fast (v3, all branches). On the bench workload up to 10 % of
-//     the rollouts slide backwards (Vx < 0) at some point, which v3 sends through the libm atan2/tan sequence for
-//     the whole warp; here they stay on the straight-line path.
+//     sign(sin α) for Vx > 0 and the sign bit of atan2's numerator for Vx < 0 (atan2 ∈ ±(π/2, π]). On the bench
+//     workload up to 10 % of the rollouts slide backwards at some point; v3 sends their whole warp through the
+//     libm atan2/tan sequence, here they stay on the straight-line path;
+//   * sign tests (Vx > 0, den > 0), the validity tests (den·Vx normal, |Ψ̇ δt| small) and the ±fy_max selection
+//     are integer operations on the high words (ALU pipe) instead of DSETP / DADD-negations (FP64 pipe);
+//   * the Euler updates are folded: Ψ̇ += c₁A − c₂F_yr, Vy += c_m(A + F_yr) − (Ψ̇δt)Vx, Vx = k_x Vx + c_m(B + F_xr ∓ C_D0)
+//     + (Ψ̇δt)Vy with A = F_yf cos δ + F_xf sin δ, B = F_xf cos δ − F_yf sin δ, k_x = 1 − c_m C_D1 (the aero term's
+//     linear part), re-using the previous sub-step's Ψ̇δt: 60 FP64-pipe instructions per sub-step instead of 75.
+//     This re-associates CAR:322-328 (differences of a few ulp per sub-step; tests/test_host_step.py bounds the
+//     deviation from the literal step);
+//   * conditions under which this is NOT the reference's arithmetic — den·Vx zero/denormal, a sign change of Vx
+//     while braking (the tyre constants hold sign(Vx), CAR:311), a yaw increment beyond the short sincos polynomial,
+//     |δ| > 0.78 — are accumulated in a predicate; the caller then discards the speculative state and integrates that
+//     control step again with car_step_fast (v3, all branches).
 // Returns true when the speculative result `o` is valid.
-MPOPIS_HD bool car_step_spec(const CarParams &P, double dt, double ddt, int nsub, const double *s,
-                                              double *o, double a0, double a1) {
+MPOPIS_HD int hi32(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2hiint(x);
+#else
+  long long b;
+  memcpy(&b, &x, sizeof b);
+  return (int)(b >> 32);
+#endif
+}
+// magnitude of `mag` (>= 0) with the sign opposite to the sign bit carried by the high word `shi`
+MPOPIS_HD double with_opposite_sign(double mag, int shi) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double(__double2hiint(mag) | (~shi & (int)0x80000000), __double2loint(mag));
+#else
+  return (shi < 0) ? mag : -mag;
+#endif
+}
+
+MPOPIS_HD bool car_step_spec(const CarParams &P, const CarDerived &D, double dt, double ddt, int nsub,
+                             const double *s, double *o, double a0, double a1) {
   double x = s[0], y = s[1], psi = s[2], Vx = s[3], Vy = s[4], psid = s[5], delta = s[6];
   const double tgt = a0 * P.d_max - delta;
   const double rate = fmin(fast_div(fabs(tgt), dt), P.dd_max) * jl_sign(tgt);  // CAR:295-296
-  const double pedal = a1;                                           // CAR:297
-  const double accel = P.Fx_max * fmax(pedal, 0.0);                  // CAR:310
-  const double bk = P.Fx_min * fmin(pedal, 0.0);                     // CAR:311 without sign(Vx)
+  const double pedal = a1;                                                    // CAR:297
+  const double accel = P.Fx_max * fmax(pedal, 0.0);                           // CAR:310
+  const double bk = P.Fx_min * fmin(pedal, 0.0);                              // CAR:311 without sign(Vx)
   const double split = pedal <= 0.0 ? P.l_brake : P.l_drive;
-  const double inv_Izz = 1 / P.Izz, inv_m = 1 / P.m;
   const double sg = jl_sign(Vx);
-  const TireConsts tc = tire_consts_fast(P, accel, bk, split, sg);
+  const TireConsts tc = tire_consts_der(P, D, accel, bk, split, sg);
   const double dlt = rate * ddt;
-  const double q = bk != 0.0 ? sg : 0.0;  // Vx·q < 0: the brake force changed direction (tc is stale)
-  bool ok = (fmax(fabs(delta), fabs(a0 * P.d_max)) <= 0.78) & (Vx != 0.0) & (fabs(dlt) <= 0.03);
+  // validity is accumulated in the SIGN BIT of an integer (ALU pipe, no predicates): a sign change of Vx while
+  // braking, den·Vx zero/denormal, |Ψ̇ δt| > 0.03 (or NaN)
+  const int hvx0 = hi32(Vx), brake_mask = bk != 0.0 ? (int)0x80000000 : 0;
+  int bad = 0;
+  const bool pre_ok = (fmax(fabs(delta), fabs(a0 * P.d_max)) <= 0.78) & (Vx != 0.0) & (fabs(dlt) <= 0.03);
   double sd, cd, sdl, cdl;
   sincos_kernel(delta, &sd, &cd);
   sincos_tiny(dlt, &sdl, &cdl);  // |rate·δt| <= δ̇_max·δt = 0.0157 for the default car
@@ -470,51 +525,53 @@ MPOPIS_HD bool car_step_spec(const CarParams &P, double dt, double ddt, int nsub
   }
   double sp, cp;
   sincos_pi(psi, &sp, &cp);
+  double dpsi = psid * ddt;  // Ψ̇·δt of the CURRENT Ψ̇: the −Ψ̇Vx / +Ψ̇Vy terms of this sub-step, the heading step of the last
 #pragma unroll 2
   for (int i = 0; i < nsub; ++i) {
-    delta += dlt;  // CAR:301
-    const double ns = fma(sd, cdl, cd * sdl);
+    const double ns = fma(sd, cdl, cd * sdl);  // sin/cos(δ + rate·δt), CAR:301
     cd = fma(cd, cdl, -(sd * sdl));
     sd = ns;
-    const double yf = Vy + P.l_f * psid, yr = Vy - P.l_r * psid;
-    const double num = yf * cd - Vx * sd, den = Vx * cd + yf * sd;  // tan α_f = num/den, tan α_r = yr/Vx
+    const double yf = fma(P.l_f, psid, Vy), yr = fma(-P.l_r, psid, Vy);
+    const double num = fma(yf, cd, -(Vx * sd)), den = fma(Vx, cd, yf * sd);  // tan α_f = num/den, tan α_r = yr/Vx
     const double dv = den * Vx;
-    ok = ok & (dv != 0.0) & (Vx * q >= 0.0);
-    double r = rcp_seed(dv);
+    const int hvx = hi32(Vx);
+    const bool fwd = hvx >= 0;
+    bad |= ((hvx ^ hvx0) & brake_mask) | ((hi32(dv) & 0x7ff00000) - 0x00100000);
+    double r = rcp_seed(dv);  // 2^-23 seed
     const double e = fma(-dv, r, 1.0);
     r = fma(r, fma(e, e, e), r);  // r(1 + e + e²): error e³ = 2^-69
     const double ta = (num * Vx) * r, ta_r = (yr * den) * r;
     const double at = fabs(ta), atr = fabs(ta_r);
     const double cubic = ta * fma(at, fma(-tc.c3_f, at, tc.c2_f), -P.C_af);  // CAR:256, Horner form
     const double cubic_r = ta_r * fma(atr, fma(-tc.c3_r, atr, tc.c2_r), -P.C_ar);
-    const bool fwd = Vx > 0.0;
-    const double fyf = ((den > 0.0) & (at < tc.thr_f)) ? cubic : copysign(tc.fymax_f, fwd ? -num : -yf);  // CAR:255-259
-    const double fyr = (fwd & (atr < tc.thr_r)) ? cubic_r : copysign(tc.fymax_r, -yr);
-    const double fx_aero = copysign(P.C_D0 + P.C_D1 * fabs(Vx), Vx);                        // CAR:308
-    const double psidd = inv_Izz * (P.l_f * (tc.fxf * sd + fyf * cd) - P.l_r * fyr);        // CAR:322
-    const double Vy_dot = inv_m * (fyf * cd + tc.fxf * sd + fyr) - psid * Vx;               // CAR:323
-    const double Vx_dot = inv_m * (tc.fxf * cd - fyf * sd + tc.fxr - fx_aero) + psid * Vy;  // CAR:324
-    psid += psidd * ddt;  // CAR:326
-    Vx += Vx_dot * ddt;   // CAR:327
-    Vy += Vy_dot * ddt;   // CAR:328
-    const double dpsi = psid * ddt;
+    const double fyf = ((hi32(den) >= 0) & (at < tc.thr_f)) ? cubic  // CAR:255-259
+                                                             : with_opposite_sign(tc.fymax_f, fwd ? hi32(num) : hi32(yf));
+    const double fyr = (fwd & (atr < tc.thr_r)) ? cubic_r : with_opposite_sign(tc.fymax_r, hi32(yr));
+    const double A = fma(fyf, cd, tc.fxf * sd), B = fma(-fyf, sd, tc.fxf * cd);
+    const double psid_n = fma(D.cI1, A, fma(-D.cI2, fyr, psid));                              // CAR:322,326
+    const double Vy_n = fma(D.cm, A + fyr, fma(-dpsi, Vx, Vy));                             // CAR:323,328
+    // CAR:308,324,327: −c_m·fx_aero = −c_m C_D1 Vx − copysign(c_m C_D0, Vx)
+    const double Vx_n = fma(D.cm, B + tc.fxr, fma(dpsi, Vy, fma(Vx, D.kx, with_opposite_sign(D.cmCD0, hvx))));
+    psid = psid_n, Vx = Vx_n, Vy = Vy_n;
+    dpsi = psid * ddt;
     psi += dpsi;  // CAR:329 (wrapped once per step below)
-    ok = ok & (fabs(dpsi) <= 0.03);
+    bad |= 0x3F9EB851 - (hi32(dpsi) & 0x7fffffff);  // |Ψ̇ δt| > 0.03 or NaN
     double sdp, cdp;
     sincos_tiny(dpsi, &sdp, &cdp);
     const double nsp = fma(sp, cdp, cp * sdp);
     cp = fma(cp, cdp, -(sp * sdp));
     sp = nsp;
-    x += (Vx * cp - Vy * sp) * ddt;  // CAR:331
-    y += (Vx * sp + Vy * cp) * ddt;  // CAR:332
+    x = fma(fma(Vx, cp, -(Vy * sp)), ddt, x);  // CAR:331
+    y = fma(fma(Vx, sp, Vy * cp), ddt, y);     // CAR:332
   }
+  delta = fma((double)nsub, dlt, delta);  // CAR:301 summed
   if (fabs(psi) > CUDART_PI) {  // CAR:330
     const double k = rint(psi * 0.15915494309189535);
     psi = fma(-k, 6.283185307179586, psi);
     psi = fma(-k, 2.4492935982947064e-16, psi);
   }
   o[0] = x, o[1] = y, o[2] = psi, o[3] = Vx, o[4] = Vy, o[5] = psid, o[6] = delta, o[7] = pedal;
-  return ok;
+  return pre_ok & (bad >= 0);
 }
 
 // reward(env::CarRacingEnv), CAR:201-213

@@ -18,8 +18,36 @@ struct CarParams {  // CAR:2-21 in declaration order
       l_brake, l_drive, b_limit;
 };
 
+// Loop-invariant combinations of the car constants, evaluated once on the host (set_car_env) so that the rollout
+// kernel reads them as constant-bank operands instead of holding ~30 registers of hoisted values (rollout.cu v4).
+struct CarDerived {
+  double cI1, cI2;   // δt·l_f/Izz, δt·l_r/Izz                       (CAR:322,326)
+  double cm;         // δt/m                                         (CAR:323-324,327-328)
+  double kx;         // 1 − (δt/m)·C_D1: linear part of the aero drag folded into the Vx update (CAR:308)
+  double cmCD0;      // (δt/m)·C_D0
+  double inv_L;      // 1/(l_f + l_r)                                (CAR:262-272)
+  double wf, wr;     // m·l_r·9.81, m·l_f·9.81
+  double thrC_f, thrC_r;  // 3/C_αf, 3/C_αr                          (CAR:255)
+  double c2C_f, c2C_r;    // C_α²/3
+  double c3C_f, c3C_r;    // C_α³/27
+};
+
+inline __host__ __device__ CarDerived derive_car(const CarParams &P, double ddt) {
+  CarDerived D;
+  const double cI = ddt * (1 / P.Izz);
+  D.cI1 = cI * P.l_f, D.cI2 = cI * P.l_r, D.cm = ddt * (1 / P.m);
+  D.kx = 1.0 - D.cm * P.C_D1, D.cmCD0 = D.cm * P.C_D0;
+  D.inv_L = 1.0 / (P.l_r + P.l_f);
+  D.wf = P.m * P.l_r * 9.81, D.wr = P.m * P.l_f * 9.81;
+  D.thrC_f = 3.0 / P.C_af, D.thrC_r = 3.0 / P.C_ar;
+  D.c2C_f = P.C_af * P.C_af / 3.0, D.c2C_r = P.C_ar * P.C_ar / 3.0;
+  D.c3C_f = P.C_af * P.C_af * P.C_af / 27.0, D.c3C_r = P.C_ar * P.C_ar * P.C_ar / 27.0;
+  return D;
+}
+
 struct CarEnvArgs {
   CarParams car[MPOPIS_MAX_CARS];
+  CarDerived der[MPOPIS_MAX_CARS];
   double cos_blimit[MPOPIS_MAX_CARS];  // cos(β_limit) for the atan-free β test (fast path)
   double dt, ddt;
   int nsub;  // round(Int, dt/δt), CAR:299
@@ -82,6 +110,7 @@ void launch_philox_uniforms(double *u, int K, uint64_t seed, uint32_t step, uint
                             cudaStream_t s);
 void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E, long long ldk, int K,
                     const int *stop, cudaStream_t s);
+void set_apply_L_path(int path);  // 0 DFMA tile, 1 DMMA row blocks, 2 DMMA column tiles (process-wide)
 void launch_transpose_in(const double *colmajor, double *dev, int cs, int K, long long ldk, cudaStream_t s);
 void launch_transpose_out(const double *dev, double *colmajor, int cs, int K, long long ldk, const double *shift_a,
                           const double *shift_b, cudaStream_t s);

@@ -133,6 +133,12 @@ struct mpopis_handle {
   int *stop() { return d_flags; }
   int *its() { return d_flags + 1; }
   int *info() { return d_flags + 2; }
+  // external-simulator seam (MPOPIS_ENV_EXTERNAL): callback of the running plan_external, pinned staging, bounds
+  mpopis_rollout_fn ext_fn = nullptr;
+  void *ext_user = nullptr;
+  double *h_ext_controls = nullptr, *h_ext_costs = nullptr, *d_ext_cc = nullptr, *d_ext_in = nullptr,
+         *d_ext_bounds = nullptr;
+  int *h_ext_stop = nullptr;
   // pinned staging
   double *h_in = nullptr, *h_out = nullptr;
   int *h_flags = nullptr;
@@ -368,7 +374,56 @@ int sharded_ce_select(mpopis_t *h, int m) {
   return 0;
 }
 
+// ---- external-simulator seam (EnvpoolEnv methods POL:148-184, 240-259; UTL:42-53, 103-121) ------------------
+// controls[k + K*(r)] = clamp(pol.U[r] + E[r,k], lo[r % as], hi[r % as]) with r = a + as*t: the K x as x T column-major
+// array get_model_controls(action_space, Vₖ, T) returns (UTL:42-53) — the device's own [cs][k] layout with pitch K.
+// cc[k] = (γ U_origᵀ Σ⁻¹)·(Vₖ − U_orig) (POL:248); one thread per sample, coalesced in k.
+__global__ void ext_controls_kernel(const double *__restrict__ E, long long ldk, const double *__restrict__ U_cur,
+                                    const double *__restrict__ U_orig, const double *__restrict__ bvec,
+                                    const double *__restrict__ bounds, int as, int cs, int K,
+                                    double *__restrict__ controls, double *__restrict__ cc, const int *stop) {
+  if (stop && *stop) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double acc = 0.0;
+  for (int r = 0; r < cs; ++r) {
+    const double v = U_cur[r] + E[(size_t)r * ldk + k];  // POL:252
+    if (bvec) acc += bvec[r] * (v - U_orig[r]);
+    const int a = r % as;
+    controls[(size_t)r * K + k] = fmin(fmax(v, bounds[a]), bounds[as + a]);
+  }
+  cc[k] = acc;
+}
+
+__global__ void ext_costs_kernel(const double *__restrict__ traj_cost, const double *__restrict__ cc, int K,
+                                 double *__restrict__ costs, const int *stop) {
+  if (stop && *stop) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) costs[k] = traj_cost[k] + cc[k];  // POL:256
+}
+
+int ext_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, const double *bvec) {
+  if (!h->ext_fn) return fail(MPOPIS_ERR_BAD_ARG, "external env: use mpopis_b200_plan_external");
+  const int K = h->Kloc, cs = h->cs;
+  cudaStream_t st = h->st;
+  ext_controls_kernel<<<(K + 127) / 128, 128, 0, st>>>(h->d_E, h->ldk, U_cur, U_orig, bvec, h->d_ext_bounds, h->as, cs, K,
+                                                       h->d_stage, h->d_ext_cc, h->stop());
+  CU(cudaMemcpyAsync(h->h_ext_controls, h->d_stage, sizeof(double) * cs * K, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_ext_stop, h->stop(), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  h->launches += 1;
+  if (*h->h_ext_stop) return 0;  // early stop (POL:459-461): this iteration is not executed
+  if (h->ext_fn(h->ext_user, h->h_ext_controls, K, h->as, h->T, h->h_ext_costs) != 0)
+    return fail(MPOPIS_ERR_BAD_ARG, "external rollout callback reported an error");
+  CU(cudaMemcpyAsync(h->d_ext_in, h->h_ext_costs, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+  ext_costs_kernel<<<(K + 255) / 256, 256, 0, st>>>(h->d_ext_in, h->d_ext_cc, K, h->d_costs + h->k0, h->stop());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, const double *bvec) {
+  if (h->cfg.env == MPOPIS_ENV_EXTERNAL) return ext_rollouts(h, U_cur, U_orig, bvec);
   RolloutArgs a{};
   a.E = h->d_E, a.ldk = h->ldk, a.U = U_cur, a.U_orig = U_orig, a.bvec = bvec;
   a.state0 = h->d_state, a.env_t = h->d_env_t, a.costs = h->d_costs + h->k0;
@@ -642,11 +697,11 @@ int ensure_elite_capacity(mpopis_t *h, int m) {
 }
 
 int upload_inputs(mpopis_t *h, const double *state, int64_t env_t, const double *U) {
-  memcpy(h->h_in, state, sizeof(double) * h->ss);
+  if (h->ss) memcpy(h->h_in, state, sizeof(double) * h->ss);
   memcpy(h->h_in + h->ss, U, sizeof(double) * h->cs);
   long long t = env_t;
   memcpy(h->h_in + h->ss + h->cs, &t, sizeof t);
-  CU(cudaMemcpyAsync(h->d_state, h->h_in, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));
+  if (h->ss) CU(cudaMemcpyAsync(h->d_state, h->h_in, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(h->d_U_orig, h->h_in + h->ss, sizeof(double) * h->cs, cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(h->d_env_t, h->h_in + h->ss + h->cs, sizeof(long long), cudaMemcpyHostToDevice, h->st));
   return 0;
@@ -714,6 +769,13 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
     h->as = 2 * cfg->n_cars, h->ss = 8 * cfg->n_cars;
   } else if (cfg->env == MPOPIS_ENV_MOUNTAIN_CAR) {
     h->as = 1, h->ss = 2;
+  } else if (cfg->env == MPOPIS_ENV_EXTERNAL) {
+    if (cfg->ext_action_size < 1 || cfg->ext_action_size > 4096 || world > 1 || cfg->log_trajectories) {
+      delete h;
+      return fail(MPOPIS_ERR_BAD_ARG, "external env: ext_action_size must be in 1..4096, world_size 1 and "
+                                      "log_trajectories 0 (the simulator's states stay with the caller)");
+    }
+    h->as = cfg->ext_action_size, h->ss = 0;
   } else {
     delete h;
     return fail(MPOPIS_ERR_BAD_ARG, "unknown env %d", cfg->env);
@@ -810,6 +872,15 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
     TRY(dalloc(&h->d_ns, 5 * cs * cs + 8));
   }
   if (cfg->log_trajectories) TRY(dalloc(&h->d_traj, Kloc * (size_t)h->T * h->ss));
+  if (cfg->env == MPOPIS_ENV_EXTERNAL) {
+    TRY(dalloc(&h->d_ext_cc, Kloc));
+    TRY(dalloc(&h->d_ext_in, Kloc));
+    TRY(dalloc(&h->d_ext_bounds, 2 * (size_t)h->as));
+    if (cudaMallocHost((void **)&h->h_ext_controls, sizeof(double) * cs * Kloc) != cudaSuccess ||
+        cudaMallocHost((void **)&h->h_ext_costs, sizeof(double) * Kloc) != cudaSuccess ||
+        cudaMallocHost((void **)&h->h_ext_stop, sizeof(int)) != cudaSuccess)
+      return bail(fail(MPOPIS_ERR_CUDA, "cudaMallocHost failed"));
+  }
   if (cudaMallocHost((void **)&h->h_in, sizeof(double) * (h->ss + cs + 2)) != cudaSuccess ||
       cudaMallocHost((void **)&h->h_out, sizeof(double) * (h->as + cs + h->ss + 2)) != cudaSuccess ||
       cudaMallocHost((void **)&h->h_flags, sizeof(int) * 4) != cudaSuccess)
@@ -849,6 +920,12 @@ int mpopis_b200_destroy(mpopis_t *h) {
                   h->d_bvec2};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  if (h->h_ext_controls) cudaFreeHost(h->h_ext_controls);
+  if (h->h_ext_costs) cudaFreeHost(h->h_ext_costs);
+  if (h->h_ext_stop) cudaFreeHost(h->h_ext_stop);
+  if (h->d_ext_cc) cudaFree(h->d_ext_cc);
+  if (h->d_ext_in) cudaFree(h->d_ext_in);
+  if (h->d_ext_bounds) cudaFree(h->d_ext_bounds);
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -898,6 +975,7 @@ int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params, d
     h->car.cos_blimit[c] = h->car.car[c].b_limit >= M_PI ? -2.0 : std::cos(h->car.car[c].b_limit);
   }
   h->car.dt = dt, h->car.ddt = ddt, h->car.nsub = (int)lrint(dt / ddt);  // CAR:299
+  for (int c = 0; c < n_cars; ++c) h->car.der[c] = derive_car(h->car.car[c], ddt);
   h->car.n_cars = n_cars, h->car.n_trk = (int)n_trk;
   if (h->d_trk) cudaFree(h->d_trk), h->d_trk = nullptr;
   if (int rc = dalloc(&h->d_trk, 3 * (size_t)n_trk)) return rc;
@@ -988,6 +1066,9 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     const int b = (int)value;
     if (b < 32 || b > 128 || b % 32) return fail(MPOPIS_ERR_BAD_ARG, "rollout_block must be 32, 64, 96 or 128");
     h->rollout_block = b;
+  } else if (!strcmp(key, "apply_l")) {
+    if (value != 0.0 && value != 1.0 && value != 2.0) return fail(MPOPIS_ERR_BAD_ARG, "apply_l must be 0, 1 or 2");
+    set_apply_L_path((int)value);  // process-wide
   } else
     return fail(MPOPIS_ERR_BAD_ARG, "unknown option %s", key);
   return 0;
@@ -1010,6 +1091,35 @@ int mpopis_b200_plan_with_noise(mpopis_t *h, const double *state, int64_t env_t,
 int mpopis_b200_plan(mpopis_t *h, const double *state, int64_t env_t, double *U_inout, double *control_out,
                      int32_t *its_run_out) {
   return mpopis_b200_plan_with_noise(h, state, env_t, U_inout, nullptr, nullptr, control_out, its_run_out);
+}
+
+int mpopis_b200_set_external_env(mpopis_t *h, const double *action_lo, const double *action_hi) {
+  if (!h || !action_lo || !action_hi) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->cfg.env != MPOPIS_ENV_EXTERNAL) return fail(MPOPIS_ERR_BAD_ARG, "handle was created for a different environment");
+  for (int a = 0; a < h->as; ++a)
+    if (!(action_lo[a] <= action_hi[a])) return fail(MPOPIS_ERR_BAD_ARG, "action bounds: lo must be <= hi");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemcpy(h->d_ext_bounds, action_lo, sizeof(double) * h->as, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_ext_bounds + h->as, action_hi, sizeof(double) * h->as, cudaMemcpyHostToDevice));
+  h->env_set = true;
+  return 0;
+}
+
+int mpopis_b200_plan_external(mpopis_t *h, double *U_inout, mpopis_rollout_fn rollout, void *user, const double *Z,
+                              const double *resample_u, double *control_out, int32_t *its_run_out) {
+  if (!h || !U_inout || !rollout || !control_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->cfg.env != MPOPIS_ENV_EXTERNAL) return fail(MPOPIS_ERR_BAD_ARG, "handle was not created with MPOPIS_ENV_EXTERNAL");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemsetAsync(h->info(), 0, sizeof(int), h->st));
+  if (int rc = upload_inputs(h, nullptr, 0, U_inout)) return rc;
+  h->ext_fn = rollout, h->ext_user = user;
+  const int rc = plan_core(h, Z, resample_u);
+  h->ext_fn = nullptr, h->ext_user = nullptr;
+  if (rc) {
+    cudaStreamSynchronize(h->st);
+    return rc;
+  }
+  return download_outputs(h, U_inout, control_out, its_run_out, nullptr);
 }
 
 int mpopis_b200_fetch(mpopis_t *h, double *costs, double *weights, double *E, double *traj) {
@@ -1157,6 +1267,7 @@ int mpopis_b200_env_step(mpopis_t *h, double *state_inout, const double *action,
                          double *reward_out, uint8_t *done_out) {
   if (!h || !state_inout || !action || !env_t_inout) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (!h->env_set) return fail(MPOPIS_ERR_BAD_ARG, "environment not set");
+  if (h->cfg.env == MPOPIS_ENV_EXTERNAL) return fail(MPOPIS_ERR_BAD_ARG, "external env: the simulator lives with the caller");
   if (int rc = set_device(h)) return rc;
   long long t = *env_t_inout;
   CU(cudaMemcpyAsync(h->d_state, state_inout, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));

@@ -45,7 +45,8 @@ __device__ __forceinline__ double cars_step_reward(const CarEnvArgs &env, const 
     bool ok[NCARS];
 #pragma unroll
     for (int c = 0; c < NCARS; ++c)
-      ok[c] = car_step_spec(env.car[c], env.dt, env.ddt, env.nsub, s + 8 * c, o + 8 * c, a[2 * c], a[2 * c + 1]);
+      ok[c] = car_step_spec(env.car[c], env.der[c], env.dt, env.ddt, env.nsub, s + 8 * c, o + 8 * c, a[2 * c],
+                            a[2 * c + 1]);
 #pragma unroll
     for (int c = 0; c < NCARS; ++c) {
       if (ok[c]) {

@@ -227,20 +227,146 @@ __global__ void __launch_bounds__(128) apply_L_dmma_kernel(const double *__restr
   }
 }
 
-static int apply_L_path() {  // MPOPIS_APPLY_L=fma selects the DFMA kernel (A/B evidence, profiles/)
-  static int path = -1;
-  if (path < 0) {
-    const char *e = getenv("MPOPIS_APPLY_L");
-    path = (e && e[0] == 'f') ? 0 : 1;
-  }
-  return path;
+// Second DMMA formulation (MPOPIS_APPLY_L=2): the kernel above re-reads Z once per 32-row block (2.9x for
+// cs = 100), stages L and Z single-buffered between two barriers and leaves the triangle's load imbalance to
+// the block scheduler. Here ONE CTA owns a 64-sample column tile and ALL rows of a 104-row block (13 row
+// fragments of 8), so Z streams through shared memory exactly once per block, double-buffered with cp.async
+// (16-byte vectors, zero-filled past cs / ldk); L (80 KB for cs = 100, shared by every CTA) is read through
+// the read-only L1 path straight into A fragments. Seven warps: warp w owns row fragments {w, 12 − w}
+// (w = 6: fragment 6 alone) — fragment f needs j < 8f + 8, so each pair costs 14 units and the triangle is
+// balanced inside the CTA. Fragment layouts as above; Z pitch 68 doubles (≡ 4 mod 16) keeps the B-fragment
+// loads conflict-free. ncu on the first cut (2 buffers, 2 barriers per chunk, L read at the point of use): 27 % of
+// the stall samples on the barrier, 23 % on the L loads (long scoreboard), DMMA pipe 44 % busy — hence the 3-stage
+// ring (one barrier per chunk) and A fragments fetched one chunk ahead. Measured DMMA cost on B200: ≈24.5 pipe
+// cycles per m8n8k4 per SM sub-partition (≈42 FMA/clk/SM, i.e. ~2/3 of the DFMA pipe's 64).
+constexpr int D2_NF = 13, D2_RB = 8 * D2_NF, D2_BN = 64, D2_BJ = 16, D2_ZP = 68, D2_NW = 7, D2_NT = 32 * D2_NW;
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
 }
+
+__global__ void __launch_bounds__(D2_NT, 2) apply_L_dmma2_kernel(const double *__restrict__ Lt, int cs,
+                                                                  const double *__restrict__ Z,
+                                                                  double *__restrict__ E, long long ldk, int K,
+                                                                  const int *stop) {
+  if (stop && *stop) return;
+  __shared__ __align__(16) double Zs[3][D2_BJ][D2_ZP];  // 3-stage ring: one barrier per chunk
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int kbase = blockIdx.x * D2_BN, i0 = blockIdx.y * D2_RB;
+  const int jend = min(i0 + D2_RB, cs);  // rows of this block only need j < jend (zeros above the diagonal)
+  const int nchunks = (jend + D2_BJ - 1) / D2_BJ;
+  // this warp's row fragments: fb, and fa (< fb) unless w == 6; first row and exclusive j bound of each
+  const int fb = D2_NF - 1 - w, fa = w;
+  const bool has_a = w < D2_NF / 2;
+  const int rowb = i0 + 8 * fb + g, rowa = i0 + 8 * fa + g;
+  const int jmax_b = (i0 + 8 * fb < cs) ? min(i0 + 8 * fb + 8, cs) : 0;
+  const int jmax_a = (has_a && i0 + 8 * fa < cs) ? min(i0 + 8 * fa + 8, cs) : 0;
+  const double *La = Lt + (size_t)min(rowa, cs - 1) * cs, *Lb = Lt + (size_t)min(rowb, cs - 1) * cs;
+  const bool va = rowa < cs, vb = rowb < cs;
+  double acca[8][2], accb[8][2];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acca[c][0] = acca[c][1] = accb[c][0] = accb[c][1] = 0.0;
+
+  auto stage = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int jc = chunk * D2_BJ, buf = chunk % 3;
+      for (int e = threadIdx.x; e < D2_BJ * (D2_BN / 2); e += D2_NT) {
+        const int jj = e / (D2_BN / 2), v = e % (D2_BN / 2);
+        const int j = jc + jj;
+        const long long kg = (long long)kbase + 2 * v;
+        const bool pred = j < cs && kg + 1 < ldk;
+        cp_async16_zfill(&Zs[buf][jj][2 * v], pred ? (const void *)(Z + (size_t)j * ldk + kg) : (const void *)Z, pred);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // always: keeps the group count uniform
+  };
+  // A fragments (rows of L) of one chunk: 4 k-steps x {a, b}; read through L1 one chunk ahead of their use
+  auto load_A = [&](int chunk, double (&A)[4][2]) {
+    const int jc = chunk * D2_BJ;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = jc + 4 * q + t;
+      A[q][0] = (va && jc + 4 * q < jmax_a && j < cs) ? __ldg(La + j) : 0.0;
+      A[q][1] = (vb && jc + 4 * q < jmax_b && j < cs) ? __ldg(Lb + j) : 0.0;
+    }
+  };
+
+  double Ac[4][2], An[4][2];
+  stage(0);
+  stage(1);
+  load_A(0, Ac);
+  for (int c = 0; c < nchunks; ++c) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // groups 0..c have landed (c + 1 may be in flight)
+    __syncthreads();  // ... for every thread; and everyone finished chunk c − 1, whose buffer stage(c + 2) refills
+    stage(c + 2);
+    if (c + 1 < nchunks) load_A(c + 1, An);
+    const int buf = c % 3, jc = c * D2_BJ;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j4 = 4 * q;
+      const bool do_b = jc + j4 < jmax_b, do_a = jc + j4 < jmax_a;  // warp-uniform (a partial block may hold a only)
+      if (do_a | do_b) {
+        double bf[8];
+#pragma unroll
+        for (int cf = 0; cf < 8; ++cf) bf[cf] = Zs[buf][j4 + t][cf * 8 + g];
+        if (do_b) {
+#pragma unroll
+          for (int cf = 0; cf < 8; ++cf)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(accb[cf][0]), "+d"(accb[cf][1])
+                         : "d"(Ac[q][1]), "d"(bf[cf]));
+        }
+        if (do_a) {
+#pragma unroll
+          for (int cf = 0; cf < 8; ++cf)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acca[cf][0]), "+d"(acca[cf][1])
+                         : "d"(Ac[q][0]), "d"(bf[cf]));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Ac[q][0] = An[q][0], Ac[q][1] = An[q][1];
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int cf = 0; cf < 8; ++cf) {
+    const int k = kbase + cf * 8 + 2 * t;
+    if (vb && jmax_b > 0) {
+      double *dst = E + (size_t)rowb * ldk + k;
+      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(accb[cf][0], accb[cf][1]);
+      else if (k < K) dst[0] = accb[cf][0];
+    }
+    if (has_a && va && jmax_a > 0) {
+      double *dst = E + (size_t)rowa * ldk + k;
+      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acca[cf][0], acca[cf][1]);
+      else if (k < K) dst[0] = acca[cf][0];
+    }
+  }
+}
+
+// 0 = DFMA register tile, 1 = DMMA (32-row blocks), 2 = DMMA column-tile kernel; MPOPIS_APPLY_L / the
+// "apply_l" option select it process-wide (A/B evidence, profiles/).
+static int g_apply_L_path = -1;
+static int apply_L_path() {
+  if (g_apply_L_path < 0) {
+    const char *e = getenv("MPOPIS_APPLY_L");
+    g_apply_L_path = (e && e[0] == 'f') ? 0 : (e && e[0] == '2') ? 2 : 1;
+  }
+  return g_apply_L_path;
+}
+void set_apply_L_path(int path) { g_apply_L_path = path; }
 
 void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E, long long ldk, int K,
                     const int *stop, cudaStream_t s) {
   if (bs < cs) {
     dim3 grid((K + 255) / 256, cs);
     apply_L_block_kernel<<<grid, 256, 0, s>>>(Lt, cs, bs, Z, E, ldk, K, stop);
+  } else if (apply_L_path() == 2) {
+    dim3 grid((K + D2_BN - 1) / D2_BN, (cs + D2_RB - 1) / D2_RB);
+    apply_L_dmma2_kernel<<<grid, D2_NT, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);
   } else if (apply_L_path() == 1) {
     dim3 grid((K + DM_BN - 1) / DM_BN, (cs + DM_BM - 1) / DM_BM);
     apply_L_dmma_kernel<<<grid, 128, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);

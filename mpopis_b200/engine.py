@@ -43,7 +43,8 @@ class Engine:
     def __init__(self, bound: _abi.Bound, *, policy: str, env: int, n_cars: int = 1, num_samples: int,
                  horizon: int, opt_its: int = 1, lam: float = 1.0, alpha: float = 1.0, lambda_ais: float = 20.0,
                  ce_elite_threshold: float = 0.8, sigma_est: str = "mle", early_stop: bool = True,
-                 log_trajectories: bool = False, device: int = 0, rank: int = 0, world_size: int = 1):
+                 log_trajectories: bool = False, device: int = 0, rank: int = 0, world_size: int = 1,
+                 ext_action_size: int = 0):
         if policy not in _abi.POLICY:
             raise ValueError(f"No policy_type of {policy}")  # example_utils.jl:126
         if sigma_est not in _abi.SIGMA_EST:
@@ -55,11 +56,14 @@ class Engine:
             num_samples=num_samples, horizon=horizon, opt_its=opt_its, lambda_=lam, alpha=alpha,
             lambda_ais=lambda_ais, ce_elite_threshold=ce_elite_threshold, sigma_est=_abi.SIGMA_EST[sigma_est],
             early_stop=int(early_stop), log_trajectories=int(log_trajectories), device=device, rank=rank,
-            world_size=world_size)
+            world_size=world_size, ext_action_size=int(ext_action_size))
         self.K, self.T = num_samples, horizon
         self.N = 1 if policy in ("mppi", "gmppi") else opt_its
-        self.as_ = 2 * n_cars if env == _abi.ENV_CAR_RACING else 1
-        self.ss = 8 * n_cars if env == _abi.ENV_CAR_RACING else 2
+        if env == _abi.ENV_EXTERNAL:
+            self.as_, self.ss = int(ext_action_size), 0
+        else:
+            self.as_ = 2 * n_cars if env == _abi.ENV_CAR_RACING else 1
+            self.ss = 8 * n_cars if env == _abi.ENV_CAR_RACING else 2
         self.cs = self.as_ * horizon
         self.world_size, self.rank = world_size, rank
         self.Kloc = num_samples // max(world_size, 1)
@@ -92,6 +96,41 @@ class Engine:
     def set_mountaincar_env(self, params7, max_steps):
         p = _f64(params7)
         self._chk(self.b.set_mountaincar_env(self.h, _d(p), int(max_steps)))
+
+    def set_external_env(self, action_lo, action_hi):
+        lo, hi = _f64(action_lo).reshape(-1), _f64(action_hi).reshape(-1)
+        if lo.size != self.as_ or hi.size != self.as_:
+            raise ValueError("action bounds must have one entry per action component")
+        self._chk(self.b.set_external_env(self.h, _d(lo), _d(hi)))
+
+    def plan_external(self, U, rollout, Z=None, resample_u=None):
+        """pol(env::EnvpoolEnv): `rollout(controls)` gets the clamped model controls as a [K, as, T] array
+        (get_model_controls UTL:42-53) and returns the K trajectory costs −Σ_t reward (UTL:103-121)."""
+        Uio = _f64(U).copy()
+        ctrl = np.zeros(self.as_)
+        its = C.c_int32(0)
+        err = []
+
+        def trampoline(_user, controls, K, as_, T, out):
+            try:
+                ctl = np.ctypeslib.as_array(controls, shape=(T, as_, K)).transpose(2, 1, 0)  # [k, a, t] view
+                costs = np.asarray(rollout(ctl), dtype=np.float64).reshape(-1)
+                if costs.size != K:
+                    raise ValueError(f"rollout returned {costs.size} costs for {K} samples")
+                np.ctypeslib.as_array(out, shape=(K,))[:] = costs
+                return 0
+            except Exception as e:  # never unwind through the C frames
+                err.append(e)
+                return 1
+
+        cb = _abi.ROLLOUT_FN(trampoline)
+        Zc = None if Z is None else _colmajor(Z)
+        uc = None if resample_u is None else _colmajor(resample_u)
+        rc = self.b.plan_external(self.h, _d(Uio), cb, None, _d(Zc), _d(uc), _d(ctrl), C.byref(its))
+        if err:
+            raise err[0]
+        self._chk(rc)
+        return ctrl, Uio, its.value
 
     def set_sigma(self, Sigma):
         S = np.asarray(Sigma, dtype=np.float64)

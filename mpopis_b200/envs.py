@@ -281,5 +281,35 @@ class MountainCarEnv(_DeviceEnvMixin):
         return self
 
 
+class ExternalEnv:
+    """The EnvpoolEnv seam (src/envs/envpool_env.jl; POL:148-184, 240-259; UTL:42-53, 103-121): a batched
+    simulator that lives with the caller. `rollout(controls[K, as, T]) -> costs[K]` must step the simulator's K
+    model environments from the current real state with the given (already clamped) controls, return
+    −Σ_t reward per sample and restore the simulator (reset!(env; restore=true)). Sampling, control cost,
+    adaptation, weights and the control update run on the device."""
+
+    def __init__(self, action_low, action_high, rollout):
+        self.lo = np.atleast_1d(np.asarray(action_low, dtype=np.float64))
+        self.hi = np.atleast_1d(np.asarray(action_high, dtype=np.float64))
+        if self.lo.shape != self.hi.shape or self.lo.ndim != 1:
+            raise ValueError("action bounds must be vectors of the same length")
+        self.rollout = rollout
+        self.state = np.zeros(0)
+        self.t = 0
+        self.done = False
+
+    def _env_kind(self):
+        return _abi.ENV_EXTERNAL
+
+    def configure_engine(self, eng):
+        eng.set_external_env(self.lo, self.hi)
+
+    def action_space(self):
+        return self.lo, self.hi
+
+    def action_space_size(self) -> int:
+        return int(self.lo.size)
+
+
 def state(env) -> np.ndarray:
     return env.state

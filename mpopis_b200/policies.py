@@ -164,6 +164,8 @@ class AbstractPathIntegralPolicy:
                 bound = self._backend
             p = self.params
             env_kind = self.env._env_kind()
+            if env_kind == _abi.ENV_EXTERNAL:
+                self._engine_args["ext_action_size"] = self.env.action_space_size()
             self._eng = Engine(bound, policy=self.symbol, env=env_kind, n_cars=getattr(self.env, "N", 1),
                                num_samples=p.num_samples, horizon=p.horizon, opt_its=self.opt_its, lam=p.λ,
                                alpha=p.α, log_trajectories=p.log, **self._engine_args, **self._extra_cfg())
@@ -185,7 +187,10 @@ class AbstractPathIntegralPolicy:
     def __call__(self, env):
         """(pol::AbstractGMPPI_Policy)(env) POL:221-238 / (pol::MPPI_Policy)(env) POL:121-146."""
         eng = self.engine()
-        control, U_rolled, self.last_its = eng.plan(env.state, env.t, self.U)
+        if env._env_kind() == _abi.ENV_EXTERNAL:  # pol(env::EnvpoolEnv): POL:148-184, 240-259
+            control, U_rolled, self.last_its = eng.plan_external(self.U, env.rollout)
+        else:
+            control, U_rolled, self.last_its = eng.plan(env.state, env.t, self.U)
         self.U[:] = U_rolled  # in place: pol.U aliases pol.params.U₀ (SURVEY App. B-2)
         if self.params.log:  # POL:140-143, 233-236
             out = eng.fetch(costs=True, weights=True, traj=True)

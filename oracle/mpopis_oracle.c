@@ -57,6 +57,10 @@ struct orc_handle {
   int64_t step;
   double *costs, *weights, *E, *traj, *Sigma_last, *U_last;
   double last_shrink;
+  /* EnvpoolEnv seam (MPOPIS_ENV_EXTERNAL): bounds of the action space and the running plan's callback */
+  double *ext_lo, *ext_hi;
+  mpopis_rollout_fn ext_fn;
+  void *ext_user;
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -402,6 +406,24 @@ static void simulate_model(orc_t *h, const double *state, int64_t env_t, const d
       row[j] = s;
     }
   }
+  if (h->cfg.env == MPOPIS_ENV_EXTERNAL) { /* simulate_model(pol, env::EnvpoolEnv, …) POL:240-259 */
+    const int64_t as = h->as, T = h->T;
+    double *ctl = malloc(sizeof(double) * cs * K), *tc = malloc(sizeof(double) * K);
+    for (int64_t k = 0; k < K; ++k) {
+      double control_cost = 0.0;
+      for (int64_t r = 0; r < cs; ++r) {
+        const double v = U[r] + E[r + cs * k]; /* Vₖ = repeat(pol.U', K) + E', POL:252 */
+        if (row) control_cost += row[r] * (v - U_orig[r]); /* POL:248 */
+        /* get_model_controls(action_space, Vₖ, T) UTL:42-53: K x as x T, clamped per action component */
+        ctl[k + K * r] = clampd(v, h->ext_lo[r % as], h->ext_hi[r % as]);
+      }
+      costs[k] = control_cost;
+    }
+    const int rc = h->ext_fn ? h->ext_fn(h->ext_user, ctl, K, as, T, tc) : -1; /* rollout_model UTL:103-121 */
+    for (int64_t k = 0; k < K; ++k) costs[k] = rc ? NAN : tc[k] + costs[k]; /* POL:256 */
+    free(ctl), free(tc), free(row);
+    return;
+  }
 #pragma omp parallel for schedule(static) num_threads(h->nthreads)
   for (int64_t k = 0; k < K; ++k) { /* Threads.@threads for k ∈ 1:K, POL:269 */
     double V[cs];
@@ -573,6 +595,12 @@ int orc_create(const mpopis_cfg_t *cfg, orc_t **out) {
     h->n_cars = cfg->n_cars, h->as = 2 * cfg->n_cars, h->ss = 8 * cfg->n_cars;
   } else if (cfg->env == MPOPIS_ENV_MOUNTAIN_CAR) {
     h->n_cars = 0, h->as = 1, h->ss = 2;
+  } else if (cfg->env == MPOPIS_ENV_EXTERNAL) {
+    if (cfg->ext_action_size < 1 || cfg->ext_action_size > 4096 || cfg->log_trajectories) {
+      free(h);
+      FAIL(MPOPIS_ERR_BAD_ARG, "external env: bad ext_action_size / log_trajectories");
+    }
+    h->n_cars = 0, h->as = cfg->ext_action_size, h->ss = 0;
   } else {
     free(h);
     FAIL(MPOPIS_ERR_BAD_ARG, "unknown env");
@@ -596,6 +624,7 @@ int orc_destroy(orc_t *h) {
   if (!h) return 0;
   free(h->tx), free(h->ty), free(h->tw), free(h->Sigma), free(h->ws);
   free(h->costs), free(h->weights), free(h->E), free(h->traj), free(h->Sigma_last), free(h->U_last);
+  free(h->ext_lo), free(h->ext_hi);
   free(h);
   return 0;
 }
@@ -698,6 +727,26 @@ static int plan_mppi(orc_t *h, const double *state, int64_t env_t, double *U, co
   /* E[k,t] = L * z  (rand(rng, P, K, T), POL:193); stored here as cs x K, r = t*as + a */
   for (int64_t k = 0; k < K; ++k)
     for (int64_t t = 0; t < T; ++t) apply_L(L, as, Z + t * as + cs * k, 1, h->E + t * as + cs * k);
+  if (h->cfg.env == MPOPIS_ENV_EXTERNAL) { /* calculate_trajectory_costs(pol::MPPI_Policy, env::EnvpoolEnv) POL:148-184 */
+    double *ctl = malloc(sizeof(double) * cs * K), *tc = malloc(sizeof(double) * K);
+    for (int64_t k = 0; k < K; ++k) {
+      double cc = 0.0;
+      for (int64_t t = 0; t < T; ++t) {
+        const double *Ei = h->E + t * as + cs * k, *ut = U + t * as;
+        for (int64_t j = 0; j < as; ++j) { /* γ * uₜ' * Σ_inv * Eᵢ, POL:164 */
+          double rj = 0.0;
+          for (int64_t i = 0; i < as; ++i) rj += (gamma * ut[i]) * A_(Sinv, i, j, as);
+          cc += rj * Ei[j];
+        }
+        for (int64_t r = 0; r < as; ++r) /* Vₜ + get_model_controls, POL:162,166 */
+          ctl[k + K * (r + as * t)] = clampd(ut[r] + Ei[r], h->ext_lo[r], h->ext_hi[r]);
+      }
+      h->costs[k] = cc;
+    }
+    const int frc = h->ext_fn ? h->ext_fn(h->ext_user, ctl, K, as, T, tc) : -1;
+    for (int64_t k = 0; k < K; ++k) h->costs[k] = frc ? NAN : tc[k] + h->costs[k]; /* POL:171 */
+    free(ctl), free(tc);
+  } else {
 #pragma omp parallel for schedule(static) num_threads(h->nthreads)
   for (int64_t k = 0; k < K; ++k) { /* POL:198-214 */
     double s[8 * MPOPIS_MAX_CARS], a[2 * MPOPIS_MAX_CARS], cost = 0.0;
@@ -726,6 +775,7 @@ static int plan_mppi(orc_t *h, const double *state, int64_t env_t, double *U, co
         for (int64_t q = 0; q < h->ss; ++q) h->traj[(size_t)k * T * h->ss + t + T * q] = s[q];
     }
     h->costs[k] = cost;
+  }
   }
   compute_weights(h->costs, K, h->cfg.lambda, h->weights); /* POL:127 */
   double *wc = calloc(cs, sizeof(double));
@@ -961,6 +1011,30 @@ int orc_plan(orc_t *h, const double *state, int64_t env_t, double *U_inout, doub
   int rc = orc_plan_with_noise(h, state, env_t, U_inout, Z, u, control_out, its_run_out);
   h->step += 1;
   free(Z), free(u);
+  return rc;
+}
+
+int orc_set_external_env(orc_t *h, const double *action_lo, const double *action_hi) {
+  if (!h || !action_lo || !action_hi) FAIL(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->cfg.env != MPOPIS_ENV_EXTERNAL) FAIL(MPOPIS_ERR_BAD_ARG, "handle was created for a different environment");
+  free(h->ext_lo), free(h->ext_hi);
+  h->ext_lo = malloc(sizeof(double) * h->as), h->ext_hi = malloc(sizeof(double) * h->as);
+  memcpy(h->ext_lo, action_lo, sizeof(double) * h->as);
+  memcpy(h->ext_hi, action_hi, sizeof(double) * h->as);
+  h->env_set = 1;
+  return 0;
+}
+
+/* pol(env::EnvpoolEnv): the same plans with the rollouts delegated to the caller's simulator */
+int orc_plan_external(orc_t *h, double *U_inout, mpopis_rollout_fn rollout, void *user, const double *Z,
+                      const double *resample_u, double *control_out, int32_t *its_run_out) {
+  if (!h || !U_inout || !rollout || !control_out) FAIL(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->cfg.env != MPOPIS_ENV_EXTERNAL) FAIL(MPOPIS_ERR_BAD_ARG, "handle was not created with MPOPIS_ENV_EXTERNAL");
+  const double dummy_state = 0.0;
+  h->ext_fn = rollout, h->ext_user = user;
+  const int rc = Z ? orc_plan_with_noise(h, &dummy_state, 0, U_inout, Z, resample_u, control_out, its_run_out)
+                   : orc_plan(h, &dummy_state, 0, U_inout, control_out, its_run_out);
+  h->ext_fn = NULL, h->ext_user = NULL;
   return rc;
 }
 

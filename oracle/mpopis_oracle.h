@@ -39,6 +39,9 @@ int orc_plan(orc_t *h, const double *state, int64_t env_t, double *U_inout, doub
 int orc_plan_with_noise(orc_t *h, const double *state, int64_t env_t, double *U_inout,
                         const double *Z, const double *resample_u, double *control_out,
                         int32_t *its_run_out);
+int orc_set_external_env(orc_t *h, const double *action_lo, const double *action_hi);
+int orc_plan_external(orc_t *h, double *U_inout, mpopis_rollout_fn rollout, void *user, const double *Z,
+                      const double *resample_u, double *control_out, int32_t *its_run_out);
 int orc_fetch(orc_t *h, double *costs, double *weights, double *E, double *traj);
 int orc_fetch_proposal(orc_t *h, double *Sigma_last, double *U_last);
 int orc_rollout_costs(orc_t *h, const double *state, int64_t env_t, const double *U,

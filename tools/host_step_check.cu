@@ -75,7 +75,7 @@ int main(int argc, char **argv) {
     memcpy(lit, s, sizeof s), memcpy(v3, s, sizeof s), memcpy(v4, s, sizeof s);
     car_step<1>(P, dt, ddt, nsub, lit, a0, a1);
     car_step<0>(P, dt, ddt, nsub, v3, a0, a1);
-    const bool ok = car_step_spec(P, dt, ddt, nsub, s, o, a0, a1);
+    const bool ok = car_step_spec(P, derive_car(P, ddt), dt, ddt, nsub, s, o, a0, a1);
     car_step<3>(P, dt, ddt, nsub, v4, a0, a1);
     if (!ok) ++repaired;
     if (!ok && s[3] > 2.0) ++repaired_fwd;
