@@ -30,9 +30,9 @@ MPOPIS_HD double rcp_seed(double d) {  // 2^-23 reciprocal seed (MUFU.RCP64H)
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
   return r;
 }
-MPOPIS_HD double mul_rn(double a, double b) { return mul_rn(a, b); }
-MPOPIS_HD double add_rn(double a, double b) { return add_rn(a, b); }
-MPOPIS_HD double sqrt_rn(double a) { return sqrt_rn(a); }
+MPOPIS_HD double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+MPOPIS_HD double add_rn(double a, double b) { return __dadd_rn(a, b); }
+MPOPIS_HD double sqrt_rn(double a) { return __dsqrt_rn(a); }
 MPOPIS_HD double rsqrt_f64(double a) { return rsqrt(a); }
 MPOPIS_HD uint4 ldg_u4(const uint4 *p) { return __ldg(p); }
 MPOPIS_HD double inf_f64() { return CUDART_INF; }
@@ -252,7 +252,7 @@ MPOPIS_HD double tire_fy_literal(double alpha, double C, double c2, double c3,
 MPOPIS_HD void car_step_fast(const CarParams &P, double dt, double ddt, int nsub, double *s,
                                               double a0, double a1);
 MPOPIS_HD bool car_step_spec(const CarParams &P, const CarDerived &D, double dt, double ddt, int nsub,
-                             const double *s, double *o, double a0, double a1);
+                             const double *s, double *o, double a0, double a1, double *trig, bool resync);
 
 template <int MODE>
 MPOPIS_HD void car_step(const CarParams &P, double dt, double ddt, int nsub, double *s,
@@ -264,7 +264,8 @@ MPOPIS_HD void car_step(const CarParams &P, double dt, double ddt, int nsub, dou
   if constexpr (MODE == 3) {
     double o[8];
     const CarDerived D = derive_car(P, ddt);  // env_step / host checker; the rollout kernel passes env.der[c]
-    if (car_step_spec(P, D, dt, ddt, nsub, s, o, a0, a1)) {
+    double trig[4];
+    if (car_step_spec(P, D, dt, ddt, nsub, s, o, a0, a1, trig, true)) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) s[q] = o[q];
     } else {
@@ -498,8 +499,11 @@ MPOPIS_HD double with_opposite_sign(double mag, int shi) {
 #endif
 }
 
+// `trig` = {sin δ, cos δ, sin Ψ, cos Ψ} carried from one control step to the next by the rollout kernel: with
+// resync == false the recurrences simply continue (their drift is one rounding per sub-step; the kernel
+// re-evaluates them from δ and Ψ every few control steps and after every repaired step).
 MPOPIS_HD bool car_step_spec(const CarParams &P, const CarDerived &D, double dt, double ddt, int nsub,
-                             const double *s, double *o, double a0, double a1) {
+                             const double *s, double *o, double a0, double a1, double *trig, bool resync) {
   double x = s[0], y = s[1], psi = s[2], Vx = s[3], Vy = s[4], psid = s[5], delta = s[6];
   const double tgt = a0 * P.d_max - delta;
   const double rate = fmin(fast_div(fabs(tgt), dt), P.dd_max) * jl_sign(tgt);  // CAR:295-296
@@ -515,16 +519,19 @@ MPOPIS_HD bool car_step_spec(const CarParams &P, const CarDerived &D, double dt,
   const int hvx0 = hi32(Vx), brake_mask = bk != 0.0 ? (int)0x80000000 : 0;
   int bad = 0;
   const bool pre_ok = (fmax(fabs(delta), fabs(a0 * P.d_max)) <= 0.78) & (Vx != 0.0) & (fabs(dlt) <= 0.03);
-  double sd, cd, sdl, cdl;
-  sincos_kernel(delta, &sd, &cd);
+  double sd, cd, sp, cp, sdl, cdl;
   sincos_tiny(dlt, &sdl, &cdl);  // |rate·δt| <= δ̇_max·δt = 0.0157 for the default car
-  if (fabs(psi) > CUDART_PI) {
-    const double k = rint(psi * 0.15915494309189535);
-    psi = fma(-k, 6.283185307179586, psi);
-    psi = fma(-k, 2.4492935982947064e-16, psi);
+  if (resync) {
+    sincos_kernel(delta, &sd, &cd);
+    if (fabs(psi) > CUDART_PI) {
+      const double k = rint(psi * 0.15915494309189535);
+      psi = fma(-k, 6.283185307179586, psi);
+      psi = fma(-k, 2.4492935982947064e-16, psi);
+    }
+    sincos_pi(psi, &sp, &cp);
+  } else {
+    sd = trig[0], cd = trig[1], sp = trig[2], cp = trig[3];
   }
-  double sp, cp;
-  sincos_pi(psi, &sp, &cp);
   double dpsi = psid * ddt;  // Ψ̇·δt of the CURRENT Ψ̇: the −Ψ̇Vx / +Ψ̇Vy terms of this sub-step, the heading step of the last
 #pragma unroll 2
   for (int i = 0; i < nsub; ++i) {
@@ -571,6 +578,7 @@ MPOPIS_HD bool car_step_spec(const CarParams &P, const CarDerived &D, double dt,
     psi = fma(-k, 2.4492935982947064e-16, psi);
   }
   o[0] = x, o[1] = y, o[2] = psi, o[3] = Vx, o[4] = Vy, o[5] = psid, o[6] = delta, o[7] = pedal;
+  trig[0] = sd, trig[1] = cd, trig[2] = sp, trig[3] = cp;
   return pre_ok & (bad >= 0);
 }
 

@@ -39,14 +39,15 @@ namespace mpopis {
 // (env)(a) + reward(env) for 1..N cars: CAR:238-241 / MCR:200-207, MCR:145-158
 template <int NCARS, int MODE>
 __device__ __forceinline__ double cars_step_reward(const CarEnvArgs &env, const TrackView &tr, double *s,
-                                                   const double *a) {
+                                                   const double *a, double *trig, bool resync, bool *trig_valid) {
   if constexpr (MODE == 3) {  // every car's straight-line step first (independent chains), then the rare repairs
     double o[8 * NCARS];
     bool ok[NCARS];
 #pragma unroll
     for (int c = 0; c < NCARS; ++c)
       ok[c] = car_step_spec(env.car[c], env.der[c], env.dt, env.ddt, env.nsub, s + 8 * c, o + 8 * c, a[2 * c],
-                            a[2 * c + 1]);
+                            a[2 * c + 1], trig + 4 * c, resync);
+    bool all_ok = true;
 #pragma unroll
     for (int c = 0; c < NCARS; ++c) {
       if (ok[c]) {
@@ -54,8 +55,10 @@ __device__ __forceinline__ double cars_step_reward(const CarEnvArgs &env, const 
         for (int q = 0; q < 8; ++q) s[8 * c + q] = o[8 * c + q];
       } else {
         car_step_fast(env.car[c], env.dt, env.ddt, env.nsub, s + 8 * c, a[2 * c], a[2 * c + 1]);
+        all_ok = false;
       }
     }
+    *trig_valid = all_ok;  // a repaired step leaves no carried sin/cos: re-evaluate at the next step
   } else {
 #pragma unroll
     for (int c = 0; c < NCARS; ++c)
@@ -100,6 +103,8 @@ __global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(co
   for (int q = 0; q < SS; ++q) s[q] = __ldg(a.state0 + q);
   const double *Ek = a.E + k;
   double cost = 0.0, cc = 0.0;
+  double trig[4 * NCARS];
+  bool trig_valid = false;
   // the noise of step t+1 is fetched while step t integrates (ncu: long-scoreboard stalls on these loads)
   double e_next[AS];
 #pragma unroll
@@ -119,7 +124,9 @@ __global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(co
       if (a.bvec) cc += __ldg(a.bvec + row) * (v - __ldg(a.U_orig + row));  // POL:272
       act[r] = clamp1(v);                                                   // UTL:55-67
     }
-    cost -= cars_step_reward<NCARS, MODE>(env, tr, s, act);  // UTL:137-138
+    // MODE 3 carries sin/cos of δ and Ψ across control steps; re-evaluated every 5th step and after a repair
+    const bool resync = !trig_valid || (t % 5) == 0;
+    cost -= cars_step_reward<NCARS, MODE>(env, tr, s, act, trig, resync, &trig_valid);  // UTL:137-138
     if (a.traj) {
 #pragma unroll
       for (int q = 0; q < SS; ++q) a.traj[((size_t)k * SS + q) * a.T + t] = s[q];  // UTL:139-141

@@ -84,7 +84,7 @@ def test_oracle_external_callback_error_is_reported(orc):
 @pytest.mark.parametrize("envname", ["mc", "car"])
 def test_gpu_external_equals_oracle_builtin(gpu_bound, orc, policy, envname):
     if envname == "mc":
-        K, T, N, as_, cov = 64, 15, 4, 1, [1.5]
+        K, T, N, as_, cov = 160, 15, 4, 1, [1.5]  # m_elite = 32 > cs = 15: Σ′ stays well conditioned
         kw = dict(lam=0.1, alpha=0.7, lam_ais=0.1, sigma_est="mle")
     else:
         K, T, N, as_, cov = 192, 12, 4, 2, block_diagm([0.0625, 0.1], 1)
