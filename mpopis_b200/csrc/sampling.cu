@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) apply_L_dmma_kernel(const double *__restr
   }
 }
 
-// Second DMMA formulation (MPOPIS_APPLY_L=2): the kernel above re-reads Z once per 32-row block (2.9x for
+// Second DMMA formulation (the default; MPOPIS_APPLY_L=1 / "apply_l" = 1 selects the kernel above): the kernel above re-reads Z once per 32-row block (2.9x for
 // cs = 100), stages L and Z single-buffered between two barriers and leaves the triangle's load imbalance to
 // the block scheduler. Here ONE CTA owns a 64-sample column tile and ALL rows of a 104-row block (13 row
 // fragments of 8), so Z streams through shared memory exactly once per block, double-buffered with cp.async
@@ -353,7 +353,7 @@ static int g_apply_L_path = -1;
 static int apply_L_path() {
   if (g_apply_L_path < 0) {
     const char *e = getenv("MPOPIS_APPLY_L");
-    g_apply_L_path = (e && e[0] == 'f') ? 0 : (e && e[0] == '2') ? 2 : 1;
+    g_apply_L_path = (e && e[0] == 'f') ? 0 : (e && e[0] == '1') ? 1 : 2;  // default: DMMA column tiles
   }
   return g_apply_L_path;
 }
