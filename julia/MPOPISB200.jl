@@ -30,7 +30,8 @@ struct Cfg                       # mpopis_cfg_t (field order and types must matc
     lambda::Float64; alpha::Float64; lambda_ais::Float64; ce_elite_threshold::Float64
     sigma_est::Int32; early_stop::Int32; log_trajectories::Int32
     device::Int32; rank::Int32; world_size::Int32
-    reserved::NTuple{4,Int32}
+    ext_action_size::Int32           # MPOPIS_ENV_EXTERNAL only
+    reserved::NTuple{3,Int32}
 end
 struct Cma                       # mpopis_cma_t
     sigma::Float64; m_elite::Int64; mu_eff::Float64; c_sigma::Float64; d_sigma::Float64
@@ -88,7 +89,8 @@ function handle(pol::AbstractPathIntegralPolicy, env; device=0)
                   hasproperty(pol, :opt_its) ? pol.opt_its : 1, P.λ, P.α,
                   hasproperty(pol, :λ_ais) ? pol.λ_ais : 20.0,
                   hasproperty(pol, :ce_elite_threshold) ? pol.ce_elite_threshold : 0.8,
-                  sigma_est_code(pol), 1, P.log ? 1 : 0, device, 0, 1, (Int32(0), Int32(0), Int32(0), Int32(0)))
+                  sigma_est_code(pol), 1, P.log ? 1 : 0, device, 0, 1,
+                  ecode == 2 ? Int32(P.as) : Int32(0), (Int32(0), Int32(0), Int32(0)))
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:mpopis_b200_create, LIB[]), Cint, (Ref{Cfg}, Ref{Ptr{Cvoid}}), cfg, out))
         h = out[]
@@ -145,6 +147,47 @@ function simulate_model_b200(pol::AbstractGMPPI_Policy, env, E::Matrix{Float64},
         (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
         h, s, env_t(env), pol.U, U_orig, E, Σ_inv, costs))
     return costs
+end
+
+# ---- the EnvpoolEnv seam (MPOPIS_ENV_EXTERNAL): MPOPIS keeps the simulator, the engine does the rest -----------------
+# Replaces calculate_trajectory_costs(pol::MPPI_Policy, env::EnvpoolEnv) (mppi_mpopi_policies.jl:148-184) and
+# simulate_model(pol::AbstractGMPPI_Policy, env::EnvpoolEnv, ...) (:240-259): the callback receives the K x as x T
+# array get_model_controls builds (utils.jl:42-53) and answers with rollout_model's trajectory costs (utils.jl:103-121).
+env_code(::MPOPIS.EnvpoolEnv) = (Int32(2), Int32(1))
+const CURRENT = Ref{Any}(nothing)                      # (pol, env) of the running plan_external
+function rollout_cb(::Ptr{Cvoid}, controls::Ptr{Float64}, K::Int64, as::Int64, T::Int64, out::Ptr{Float64})::Cint
+    try
+        pol, env = CURRENT[]
+        cost = MPOPIS.rollout_model(env, Int(T), unsafe_wrap(Array, controls, (Int(K), Int(as), Int(T))), pol)
+        unsafe_copyto!(out, pointer(cost), K)
+        return Cint(0)
+    catch
+        return Cint(1)                                 # never unwind through the C frames
+    end
+end
+function set_env!(h, env::MPOPIS.EnvpoolEnv)
+    lo = Vector{Float64}(leftendpoint(action_space(env))); hi = Vector{Float64}(rightendpoint(action_space(env)))
+    check(ccall((:mpopis_b200_set_external_env, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h, lo, hi))
+end
+function plan_external!(pol, env::MPOPIS.EnvpoolEnv)
+    h = handle(pol, env)
+    cb = @cfunction(rollout_cb, Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}))
+    control = Vector{Float64}(undef, pol.params.as); its = Ref{Int32}(0)
+    CURRENT[] = (pol, env)
+    try
+        check(ccall((:mpopis_b200_plan_external, LIB[]), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+            h, pol.U, cb, C_NULL, C_NULL, C_NULL, control, its))
+    finally
+        CURRENT[] = nothing
+    end
+    return pol.params.as == 1 ? control : reshape(control, :, 1)
+end
+"Route `pol(env::EnvpoolEnv)` through the engine (sampling / adaptation / weights on the GPU, rollouts in EnvPool)."
+function enable_external!()
+    @eval (pol::AbstractGMPPI_Policy)(env::MPOPIS.EnvpoolEnv) = plan_external!(pol, env)
+    @eval (pol::MPPI_Policy)(env::MPOPIS.EnvpoolEnv) = plan_external!(pol, env)
+    nothing
 end
 
 # ---- dispatch: enable!() defines the more specific methods -----------------------------------------------------
