@@ -140,6 +140,13 @@ void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const 
 void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int corrected, int method,
                          const double *qpart, int nq, double ridge, double *Sigma, double *lambda_out,
                          const int *stop, cudaStream_t s);
+// single-CTA fusion of the whole moment chain for n <= MOMENTS_SMALL_MAX columns (single GPU)
+constexpr int MOMENTS_SMALL_MAX = 512;
+void launch_moments_small(const double *X, long long ld, int p, int n, const double *w, const int *cols, int want_cov,
+                          int corrected,
+                          int method, double ridge, double *mu_out, double *U, const double *scale_dev,
+                          double *sums_out, double *Sraw, double *Sigma, double *lambda_out, const int *stop,
+                          cudaStream_t s);
 void launch_gather_cols(const double *E, long long ldk, int cs, const int *order, int m, long long k0, int Kloc,
                         double *X, long long ldx, double *mask, const int *stop, cudaStream_t s,
                         const int *m_dev = nullptr);

@@ -100,6 +100,7 @@ struct mpopis_handle {
   uint64_t seed = 0;
   long long step = 0;
   int rollout_variant = 3, rollout_block = 64, coop_max = 1, sort_max = 1;
+  bool moments_small = true;  // single-CTA moment chain for small n ("moments_small" option, A/B)
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
   bool L0_valid = false;
   mpopis_cma_t cma{};
@@ -283,9 +284,17 @@ int allgather_costs(mpopis_t *h) {
 // w: per-local-column weights or nullptr. Adds the mean to U_cur when update_U (scaled by *scale_dev).
 int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, bool want_cov, int corrected,
             int method, double ridge, bool update_U, const double *scale_dev, double *Sigma_out,
-            const int *n_dev = nullptr, bool sharded_stop = false) {
+            const int *n_dev = nullptr, bool sharded_stop = false, const int *cols = nullptr) {
   const int cs = h->cs;
   const int *stop = h->stop();
+  if (h->world == 1 && n <= MOMENTS_SMALL_MAX && !n_dev && !sharded_stop && h->moments_small) {
+    // the reference's own problem sizes: one launch instead of eight
+    launch_moments_small(X, ld, cs, n, w, cols, want_cov, corrected, method, ridge, h->d_mu, update_U ? h->d_U_cur : nullptr,
+                         scale_dev, h->d_sums, h->d_Sraw, Sigma_out, h->d_lambda, stop, h->st);
+    h->launches += 1;
+    mark(h, "moments.small");
+    return 0;
+  }
   const int nch = rowsum_nchunks(n);
   const bool shrink = want_cov && (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS);
   // Sharded shrinkage: the first all-reduce also carries Σx² so that the standardisation of the shrinkage
@@ -564,9 +573,18 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
                                                              h->sort_max, st);
           if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
         }
+        h->launches += sort_launches(K);
+        if (pol == MPOPIS_POLICY_CEMPPI && h->world == 1 && m <= MOMENTS_SMALL_MAX && h->moments_small) {
+          // small elite set: the single-CTA moment kernel reads the elite columns through `order` (no gather)
+          mark(h, "select");
+          if (int rc = moments(h, h->d_E, h->ldk, m, nullptr, true, 0, h->cfg.sigma_est, 10e-9, true, nullptr, h->d_Sigma,
+                               nullptr, false, h->d_order))
+            return rc;
+          break;
+        }
         launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, m, h->k0, Kloc, h->d_X, h->ldm,
                            h->world > 1 ? h->d_mask : nullptr, stop, st);
-        h->launches += 1 + sort_launches(K);
+        h->launches += 1;
         mark(h, "select");
         if (pol == MPOPIS_POLICY_CEMPPI) {
           if (int rc = moments(h, h->d_X, h->ldm, m, h->world > 1 ? h->d_mask : nullptr, true, 0,
@@ -1066,6 +1084,8 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     const int b = (int)value;
     if (b < 32 || b > 128 || b % 32) return fail(MPOPIS_ERR_BAD_ARG, "rollout_block must be 32, 64, 96 or 128");
     h->rollout_block = b;
+  } else if (!strcmp(key, "moments_small")) {
+    h->moments_small = value != 0.0;
   } else if (!strcmp(key, "apply_l")) {
     if (value != 0.0 && value != 1.0 && value != 2.0) return fail(MPOPIS_ERR_BAD_ARG, "apply_l must be 0, 1 or 2");
     set_apply_L_path((int)value);  // process-wide

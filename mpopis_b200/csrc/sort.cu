@@ -178,7 +178,51 @@ __global__ void __launch_bounds__(256) merge_all_kernel(unsigned long long *kin,
 
 }  // namespace
 
-int sort_launches(int K) { return 2; }
+// K <= TILE (the reference's own sizes, K = 150 / 375 / 20): ONE ordinary launch — a bitonic network over the next
+// power of two >= K instead of the full 2048-entry tile, with the elite early-stop test at its end — replaces the
+// tile sort + the cooperative merge kernel (whose only job would be that test).
+__global__ void __launch_bounds__(1024) small_sort_kernel(const double *__restrict__ costs, int n, int tn,
+                                                           unsigned long long *__restrict__ keys,
+                                                           int *__restrict__ vals, int m, int early_stop,
+                                                           int *stop_flag, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ unsigned long long sk[TILE];
+  __shared__ int sv[TILE];
+  __shared__ double red[32];
+  for (int e = threadIdx.x; e < tn; e += 1024) {
+    sk[e] = e < n ? key_of(costs[e]) : KEY_PAD;
+    sv[e] = e < n ? e : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k = 2; k <= tn; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int t = threadIdx.x;
+      if (t < (tn >> 1)) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair, bit j clear
+        const int p = i | j;
+        const bool up = (i & k) == 0;
+        const unsigned long long ka = sk[i], kb = sk[p];
+        const int va = sv[i], vb = sv[p];
+        if (lt(kb, vb, ka, va) == up) sk[i] = kb, sv[i] = vb, sk[p] = ka, sv[p] = va;
+      }
+      __syncthreads();
+    }
+  for (int e = threadIdx.x; e < n; e += 1024) keys[e] = sk[e], vals[e] = sv[e];
+  if (stop_flag && m > 1) {  // maximum(abs.(diff(elite_traj_cost))) < 10e-3, POL:458-461, 566-569
+    double mx = -1.0;
+    for (int j = threadIdx.x; j + 1 < m; j += 1024) mx = fmax(mx, fabs(cost_of(sk[j + 1]) - cost_of(sk[j])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 32; ++w) mx = fmax(mx, red[w]);
+      if (early_stop && mx < 10e-3) *stop_flag = 1;
+    }
+  }
+}
+
+int sort_launches(int K) { return K <= TILE ? 1 : 2; }
 
 // Sorts costs[0:K]; on return `order` holds the stable ascending permutation (0-based sample ids).
 // keys_a/keys_b, vals_b: scratch of K entries. With stop_flag != nullptr the kernel also evaluates the elite
@@ -187,6 +231,12 @@ int sort_launches(int K) { return 2; }
 int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsigned long long *keys_b, int *order,
                     int *vals_b, int m, int early_stop, int *stop_flag, const int *stop, int max_ctas,
                     cudaStream_t s) {
+  if (K <= TILE) {
+    int tn = 32;
+    while (tn < K) tn <<= 1;
+    small_sort_kernel<<<1, 1024, 0, s>>>(costs, K, tn, keys_a, order, m, early_stop, stop_flag, stop);
+    return (int)cudaGetLastError();
+  }
   const int ntiles = (K + TILE - 1) / TILE;
   int passes = 0;
   for (long long L = TILE; L < K; L <<= 1) ++passes;

@@ -574,6 +574,136 @@ void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int c
                                                           Sigma, lambda_out, stop);
 }
 
+// ---- G5, small-n path: the whole moment chain in ONE CTA -----------------------------------------------------
+// For n <= 512 columns (the reference's own sizes: K = 150 -> 30 elites, K = 20 for MountainCar) the chain above is
+// eight launches of a few µs of latency each — more than the work. This kernel does count, (weighted) mean, U += μ,
+// centred scatter matrix, the shrinkage statistic and the final Σ′ = shrink(S) + ridge·I with the same formulas
+// (rowsum_partial → finalize_mean → syrk_partial → shrink_q_partial → cov_finalize), single GPU only. `cols` (nullable)
+// selects the columns — the elite set order[0:m] of :cemppi, which saves the gather kernel as well. Sraw is a
+// p x p global scratch (L1/L2-resident), re-read by the same CTA after a barrier.
+__global__ void __launch_bounds__(1024) moments_small_kernel(const double *__restrict__ X, long long ld, int p, int n,
+                                                              const double *__restrict__ w, const int *__restrict__ cols,
+                                                              int want_cov,
+                                                              int corrected, int method, double ridge,
+                                                              double *__restrict__ mu_out, double *__restrict__ U,
+                                                              const double *scale_dev, double *__restrict__ sums_out,
+                                                              double *__restrict__ Sraw, double *__restrict__ Sigma,
+                                                              double *lambda_out, const int *stop) {
+  if (stop && *stop) return;
+  extern __shared__ double msm[];  // mu[p] | dinv[p] | red[33]
+  double *mu = msm, *dinv = msm + p, *red = msm + 2 * p;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double c = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) c += w ? w[k] : 1.0;
+  const double cnt = block_reduce<0>(c, red);
+  for (int r = wid; r < p; r += nw) {  // one warp per row: coalesced in k
+    double a = 0.0;
+    for (int k = lane; k < n; k += 32) a = fma(w ? w[k] : 1.0, X[(size_t)r * ld + (cols ? cols[k] : k)], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      const double m = a / cnt;
+      mu[r] = m;
+      if (mu_out) mu_out[r] = m;
+      if (sums_out) sums_out[r] = a;
+      if (U) U[r] = U[r] + (scale_dev ? *scale_dev : 1.0) * m;  // pol.U = pol.U + vec(μ′), POL:365,465,...
+    }
+  }
+  if (threadIdx.x == 0 && sums_out) sums_out[p] = cnt;
+  __syncthreads();
+  if (!want_cov) return;
+  for (int i = wid; i < p; i += nw) {  // lower triangle, one warp per row i, lanes over j <= i
+    const double *xi = X + (size_t)i * ld;
+    const double mi = mu[i];
+    for (int j = lane; j <= i; j += 32) {
+      const double *xj = X + (size_t)j * ld;
+      const double mj = mu[j];
+      double a = 0.0;
+      for (int k = 0; k < n; ++k) {
+        const int ck = cols ? cols[k] : k;
+        const double t = (xi[ck] - mi) * (xj[ck] - mj);
+        a = w ? fma(w[k], t, a) : a + t;
+      }
+      Sraw[(size_t)i * p + j] = a;
+      Sraw[(size_t)j * p + i] = a;
+    }
+  }
+  __syncthreads();
+  const double denom = cnt - (corrected ? 1.0 : 0.0), inv = 1.0 / denom;
+  double lam = 0.0;
+  if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
+    const bool ss = method == MPOPIS_SIGMA_SS;
+    // Σ_{i≠j} Σ_k (z_ki z_kj)² = Σ_k [(Σ_i z_ki²)² − Σ_i z_ki⁴]  (shrink_q_partial_kernel)
+    for (int i = threadIdx.x; i < p; i += blockDim.x) dinv[i] = ss ? 1.0 / sqrt(Sraw[(size_t)i * p + i] / cnt) : 1.0;
+    __syncthreads();
+    double q = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      if (w && w[k] == 0.0) continue;
+      const int ck = cols ? cols[k] : k;
+      double a = 0.0, b = 0.0;
+      for (int i = 0; i < p; ++i) {
+        const double z = (X[(size_t)i * ld + ck] - mu[i]) * dinv[i];
+        const double z2 = z * z;
+        a += z2;
+        b = fma(z2, z2, b);
+      }
+      q += a * a - b;
+    }
+    q = block_reduce<0>(q, red);
+    // cov_finalize_kernel, :lw / :ss
+    for (int i = threadIdx.x; i < p; i += blockDim.x) dinv[i] = ss ? 1.0 / sqrt(Sraw[(size_t)i * p + i] * inv) : 1.0;
+    __syncthreads();
+    double r2 = 0.0;
+    for (int i = wid; i < p; i += nw) {
+      const double di = dinv[i] * inv;
+      for (int j = lane; j < p; j += 32) {
+        if (i == j) continue;
+        const double v = Sraw[(size_t)i * p + j] * di * dinv[j];
+        r2 = fma(v, v, r2);
+      }
+    }
+    r2 = block_reduce<0>(r2, red);
+    const double nn = cnt;
+    const double num = (q - nn * r2) * nn / ((nn - 1.0) * nn * nn);
+    lam = fmin(fmax(num / r2, 0.0), 1.0);
+  } else if (method == MPOPIS_SIGMA_RBLW || method == MPOPIS_SIGMA_OAS) {
+    double tr = 0.0, tr2 = 0.0;
+    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+      const double v = Sraw[e] * inv;
+      tr2 = fma(v, v, tr2);
+      if (e / p == e % p) tr += v;
+    }
+    tr = block_reduce<0>(tr, red);
+    tr2 = block_reduce<0>(tr2, red);
+    const double nn = cnt, pd = (double)p, trsq = tr * tr;
+    if (method == MPOPIS_SIGMA_RBLW) lam = ((nn - 2) / nn * tr2 + trsq) / ((nn + 2) * (tr2 - trsq / pd));
+    else lam = ((1.0 - 2.0 / pd) * tr2 + trsq) / ((nn + 1.0 - 2.0 / pd) * (tr2 - trsq / pd));
+    lam = fmin(fmax(lam, 0.0), 1.0);
+    const double F = tr / pd;
+    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+      const bool dg = e / p == e % p;
+      Sigma[e] = (1.0 - lam) * (Sraw[e] * inv) + (dg ? lam * F : 0.0) + (dg ? ridge : 0.0);
+    }
+    if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
+    return;
+  }
+  for (int i = wid; i < p; i += nw)
+    for (int j = lane; j < p; j += 32) {
+      const double v = Sraw[(size_t)i * p + j] * inv;
+      Sigma[(size_t)i * p + j] = i == j ? v + ridge : (1.0 - lam) * v;
+    }
+  if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
+}
+
+void launch_moments_small(const double *X, long long ld, int p, int n, const double *w, const int *cols, int want_cov,
+                          int corrected,
+                          int method, double ridge, double *mu_out, double *U, const double *scale_dev,
+                          double *sums_out, double *Sraw, double *Sigma, double *lambda_out, const int *stop,
+                          cudaStream_t s) {
+  moments_small_kernel<<<1, 1024, sizeof(double) * (2 * p + 40), s>>>(X, ld, p, n, w, cols, want_cov, corrected, method, ridge,
+                                                                     mu_out, U, scale_dev, sums_out, Sraw, Sigma,
+                                                                     lambda_out, stop);
+}
+
 // ---- G4: elite gather + early-stop test ---------------------------------------------------------
 // X[r][j] = E[r][order[j] − k0] for the elites that live in this shard (k0 <= order[j] < k0 + Kloc);
 // elites owned by other shards contribute zeros (they are summed in by the all-reduce).

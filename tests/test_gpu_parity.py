@@ -429,3 +429,28 @@ def test_closed_loop_lap_engine_vs_oracle(gpu_bound, orc):
         assert rew > -4000  # stays on the track
     print(f"closed loop, 25 steps: worst |Δ| = {worst:.2e}")
     assert worst < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("policy,sigma_est", [("cemppi", "ss"), ("cemppi", "lw"), ("cemppi", "oas"), ("cemppi", "mle"),
+                                              ("μΣaismppi", "mle"), ("pmcmppi", "mle"), ("imppi", "mle")])
+def test_single_cta_moment_chain_equals_the_kernel_chain(gpu_bound, policy, sigma_est):
+    """n <= 512 columns take ONE kernel for count / mean / scatter / shrinkage / Σ′ (stats.cu: moments_small_kernel);
+    the multi-kernel chain stays selectable ("moments_small" = 0): same proposal, same control."""
+    env = make_env("car")
+    K, T, N = 256, 20, 4
+    rng = np.random.Generator(np.random.Philox(key=5))
+    Z, u = rng.standard_normal((2 * T, K, N)), rng.uniform(size=(K, N - 1))
+    out = []
+    for flag in (1, 0):
+        g = configure(Engine(gpu_bound, **engine_kwargs(policy, env, K, T, N, sigma_est=sigma_est)), env, policy)
+        g.set_option("moments_small", flag)
+        ctrl, U2, its = g.plan(synthetic_states()[1], 0, np.zeros(g.cs), Z=Z, resample_u=u)
+        S, Ul = g.fetch_proposal()
+        out.append((ctrl, U2, its, S, Ul, g.last_shrinkage(), g.launch_count()))
+    a, b = out
+    assert a[2] == b[2] and a[6] < b[6]  # same iterations, fewer launches
+    np.testing.assert_allclose(a[3], b[3], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(a[4], b[4], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(a[5], b[5], rtol=1e-9, atol=1e-12)
