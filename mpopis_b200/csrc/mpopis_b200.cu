@@ -287,7 +287,7 @@ int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, 
             const int *n_dev = nullptr, bool sharded_stop = false, const int *cols = nullptr) {
   const int cs = h->cs;
   const int *stop = h->stop();
-  if (h->world == 1 && n <= MOMENTS_SMALL_MAX && !n_dev && !sharded_stop && h->moments_small) {
+  if (h->world == 1 && n <= MOMENTS_SMALL_MAX && cs <= 512 && !n_dev && !sharded_stop && h->moments_small) {
     // the reference's own problem sizes: one launch instead of eight
     launch_moments_small(X, ld, cs, n, w, cols, want_cov, corrected, method, ridge, h->d_mu, update_U ? h->d_U_cur : nullptr,
                          scale_dev, h->d_sums, h->d_Sraw, Sigma_out, h->d_lambda, stop, h->st);
@@ -574,7 +574,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
           if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
         }
         h->launches += sort_launches(K);
-        if (pol == MPOPIS_POLICY_CEMPPI && h->world == 1 && m <= MOMENTS_SMALL_MAX && h->moments_small) {
+        if (pol == MPOPIS_POLICY_CEMPPI && h->world == 1 && m <= MOMENTS_SMALL_MAX && cs <= 512 && h->moments_small) {
           // small elite set: the single-CTA moment kernel reads the elite columns through `order` (no gather)
           mark(h, "select");
           if (int rc = moments(h, h->d_E, h->ldk, m, nullptr, true, 0, h->cfg.sigma_est, 10e-9, true, nullptr, h->d_Sigma,

@@ -579,24 +579,27 @@ void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int c
 // eight launches of a few µs of latency each — more than the work. This kernel does count, (weighted) mean, U += μ,
 // centred scatter matrix, the shrinkage statistic and the final Σ′ = shrink(S) + ridge·I with the same formulas
 // (rowsum_partial → finalize_mean → syrk_partial → shrink_q_partial → cov_finalize), single GPU only. `cols` (nullable)
-// selects the columns — the elite set order[0:m] of :cemppi, which saves the gather kernel as well. Sraw is a
-// p x p global scratch (L1/L2-resident), re-read by the same CTA after a barrier.
+// selects the columns — the elite set order[0:m] of :cemppi, which saves the gather kernel as well. The centred
+// columns are staged in shared memory in chunks of kc (Xs[p][pitch], odd pitch: conflict-free for lanes over rows);
+// a first cut that read the (gathered) columns straight from global memory inside the p²/2 dot products was a serial
+// chain of dependent L2 loads: 119 µs for p = 100, n = 30 (profiles/README.md). Sraw is a p x p global scratch
+// (L1/L2-resident) accumulated chunk by chunk and re-read by the same CTA after a barrier.
 __global__ void __launch_bounds__(1024) moments_small_kernel(const double *__restrict__ X, long long ld, int p, int n,
                                                               const double *__restrict__ w, const int *__restrict__ cols,
-                                                              int want_cov,
-                                                              int corrected, int method, double ridge,
-                                                              double *__restrict__ mu_out, double *__restrict__ U,
-                                                              const double *scale_dev, double *__restrict__ sums_out,
-                                                              double *__restrict__ Sraw, double *__restrict__ Sigma,
-                                                              double *lambda_out, const int *stop) {
+                                                              int want_cov, int corrected, int method, double ridge,
+                                                              int kc, int pitch, double *__restrict__ mu_out,
+                                                              double *__restrict__ U, const double *scale_dev,
+                                                              double *__restrict__ sums_out, double *__restrict__ Sraw,
+                                                              double *__restrict__ Sigma, double *lambda_out,
+                                                              const int *stop) {
   if (stop && *stop) return;
-  extern __shared__ double msm[];  // mu[p] | dinv[p] | red[33]
-  double *mu = msm, *dinv = msm + p, *red = msm + 2 * p;
+  extern __shared__ double msm[];  // mu[p] | dinv[p] | red[40] | sw[kc] | Xs[p][pitch]
+  double *mu = msm, *dinv = msm + p, *red = msm + 2 * p, *sw = msm + 2 * p + 40, *Xs = sw + kc;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   double c = 0.0;
   for (int k = threadIdx.x; k < n; k += blockDim.x) c += w ? w[k] : 1.0;
   const double cnt = block_reduce<0>(c, red);
-  for (int r = wid; r < p; r += nw) {  // one warp per row: coalesced in k
+  for (int r = wid; r < p; r += nw) {  // one warp per row, lanes over the columns
     double a = 0.0;
     for (int k = lane; k < n; k += 32) a = fma(w ? w[k] : 1.0, X[(size_t)r * ld + (cols ? cols[k] : k)], a);
     a = warp_sum(a);
@@ -611,20 +614,29 @@ __global__ void __launch_bounds__(1024) moments_small_kernel(const double *__res
   if (threadIdx.x == 0 && sums_out) sums_out[p] = cnt;
   __syncthreads();
   if (!want_cov) return;
-  for (int i = wid; i < p; i += nw) {  // lower triangle, one warp per row i, lanes over j <= i
-    const double *xi = X + (size_t)i * ld;
-    const double mi = mu[i];
-    for (int j = lane; j <= i; j += 32) {
-      const double *xj = X + (size_t)j * ld;
-      const double mj = mu[j];
-      double a = 0.0;
-      for (int k = 0; k < n; ++k) {
-        const int ck = cols ? cols[k] : k;
-        const double t = (xi[ck] - mi) * (xj[ck] - mj);
-        a = w ? fma(w[k], t, a) : a + t;
+  auto stage = [&](int c0, int nc) {  // Xs[i][k] = X[i][col(c0 + k)] − μ_i, sw[k] = w_k (all loads independent)
+    for (int e = threadIdx.x; e < p * nc; e += blockDim.x) {
+      const int i = e / nc, k = e - i * nc;
+      const int ck = cols ? cols[c0 + k] : c0 + k;
+      Xs[i * pitch + k] = X[(size_t)i * ld + ck] - mu[i];
+    }
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) sw[k] = w ? w[c0 + k] : 1.0;
+  };
+  for (int c0 = 0; c0 < n; c0 += kc) {  // centred scatter matrix, lower triangle: one warp per row i, lanes over j <= i
+    const int nc = min(kc, n - c0);
+    __syncthreads();
+    stage(c0, nc);
+    __syncthreads();
+    for (int i = wid; i < p; i += nw) {
+      const double *xi = Xs + i * pitch;
+      for (int j = lane; j <= i; j += 32) {
+        const double *xj = Xs + j * pitch;
+        double a = 0.0;
+        for (int k = 0; k < nc; ++k) a = fma(sw[k] * xi[k], xj[k], a);
+        const double v = (c0 ? Sraw[(size_t)i * p + j] : 0.0) + a;
+        Sraw[(size_t)i * p + j] = v;
+        Sraw[(size_t)j * p + i] = v;
       }
-      Sraw[(size_t)i * p + j] = a;
-      Sraw[(size_t)j * p + i] = a;
     }
   }
   __syncthreads();
@@ -632,21 +644,29 @@ __global__ void __launch_bounds__(1024) moments_small_kernel(const double *__res
   double lam = 0.0;
   if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
     const bool ss = method == MPOPIS_SIGMA_SS;
-    // Σ_{i≠j} Σ_k (z_ki z_kj)² = Σ_k [(Σ_i z_ki²)² − Σ_i z_ki⁴]  (shrink_q_partial_kernel)
+    // Σ_{i≠j} Σ_k (z_ki z_kj)² = Σ_k [(Σ_i z_ki²)² − Σ_i z_ki⁴]  (shrink_q_partial_kernel); one warp per column
     for (int i = threadIdx.x; i < p; i += blockDim.x) dinv[i] = ss ? 1.0 / sqrt(Sraw[(size_t)i * p + i] / cnt) : 1.0;
     __syncthreads();
     double q = 0.0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-      if (w && w[k] == 0.0) continue;
-      const int ck = cols ? cols[k] : k;
-      double a = 0.0, b = 0.0;
-      for (int i = 0; i < p; ++i) {
-        const double z = (X[(size_t)i * ld + ck] - mu[i]) * dinv[i];
-        const double z2 = z * z;
-        a += z2;
-        b = fma(z2, z2, b);
+    for (int c0 = 0; c0 < n; c0 += kc) {
+      const int nc = min(kc, n - c0);
+      if (n > kc) {  // a single chunk is still resident
+        __syncthreads();
+        stage(c0, nc);
+        __syncthreads();
       }
-      q += a * a - b;
+      for (int k = wid; k < nc; k += nw) {
+        if (sw[k] == 0.0) continue;  // warp-uniform
+        double a = 0.0, b = 0.0;
+        for (int i = lane; i < p; i += 32) {
+          const double z = Xs[i * pitch + k] * dinv[i];
+          const double z2 = z * z;
+          a += z2;
+          b = fma(z2, z2, b);
+        }
+        a = warp_sum(a), b = warp_sum(b);
+        if (lane == 0) q += a * a - b;
+      }
     }
     q = block_reduce<0>(q, red);
     // cov_finalize_kernel, :lw / :ss
@@ -695,13 +715,21 @@ __global__ void __launch_bounds__(1024) moments_small_kernel(const double *__res
 }
 
 void launch_moments_small(const double *X, long long ld, int p, int n, const double *w, const int *cols, int want_cov,
-                          int corrected,
-                          int method, double ridge, double *mu_out, double *U, const double *scale_dev,
+                          int corrected, int method, double ridge, double *mu_out, double *U, const double *scale_dev,
                           double *sums_out, double *Sraw, double *Sigma, double *lambda_out, const int *stop,
                           cudaStream_t s) {
-  moments_small_kernel<<<1, 1024, sizeof(double) * (2 * p + 40), s>>>(X, ld, p, n, w, cols, want_cov, corrected, method, ridge,
-                                                                     mu_out, U, scale_dev, sums_out, Sraw, Sigma,
-                                                                     lambda_out, stop);
+  // chunk of columns staged in shared memory: 2p + 40 + kc + p·pitch doubles <= 96 KB with pitch <= kc + 1
+  int kc = (int)((96LL * 1024 / 8 - 3LL * p - 40) / (p + 1));
+  kc = kc < 1 ? 1 : (kc > n ? n : kc);
+  const int pitch = kc | 1;  // odd: lanes over rows hit distinct banks
+  const size_t smem = sizeof(double) * (2 * (size_t)p + 40 + kc + (size_t)p * pitch);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(moments_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  moments_small_kernel<<<1, 1024, smem, s>>>(X, ld, p, n, w, cols, want_cov, corrected, method, ridge, kc, pitch, mu_out,
+                                             U, scale_dev, sums_out, Sraw, Sigma, lambda_out, stop);
 }
 
 // ---- G4: elite gather + early-stop test ---------------------------------------------------------
