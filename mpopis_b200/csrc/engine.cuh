@@ -92,8 +92,8 @@ struct PeerMailboxes {
 
 // ---- launchers (host). Every kernel of the AIS loop takes the device-side `stop` flag ----------
 // rollout.cu  (variant 0 = fast math-equivalent formulation, 1 = literal libm call sequence)
-void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, const int *stop,
-                        cudaStream_t s);
+void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, int stage,
+                        const int *stop, cudaStream_t s);
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
                         unsigned char *within, int use_lut, cudaStream_t s);

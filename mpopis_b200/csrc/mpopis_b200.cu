@@ -99,7 +99,7 @@ struct mpopis_handle {
   double gamma = 0.0;
   uint64_t seed = 0;
   long long step = 0;
-  int rollout_variant = 3, rollout_block = 64, coop_max = 1, sort_max = 1;
+  int rollout_variant = 3, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1;
   bool moments_small = true;  // single-CTA moment chain for small n ("moments_small" option, A/B)
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
   bool L0_valid = false;
@@ -439,7 +439,7 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
   a.traj = h->cfg.log_trajectories ? h->d_traj : nullptr;
   a.K = h->Kloc, a.T = h->T;
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
-    launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->stop(), h->st);
+    launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->rollout_stage, h->stop(), h->st);
   else
     launch_rollout_mc(h->mc, a, h->rollout_block, h->stop(), h->st);
   h->launches += 1;
@@ -813,6 +813,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   if (const char *e = getenv("MPOPIS_TRACE")) h->trace = atoi(e) != 0;
   if (const char *e = getenv("MPOPIS_ROLLOUT_VARIANT")) h->rollout_variant = atoi(e);
   if (const char *e = getenv("MPOPIS_ROLLOUT_BLOCK")) h->rollout_block = atoi(e);
+  if (const char *e = getenv("MPOPIS_ROLLOUT_STAGE")) h->rollout_stage = atoi(e) != 0;
   if (h->rollout_block < 32 || h->rollout_block > 128 || h->rollout_block % 32) h->rollout_block = 64;
 
   auto bail = [&](int rc) {
@@ -1080,6 +1081,10 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
       return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1, 2 or 3");
     h->rollout_variant = (int)value;
   }
+  else if (!strcmp(key, "rollout_stage")) {
+    if (value != 0.0 && value != 1.0) return fail(MPOPIS_ERR_BAD_ARG, "rollout_stage must be 0 or 1");
+    h->rollout_stage = (int)value;
+  }
   else if (!strcmp(key, "rollout_block")) {
     const int b = (int)value;
     if (b < 32 || b > 128 || b % 32) return fail(MPOPIS_ERR_BAD_ARG, "rollout_block must be 32, 64, 96 or 128");
@@ -1087,7 +1092,8 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
   } else if (!strcmp(key, "moments_small")) {
     h->moments_small = value != 0.0;
   } else if (!strcmp(key, "apply_l")) {
-    if (value != 0.0 && value != 1.0 && value != 2.0) return fail(MPOPIS_ERR_BAD_ARG, "apply_l must be 0, 1 or 2");
+    if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
+      return fail(MPOPIS_ERR_BAD_ARG, "apply_l must be 0, 1, 2 or 3");
     set_apply_L_path((int)value);  // process-wide
   } else
     return fail(MPOPIS_ERR_BAD_ARG, "unknown option %s", key);

@@ -29,6 +29,7 @@
 // The integer decisions of within_track (first arg-min, neighbour choice) use explicitly
 // non-contracted arithmetic (__dmul_rn/__dadd_rn) in every mode so that, on identical inputs, the
 // indices equal the reference's Float64 evaluation bit for bit.
+#include <cuda/ptx>
 #include <math_constants.h>
 
 #include "car_model.cuh"
@@ -88,16 +89,51 @@ __device__ __forceinline__ TrackView stage_track(const CarEnvArgs &env, double *
   return tr;
 }
 
-template <int NCARS, int MODE>
+// STAGE 1: the noise tile of a warp — AS rows x 32 samples, 256 contiguous bytes per row — is brought into shared
+// memory by the TMA bulk-copy engine (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), a few control steps
+// ahead, in a per-warp ring: no CTA-wide barrier, no registers held across the step. ncu on the register prefetch of
+// STAGE 0 (load E of step t+1, integrate step t): under the 128-register cap the prefetched values are spilled right
+// after the load, so the warp waits for the load after all — 24 % of the per-step stall samples sit on those two
+// STL instructions (≈11 % of the kernel; profiles/README.md). The kernel stays FP64-bound; this removes a stall, it
+// does not turn it into a bandwidth kernel.
+template <int NCARS, int MODE, int STAGE>
 __global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(const __grid_constant__ CarEnvArgs env,
                                                           const __grid_constant__ RolloutArgs a,
                                                           const int *stop) {
   extern __shared__ double smem[];
+  constexpr int AS = 2 * NCARS, SS = 8 * NCARS;
+  constexpr int D = NCARS <= 2 ? 4 : 2;  // ring depth (control steps in flight)
+  __shared__ __align__(128) double Es[STAGE ? 4 : 1][STAGE ? D : 1][STAGE ? AS : 1][32];
+  __shared__ __align__(8) uint64_t bars[STAGE ? 4 : 1][D];
   if (stop && *stop) return;
   const TrackView tr = stage_track(env, smem);
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.K) return;
-  constexpr int AS = 2 * NCARS, SS = 8 * NCARS;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long kw = (long long)blockIdx.x * blockDim.x + w * 32;  // first sample of this warp
+  if constexpr (STAGE) {
+    if (kw >= a.K) return;  // whole warp out of range; a partly filled warp keeps all lanes (they integrate padding)
+  } else {
+    if (k >= a.K) return;
+  }
+  auto issue = [&](int t) {  // lane 0: arm the stage's mbarrier and start the AS bulk copies of control step t
+    namespace ptx = cuda::ptx;
+    const int st = t % D;
+    ptx::fence_proxy_async(ptx::space_shared);  // the stage was read through the generic proxy
+    ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, &bars[w][st], AS * 256);
+#pragma unroll
+    for (int r = 0; r < AS; ++r)
+      ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, &Es[w][st][r][0],
+                         a.E + (size_t)(t * AS + r) * a.ldk + kw, 256, &bars[w][st]);
+  };
+  if constexpr (STAGE) {
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < D; ++q) cuda::ptx::mbarrier_init(&bars[w][q], 1);
+      cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+      for (int t = 0; t < D && t < a.T; ++t) issue(t);
+    }
+    __syncwarp();
+  }
   double s[SS];
 #pragma unroll
   for (int q = 0; q < SS; ++q) s[q] = __ldg(a.state0 + q);
@@ -105,17 +141,29 @@ __global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(co
   double cost = 0.0, cc = 0.0;
   double trig[4 * NCARS];
   bool trig_valid = false;
-  // the noise of step t+1 is fetched while step t integrates (ncu: long-scoreboard stalls on these loads)
+  // STAGE 0: the noise of step t+1 is fetched while step t integrates
   double e_next[AS];
+  if constexpr (!STAGE) {
 #pragma unroll
-  for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)r * a.ldk];
+    for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)r * a.ldk];
+  }
   for (int t = 0; t < a.T; ++t) {
     double act[AS], e_cur[AS];
+    if constexpr (STAGE) {
+      const int st = t % D;
+      while (!cuda::ptx::mbarrier_try_wait_parity(&bars[w][st], (unsigned)((t / D) & 1))) {
+      }
 #pragma unroll
-    for (int r = 0; r < AS; ++r) e_cur[r] = e_next[r];
-    if (t + 1 < a.T) {
+      for (int r = 0; r < AS; ++r) e_cur[r] = Es[w][st][r][lane];
+      __syncwarp();  // every lane has read the stage before it is refilled
+      if (lane == 0 && t + D < a.T) issue(t + D);
+    } else {
 #pragma unroll
-      for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)((t + 1) * AS + r) * a.ldk];
+      for (int r = 0; r < AS; ++r) e_cur[r] = e_next[r];
+      if (t + 1 < a.T) {
+#pragma unroll
+        for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)((t + 1) * AS + r) * a.ldk];
+      }
     }
 #pragma unroll
     for (int r = 0; r < AS; ++r) {
@@ -127,12 +175,12 @@ __global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(co
     // MODE 3 carries sin/cos of δ and Ψ across control steps; re-evaluated every 5th step and after a repair
     const bool resync = !trig_valid || (t % 5) == 0;
     cost -= cars_step_reward<NCARS, MODE>(env, tr, s, act, trig, resync, &trig_valid);  // UTL:137-138
-    if (a.traj) {
+    if (a.traj && k < a.K) {
 #pragma unroll
       for (int q = 0; q < SS; ++q) a.traj[((size_t)k * SS + q) * a.T + t] = s[q];  // UTL:139-141
     }
   }
-  a.costs[k] = cost + cc;  // POL:274-275
+  if (k < a.K) a.costs[k] = cost + cc;  // POL:274-275
 }
 
 // RLEnvs MountainCarEnv(continuous=true) step + EXM:10-22 reward
@@ -175,17 +223,17 @@ __global__ void __launch_bounds__(128) rollout_mc_kernel(const __grid_constant__
   a.costs[k] = cost + cc;
 }
 
-template <int MODE>
+template <int MODE, int STAGE>
 static void launch_rollout_car_v(const CarEnvArgs &env, const RolloutArgs &a, int block, const int *stop,
                                  cudaStream_t st) {
   const int grid = (a.K + block - 1) / block;
   const size_t smem = sizeof(double) * 3 * env.n_trk;
-#define MPOPIS_LAUNCH(N)                                                                   \
-  case N:                                                                                  \
-    if (smem > 48 * 1024)                                                                  \
-      cudaFuncSetAttribute(rollout_car_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           (int)smem);                                                     \
-    rollout_car_kernel<N, MODE><<<grid, block, smem, st>>>(env, a, stop);                 \
+#define MPOPIS_LAUNCH(N)                                                                               \
+  case N:                                                                                              \
+    if (smem > 40 * 1024)                                                                              \
+      cudaFuncSetAttribute(rollout_car_kernel<N, MODE, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem);                                                                 \
+    rollout_car_kernel<N, MODE, STAGE><<<grid, block, smem, st>>>(env, a, stop);                      \
     break;
   switch (env.n_cars) {
     MPOPIS_LAUNCH(1)
@@ -193,7 +241,7 @@ static void launch_rollout_car_v(const CarEnvArgs &env, const RolloutArgs &a, in
     MPOPIS_LAUNCH(3)
     MPOPIS_LAUNCH(4)
   }
-  if constexpr (MODE == 0 || MODE == 3) {  // 5..8 cars: only the production variants are instantiated (build time)
+  if constexpr ((MODE == 0 || MODE == 3) && STAGE == 0) {  // 5..8 cars: production variants, register prefetch only
     switch (env.n_cars) {
       MPOPIS_LAUNCH(5)
       MPOPIS_LAUNCH(6)
@@ -204,12 +252,15 @@ static void launch_rollout_car_v(const CarEnvArgs &env, const RolloutArgs &a, in
 #undef MPOPIS_LAUNCH
 }
 
-void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, const int *stop,
-                        cudaStream_t st) {
-  if (variant == 3) launch_rollout_car_v<3>(env, a, block, stop, st);
-  else if (variant == 0 || env.n_cars > 4) launch_rollout_car_v<0>(env, a, block, stop, st);
-  else if (variant == 1) launch_rollout_car_v<1>(env, a, block, stop, st);
-  else launch_rollout_car_v<2>(env, a, block, stop, st);
+// stage: 0 = register prefetch of the next step's noise, 1 = TMA bulk copies into a per-warp shared-memory ring
+// (variant 3, up to 4 cars, the rows of E 256-byte aligned per warp — guaranteed by ldk % 32 == 0)
+void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, int stage,
+                        const int *stop, cudaStream_t st) {
+  if (variant == 3 && stage == 1 && env.n_cars <= 4) launch_rollout_car_v<3, 1>(env, a, block, stop, st);
+  else if (variant == 3) launch_rollout_car_v<3, 0>(env, a, block, stop, st);
+  else if (variant == 0 || env.n_cars > 4) launch_rollout_car_v<0, 0>(env, a, block, stop, st);
+  else if (variant == 1) launch_rollout_car_v<1, 0>(env, a, block, stop, st);
+  else launch_rollout_car_v<2, 0>(env, a, block, stop, st);
 }
 
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t st) {

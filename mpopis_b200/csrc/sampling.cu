@@ -347,13 +347,104 @@ __global__ void __launch_bounds__(D2_NT, 2) apply_L_dmma2_kernel(const double *_
   }
 }
 
+// Third DMMA formulation ("apply_l" = 3, opt-in until measured): the kernel above balances the triangle over its
+// seven warps only on average — per 16-row chunk the warps hold 2, 1 or 0 active row fragments and the barrier
+// makes everyone wait for the busiest (≈70 % lock-step efficiency, 22 % of the stall samples on the barrier). Here
+// the COLUMNS are split instead: a CTA is 8 warps x 8 samples, every warp carries all 13 row fragments of the
+// 104-row block (26 accumulator doubles), so each warp does the whole triangle for its 8 columns and the warps
+// are perfectly balanced. L chunks (104 x 16) travel through the same 3-stage cp.async ring as Z.
+constexpr int D3_NW = 8, D3_NT = 32 * D3_NW, D3_BN = 8 * D3_NW, D3_LP = 20;
+struct D3Smem {
+  double Zs[3][D2_BJ][D2_ZP];
+  double Ls[3][D2_RB][D3_LP];
+};
+
+__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gsrc, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(D3_NT, 2) apply_L_dmma3_kernel(const double *__restrict__ Lt, int cs,
+                                                                  const double *__restrict__ Z,
+                                                                  double *__restrict__ E, long long ldk, int K,
+                                                                  const int *stop) {
+  if (stop && *stop) return;
+  extern __shared__ __align__(16) unsigned char d3raw[];
+  D3Smem &sm = *reinterpret_cast<D3Smem *>(d3raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int kbase = blockIdx.x * D3_BN, i0 = blockIdx.y * D2_RB;
+  const int jend = min(i0 + D2_RB, cs);
+  const int nchunks = (jend + D2_BJ - 1) / D2_BJ;
+  const int nfr = min(D2_NF, (cs - i0 + 7) / 8);  // row fragments of this block that contain rows < cs
+  double acc[D2_NF][2];
+#pragma unroll
+  for (int f = 0; f < D2_NF; ++f) acc[f][0] = acc[f][1] = 0.0;
+
+  auto stage = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int jc = chunk * D2_BJ, buf = chunk % 3;
+      for (int e = threadIdx.x; e < D2_BJ * (D3_BN / 2); e += D3_NT) {  // Z: 16 rows x 64 samples, 16-byte vectors
+        const int jj = e / (D3_BN / 2), v = e % (D3_BN / 2);
+        const int j = jc + jj;
+        const long long kg = (long long)kbase + 2 * v;
+        const bool pred = j < cs && kg + 1 < ldk;
+        cp_async16_zfill(&sm.Zs[buf][jj][2 * v], pred ? (const void *)(Z + (size_t)j * ldk + kg) : (const void *)Z, pred);
+      }
+      for (int e = threadIdx.x; e < 8 * nfr * D2_BJ; e += D3_NT) {  // L: rows i0.. x 16 columns jc.., 8-byte copies
+        const int ii = e / D2_BJ, jj = e % D2_BJ;
+        const int i = i0 + ii, j = jc + jj;
+        const bool pred = i < cs && j < cs;
+        cp_async8_zfill(&sm.Ls[buf][ii][jj], pred ? (const void *)(Lt + (size_t)i * cs + j) : (const void *)Lt, pred);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stage(0);
+  stage(1);
+  for (int c = 0; c < nchunks; ++c) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    stage(c + 2);
+    const int buf = c % 3, jc = c * D2_BJ;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j4 = 4 * q, jg = jc + j4;
+      if (jg >= jend) break;
+      const double bf = sm.Zs[buf][j4 + t][w * 8 + g];
+      const int fmin = (jg - i0) >> 3;  // fragment f needs j < i0 + 8f + 8  <=>  f > (j − i0)/8 − 1
+#pragma unroll
+      for (int f = 0; f < D2_NF; ++f) {
+        if (f >= fmin && f < nfr) {  // warp-uniform
+          const double af = sm.Ls[buf][f * 8 + g][j4 + t];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[f][0]), "+d"(acc[f][1])
+                       : "d"(af), "d"(bf));
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const int k = kbase + w * 8 + 2 * t;
+#pragma unroll
+  for (int f = 0; f < D2_NF; ++f) {
+    const int i = i0 + f * 8 + g;
+    if (f < nfr && i < cs) {
+      double *dst = E + (size_t)i * ldk + k;
+      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[f][0], acc[f][1]);
+      else if (k < K) dst[0] = acc[f][0];
+    }
+  }
+}
+
 // 0 = DFMA register tile, 1 = DMMA (32-row blocks), 2 = DMMA column-tile kernel; MPOPIS_APPLY_L / the
 // "apply_l" option select it process-wide (A/B evidence, profiles/).
 static int g_apply_L_path = -1;
 static int apply_L_path() {
   if (g_apply_L_path < 0) {
     const char *e = getenv("MPOPIS_APPLY_L");
-    g_apply_L_path = (e && e[0] == 'f') ? 0 : (e && e[0] == '1') ? 1 : 2;  // default: DMMA column tiles
+    g_apply_L_path = (e && e[0] == 'f') ? 0 : (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;  // default: 2
   }
   return g_apply_L_path;
 }
@@ -364,6 +455,14 @@ void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E
   if (bs < cs) {
     dim3 grid((K + 255) / 256, cs);
     apply_L_block_kernel<<<grid, 256, 0, s>>>(Lt, cs, bs, Z, E, ldk, K, stop);
+  } else if (apply_L_path() == 3) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(apply_L_dmma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(D3Smem));
+      attr_set = true;
+    }
+    dim3 grid((K + D3_BN - 1) / D3_BN, (cs + D2_RB - 1) / D2_RB);
+    apply_L_dmma3_kernel<<<grid, D3_NT, sizeof(D3Smem), s>>>(Lt, cs, Z, E, ldk, K, stop);
   } else if (apply_L_path() == 2) {
     dim3 grid((K + D2_BN - 1) / D2_BN, (cs + D2_RB - 1) / D2_RB);
     apply_L_dmma2_kernel<<<grid, D2_NT, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);

@@ -454,3 +454,23 @@ def test_single_cta_moment_chain_equals_the_kernel_chain(gpu_bound, policy, sigm
     np.testing.assert_allclose(a[4], b[4], rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(a[0], b[0], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(a[5], b[5], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_cars,K", [(1, 2050), (1, 70), (2, 333), (3, 96), (4, 64)])
+def test_tma_staged_noise_equals_register_prefetch(gpu_bound, n_cars, K):
+    """"rollout_stage" = 1 brings the noise tile of every warp into shared memory with TMA bulk copies (per-warp ring,
+    mbarrier completion) instead of prefetching it into registers: same arithmetic, so the costs are bit-identical —
+    including warps that are only partly filled (K not a multiple of 32)."""
+    env = make_env("car", n_cars)
+    T = 50
+    g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, K, T, 1)), env, "gmppi")
+    rng = np.random.default_rng(100 + n_cars)
+    E = rng.standard_normal((g.cs, K)) * 0.3
+    U = rng.uniform(-0.3, 0.3, g.cs)
+    st = env.state
+    g.set_option("rollout_stage", 0)
+    c0 = g.rollout_costs(st, 0, U, U, E)
+    g.set_option("rollout_stage", 1)
+    c1 = g.rollout_costs(st, 0, U, U, E)
+    assert np.array_equal(c0, c1)

@@ -1,5 +1,6 @@
 """A/B on one GPU: rollout variant (0 = v3 branchy, 3 = v4 straight-line) x E = L·Z kernel (1 = DMMA row blocks,
-2 = DMMA column tiles) x threads per rollout CTA, K = 65536 :cemppi control steps without early stop
+2 = DMMA column tiles, 3 = DMMA column split) x threads per rollout CTA x noise staging (0 = register prefetch,
+1 = TMA bulk copies into a per-warp shared-memory ring), K = 65536 :cemppi control steps without early stop
 (CUDA-event timings from the engine: whole step and the rollout launches inside it)."""
 import sys
 from pathlib import Path
@@ -9,13 +10,15 @@ from bench import make_engine
 from mpopis_b200 import _lib
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-configs = [(0, 1, 64), (3, 1, 64), (3, 2, 64), (3, 2, 128), (3, 2, 32), (0, 2, 64)]
+configs = [(0, 1, 64, 0), (3, 1, 64, 0), (3, 2, 64, 0), (3, 2, 64, 1), (3, 3, 64, 1), (3, 3, 64, 0), (3, 2, 128, 1),
+           (3, 2, 32, 1)]
 ref_ctrl = None
-for variant, apl, blk in configs:
+for variant, apl, blk, stage in configs:
     env, eng = make_engine(_lib.product(), K, 0, 1, 0, early_stop=False)
     eng.set_option("rollout_variant", variant)
     eng.set_option("apply_l", apl)
     eng.set_option("rollout_block", blk)
+    eng.set_option("rollout_stage", stage)
     U = np.zeros(eng.cs)
     tot, roll = [], []
     for i in range(6):
@@ -25,7 +28,7 @@ for variant, apl, blk in configs:
             tot.append(tm["total_ms"]), roll.append(tm["rollout_ms"] / max(tm["rollout_launches"], 1))
     if ref_ctrl is None:
         ref_ctrl = ctrl
-    print(f"K={K} variant={variant} apply_l={apl} block={blk}: step {np.median(tot):.3f} ms, rollout launch "
+    print(f"K={K} variant={variant} apply_l={apl} block={blk} stage={stage}: step {np.median(tot):.3f} ms, rollout launch "
           f"{np.median(roll) * 1e3:.1f} us, control {ctrl} (|Δ vs first config| {np.max(np.abs(ctrl - ref_ctrl)):.2e})",
           flush=True)
     eng.close()
