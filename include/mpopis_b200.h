@@ -224,11 +224,16 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
 int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out);
 /* Tuning knobs, not part of the reference API: "rollout_variant" (3 = default, speculative straight-line
  * step with repair; 0 = branchy fast formulation; 2 = first fast cut; 1 = literal libm call sequence of
- * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128), "rollout_stage" (how the rollout
+ * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128), "rollout_profile" (1 = record per-warp cycles of the rollout kernel, see warp_cycles), "rollout_stage" (how the rollout
  * kernel reads the noise tensor: 0 = register prefetch, 1 = TMA bulk copies into a per-warp shared-memory ring), "apply_l" (E = L·Z kernel,
  * process-wide: 0 = DFMA register tile, 1 = DMMA 32-row blocks, 2 = DMMA column tiles with cp.async),
  * "moments_small" (1 = single-CTA moment chain for <= 512 columns, the default; 0 = the multi-kernel chain). */
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value);
+
+/* Profiling aid: with set_option("rollout_profile", 1) every warp of the rollout kernel records the clock64() cycles
+ * it spent in the kernel; this returns the values of the most recent rollout launch (ceil(K_local/32) entries at most
+ * n are written) — the spread between warps shows how much of a launch is tail (repaired steps, full track scans). */
+int mpopis_b200_warp_cycles(mpopis_t *h, int64_t *cycles_out, int64_t n);
 
 /* Device-resident control loop used by bench.py's `value` leg: state and U stay in HBM, the
  * step is enqueued without host copies of inputs; the control is applied to the resident env

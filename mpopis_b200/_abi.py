@@ -96,6 +96,7 @@ PRODUCT_ONLY = {
     "launch_count": (C.c_int64, [_H]),
     "last_timing": (C.c_int, [_H, _D, _D, _I32]),
     "stream": (C.c_void_p, [_H]),
+    "warp_cycles": (C.c_int, [_H, _I64, C.c_int64]),
 }
 ORACLE_ONLY = {
     "set_threads": (C.c_int, [_H, C.c_int]),

@@ -77,6 +77,7 @@ struct RolloutArgs {
   double *costs;        // [K_local]
   double *traj;         // nullptr or [K_local][ss][T] (logger, UTL:139-141)
   int K;                // samples of this shard
+  long long *warp_cycles; // nullptr, or one slot per warp: clock64() spent in the kernel ("rollout_profile" option)
   int T;                // horizon
 };
 

@@ -115,7 +115,7 @@ struct mpopis_handle {
          *d_cdf = nullptr, *d_wcnt = nullptr, *d_ws = nullptr, *d_sigma = nullptr, *d_psig = nullptr,
          *d_pSig = nullptr, *d_dw = nullptr, *d_C = nullptr, *d_ns = nullptr, *d_reward = nullptr,
          *d_ones = nullptr;
-  long long *d_env_t = nullptr;
+  long long *d_env_t = nullptr, *d_warp_cycles = nullptr;  // d_warp_cycles: "rollout_profile" option
   unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
   int *d_order = nullptr, *d_vals_b = nullptr, *d_hist = nullptr, *d_counts = nullptr, *d_flags = nullptr;
   unsigned char *d_done = nullptr;
@@ -438,6 +438,7 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
   a.state0 = h->d_state, a.env_t = h->d_env_t, a.costs = h->d_costs + h->k0;
   a.traj = h->cfg.log_trajectories ? h->d_traj : nullptr;
   a.K = h->Kloc, a.T = h->T;
+  a.warp_cycles = h->d_warp_cycles;
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
     launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->rollout_stage, h->stop(), h->st);
   else
@@ -939,6 +940,7 @@ int mpopis_b200_destroy(mpopis_t *h) {
                   h->d_bvec2};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  if (h->d_warp_cycles) cudaFree(h->d_warp_cycles);
   if (h->h_ext_controls) cudaFreeHost(h->h_ext_controls);
   if (h->h_ext_costs) cudaFreeHost(h->h_ext_costs);
   if (h->h_ext_stop) cudaFreeHost(h->h_ext_stop);
@@ -1080,6 +1082,13 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
       return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1, 2 or 3");
     h->rollout_variant = (int)value;
+  }
+  else if (!strcmp(key, "rollout_profile")) {  // per-warp clock64() of the rollout kernel, read with warp_cycles()
+    if (value != 0.0 && !h->d_warp_cycles) {
+      if (int rc = dalloc(&h->d_warp_cycles, (size_t)h->Kloc / 32 + 2)) return rc;
+    } else if (value == 0.0 && h->d_warp_cycles) {
+      cudaFree(h->d_warp_cycles), h->d_warp_cycles = nullptr;
+    }
   }
   else if (!strcmp(key, "rollout_stage")) {
     if (value != 0.0 && value != 1.0) return fail(MPOPIS_ERR_BAD_ARG, "rollout_stage must be 0 or 1");
@@ -1370,6 +1379,16 @@ int mpopis_b200_cov_estimate(mpopis_t *h, int32_t sigma_est, const double *X, in
   CU(cudaGetLastError());
   cudaFree(dcm), cudaFree(dX), cudaFree(dS);
   if (dw) cudaFree(dw);
+  return 0;
+}
+
+int mpopis_b200_warp_cycles(mpopis_t *h, int64_t *cycles_out, int64_t n) {
+  if (!h || !cycles_out || n < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
+  if (!h->d_warp_cycles) return fail(MPOPIS_ERR_BAD_ARG, "set_option(\"rollout_profile\", 1) first");
+  if (int rc = set_device(h)) return rc;
+  const int64_t nw = (h->Kloc + 31) / 32;
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaMemcpy(cycles_out, h->d_warp_cycles, sizeof(long long) * (size_t)(n < nw ? n : nw), cudaMemcpyDeviceToHost));
   return 0;
 }
 

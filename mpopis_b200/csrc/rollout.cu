@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(co
   __shared__ __align__(128) double Es[STAGE ? 4 : 1][STAGE ? D : 1][STAGE ? AS : 1][32];
   __shared__ __align__(8) uint64_t bars[STAGE ? 4 : 1][D];
   if (stop && *stop) return;
+  const long long t_begin = a.warp_cycles ? clock64() : 0;
   const TrackView tr = stage_track(env, smem);
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_kernel(co
     }
   }
   if (k < a.K) a.costs[k] = cost + cc;  // POL:274-275
+  if (a.warp_cycles && lane == 0) a.warp_cycles[k >> 5] = clock64() - t_begin;
 }
 
 // RLEnvs MountainCarEnv(continuous=true) step + EXM:10-22 reward

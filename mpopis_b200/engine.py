@@ -299,6 +299,13 @@ class Engine:
         buf = C.create_string_buffer(nccl_id, 128)
         self._chk(self.b.comm_init(self.h, buf))
 
+    def warp_cycles(self) -> np.ndarray:
+        """Per-warp clock64() cycles of the most recent rollout launch (needs set_option("rollout_profile", 1))."""
+        n = (self.Kloc + 31) // 32
+        out = np.zeros(n, dtype=np.int64)
+        self._chk(self.b.warp_cycles(self.h, out.ctypes.data_as(C.POINTER(C.c_int64)), n))
+        return out
+
     def launch_count(self) -> int:
         return int(self.b.launch_count(self.h))
 
