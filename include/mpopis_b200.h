@@ -224,7 +224,9 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
 int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out);
 /* Tuning knobs, not part of the reference API: "rollout_variant" (3 = default, speculative straight-line
  * step with repair; 0 = branchy fast formulation; 2 = first fast cut; 1 = literal libm call sequence of
- * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128), "rollout_profile" (1 = record per-warp cycles of the rollout kernel, see warp_cycles), "rollout_stage" (how the rollout
+ * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128), "rollout_queue" (n > 0: persistent work-queue rollout kernel with n warps per SM handing out
+ * (32 rollouts x 10 control steps) units dynamically; 0 = one thread per rollout, one launch-time placement),
+ * "rollout_profile" (1 = record per-warp cycles of the rollout kernel, see warp_cycles), "rollout_stage" (how the rollout
  * kernel reads the noise tensor: 0 = register prefetch, 1 = TMA bulk copies into a per-warp shared-memory ring), "apply_l" (E = L·Z kernel,
  * process-wide: 0 = DFMA register tile, 1 = DMMA 32-row blocks, 2 = DMMA column tiles with cp.async),
  * "moments_small" (1 = single-CTA moment chain for <= 512 columns, the default; 0 = the multi-kernel chain). */

@@ -77,6 +77,11 @@ struct RolloutArgs {
   double *costs;        // [K_local]
   double *traj;         // nullptr or [K_local][ss][T] (logger, UTL:139-141)
   int K;                // samples of this shard
+  // work-queue variant (rollout_car_queue_kernel): per-rollout state between units of `unit_len` control steps,
+  // [head | done[batches]] counters (zeroed before every launch); queue_ctas = persistent grid size
+  double *ws;
+  int *ws_sync;
+  int unit_len, queue_ctas;
   long long *warp_cycles; // nullptr, or one slot per warp: clock64() spent in the kernel ("rollout_profile" option)
   int T;                // horizon
 };
@@ -95,6 +100,9 @@ struct PeerMailboxes {
 // rollout.cu  (variant 0 = fast math-equivalent formulation, 1 = literal libm call sequence)
 void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, int stage,
                         const int *stop, cudaStream_t s);
+// 0 when the work-queue kernel does not apply (then launch_rollout_car must be used)
+int rollout_queue_fields(int n_cars);  // doubles of scratch per rollout
+int launch_rollout_car_queue(const CarEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
                         unsigned char *within, int use_lut, cudaStream_t s);

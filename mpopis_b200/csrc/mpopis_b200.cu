@@ -115,6 +115,9 @@ struct mpopis_handle {
          *d_cdf = nullptr, *d_wcnt = nullptr, *d_ws = nullptr, *d_sigma = nullptr, *d_psig = nullptr,
          *d_pSig = nullptr, *d_dw = nullptr, *d_C = nullptr, *d_ns = nullptr, *d_reward = nullptr,
          *d_ones = nullptr;
+  double *d_rq_ws = nullptr;  // work-queue rollout kernel: state scratch and [head | done[]] counters
+  int *d_rq_sync = nullptr;
+  int rollout_queue = 0, num_sms = 0;  // "rollout_queue" option: 0 off, n = persistent warps per SM
   long long *d_env_t = nullptr, *d_warp_cycles = nullptr;  // d_warp_cycles: "rollout_profile" option
   unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
   int *d_order = nullptr, *d_vals_b = nullptr, *d_hist = nullptr, *d_counts = nullptr, *d_flags = nullptr;
@@ -439,8 +442,20 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
   a.traj = h->cfg.log_trajectories ? h->d_traj : nullptr;
   a.K = h->Kloc, a.T = h->T;
   a.warp_cycles = h->d_warp_cycles;
-  if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
-    launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->rollout_stage, h->stop(), h->st);
+  if (h->cfg.env == MPOPIS_ENV_CAR_RACING) {
+    bool queued = false;
+    // work queue: only when the rollouts are more than the persistent grid holds at once (otherwise every warp has
+    // exactly one batch and the plain kernel is the same thing without the bookkeeping)
+    if (h->rollout_queue > 0 && h->rollout_variant == 3 && h->cfg.n_cars == 1 && h->d_rq_ws &&
+        (h->Kloc + 31) / 32 > h->rollout_queue * h->num_sms) {
+      a.ws = h->d_rq_ws, a.ws_sync = h->d_rq_sync;
+      a.unit_len = h->T >= 20 ? 10 : (h->T + 1) / 2;
+      a.queue_ctas = h->rollout_queue * h->num_sms * 32 / h->rollout_block;
+      queued = launch_rollout_car_queue(h->car, a, h->rollout_block, h->stop(), h->st) != 0;
+    }
+    if (!queued)
+      launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->rollout_stage, h->stop(), h->st);
+  }
   else
     launch_rollout_mc(h->mc, a, h->rollout_block, h->stop(), h->st);
   h->launches += 1;
@@ -908,6 +923,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   h->ev.resize(2 + 2 * h->N);
   for (auto &e : h->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MPOPIS_ERR_CUDA, "cudaEventCreate failed"));
+  h->num_sms = prop.multiProcessorCount;
   h->coop_max = inv_sqrt_max_ctas(prop.multiProcessorCount);
   h->sort_max = sort_max_ctas(prop.multiProcessorCount);
   {  // Σ defaults to the identity until set_sigma()
@@ -941,6 +957,8 @@ int mpopis_b200_destroy(mpopis_t *h) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->d_warp_cycles) cudaFree(h->d_warp_cycles);
+  if (h->d_rq_ws) cudaFree(h->d_rq_ws);
+  if (h->d_rq_sync) cudaFree(h->d_rq_sync);
   if (h->h_ext_controls) cudaFreeHost(h->h_ext_controls);
   if (h->h_ext_costs) cudaFreeHost(h->h_ext_costs);
   if (h->h_ext_stop) cudaFreeHost(h->h_ext_stop);
@@ -1082,6 +1100,16 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
       return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1, 2 or 3");
     h->rollout_variant = (int)value;
+  }
+  else if (!strcmp(key, "rollout_queue")) {  // persistent warps per SM of the work-queue rollout kernel (0 = off)
+    const int n = (int)value;
+    if (n < 0 || n > 16 || (n * 32) % h->rollout_block) return fail(MPOPIS_ERR_BAD_ARG, "rollout_queue must be 0..16 warps per SM, a multiple of the CTA's warps");
+    if (n > 0 && !h->d_rq_ws && rollout_queue_fields(h->cfg.env == MPOPIS_ENV_CAR_RACING ? h->cfg.n_cars : 0) > 0) {
+      const size_t nb = ((size_t)h->Kloc + 31) / 32;
+      if (int rc = dalloc(&h->d_rq_ws, nb * 32 * (size_t)rollout_queue_fields(h->cfg.n_cars))) return rc;
+      if (int rc = dalloc(&h->d_rq_sync, nb + 1)) return rc;
+    }
+    h->rollout_queue = n;
   }
   else if (!strcmp(key, "rollout_profile")) {  // per-warp clock64() of the rollout kernel, read with warp_cycles()
     if (value != 0.0 && !h->d_warp_cycles) {

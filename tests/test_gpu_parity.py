@@ -475,3 +475,22 @@ def test_tma_staged_noise_equals_register_prefetch(gpu_bound, n_cars, K):
     g.set_option("rollout_stage", 1)
     c1 = g.rollout_costs(st, 0, U, U, E)
     assert_costs_close(c1, c0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [50, 23])
+def test_work_queue_rollouts_equal_the_plain_kernel(gpu_bound, T):
+    """"rollout_queue" = 12: a persistent grid of 12 warps per SM pulls (32 rollouts x 10 control steps) units from an
+    atomic counter and carries the rollout state through a scratch buffer between units — same arithmetic as the
+    one-thread-per-rollout launch, including a last unit shorter than the others and a last batch that is not full."""
+    env = make_env("car")
+    K = 65536 - 13
+    g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, K, T, 1)), env, "gmppi")
+    rng = np.random.default_rng(7)
+    E = rng.standard_normal((g.cs, K)) * 0.3
+    U = rng.uniform(-0.3, 0.3, g.cs)
+    st = synthetic_states()[3]
+    c0 = g.rollout_costs(st, 0, U, U, E)
+    g.set_option("rollout_queue", 12)
+    c1 = g.rollout_costs(st, 0, U, U, E)
+    assert_costs_close(c1, c0)

@@ -10,15 +10,16 @@ from bench import make_engine
 from mpopis_b200 import _lib
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-configs = [(0, 1, 64, 0), (3, 1, 64, 0), (3, 2, 64, 0), (3, 2, 64, 1), (3, 3, 64, 1), (3, 3, 64, 0), (3, 2, 128, 1),
-           (3, 2, 32, 1)]
+configs = [(0, 1, 64, 0, 0), (3, 2, 64, 0, 0), (3, 2, 64, 1, 0), (3, 2, 64, 0, 12), (3, 2, 64, 0, 14), (3, 2, 64, 0, 16),
+           (3, 2, 64, 0, 10), (3, 2, 128, 0, 12)]
 ref_ctrl = None
-for variant, apl, blk, stage in configs:
+for variant, apl, blk, stage, queue in configs:
     env, eng = make_engine(_lib.product(), K, 0, 1, 0, early_stop=False)
     eng.set_option("rollout_variant", variant)
     eng.set_option("apply_l", apl)
     eng.set_option("rollout_block", blk)
     eng.set_option("rollout_stage", stage)
+    eng.set_option("rollout_queue", queue)
     U = np.zeros(eng.cs)
     tot, roll = [], []
     for i in range(6):
@@ -28,7 +29,7 @@ for variant, apl, blk, stage in configs:
             tot.append(tm["total_ms"]), roll.append(tm["rollout_ms"] / max(tm["rollout_launches"], 1))
     if ref_ctrl is None:
         ref_ctrl = ctrl
-    print(f"K={K} variant={variant} apply_l={apl} block={blk} stage={stage}: step {np.median(tot):.3f} ms, rollout launch "
+    print(f"K={K} variant={variant} apply_l={apl} block={blk} stage={stage} queue={queue}: step {np.median(tot):.3f} ms, rollout launch "
           f"{np.median(roll) * 1e3:.1f} us, control {ctrl} (|Δ vs first config| {np.max(np.abs(ctrl - ref_ctrl)):.2e})",
           flush=True)
     eng.close()

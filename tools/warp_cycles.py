@@ -10,6 +10,8 @@ from mpopis_b200 import _lib
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 env, eng = make_engine(_lib.product(), K, 0, 1, 0, early_stop=False)
 eng.set_option("rollout_profile", 1)
+if len(sys.argv) > 2:
+    eng.set_option("rollout_queue", int(sys.argv[2]))
 U = np.zeros(eng.cs)
 st = env.state.copy()
 for i in range(12):
