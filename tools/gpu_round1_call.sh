@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-( timeout 150 python -m pytest tests/test_gpu_parity.py -m gpu -q -rf -k "work_queue" ) > gpurun_out/pytest_queue.log 2>&1; echo "queue rc=$?" >> gpurun_out/pytest_queue.log
-timeout 200 python tools/ab_variants.py > gpurun_out/ab.log 2>&1
-timeout 100 python tools/warp_cycles.py 65536 12 > gpurun_out/warp_cycles_q12.log 2>&1
-tail -3 gpurun_out/pytest_queue.log; cat gpurun_out/ab.log; tail -3 gpurun_out/warp_cycles_q12.log
+( time timeout 900 python -m pytest tests -m gpu -q --maxfail=15 -rf --durations=5 ) > gpurun_out/pytest.log 2>&1
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+timeout 400 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
+tail -4 gpurun_out/pytest.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.log | cut -c1-300; tail -3 gpurun_out/bench.err
