@@ -4,8 +4,9 @@ The rollout kernel runs ~3.5 warps per scheduler, each stalled most of the time 
 (ncu: "wait"), so what matters besides the FP64 instruction count is how many dependent instructions ptxas placed
 back to back. This tool replays the hot loop (found as the innermost backward branch containing N MUFU.RCP64H) through
 a scoreboard: an instruction issues one cycle after its predecessor at the earliest and not before its source
-registers / predicates are ready. Latencies are calibrated against ncu's per-instruction stall samples on B200
-(dependent FP64 ≈ 18 cycles under 3-4 warps of contention). It prints cycles per iteration and the stall histogram.
+registers / predicates are ready. FP64 latencies are the dependent-issue latencies measured on B200 by
+tools/fp64_mix_bench.cu (DFMA 23, DMUL/DADD 25 cycles; the numbers quoted in DESIGN.md / profiles for round 1 were
+produced with an earlier calibration of 18). It prints cycles per iteration and the stall histogram.
 
     cuobjdump -sass file.o > f.sass; python tools/sass_sched.py f.sass [n_rcp_in_loop=2]
 """
@@ -13,7 +14,7 @@ import re
 import sys
 from collections import Counter
 
-LAT = {"DFMA": 18, "DMUL": 18, "DADD": 18, "DSETP": 18, "MUFU": 30, "LDC": 30, "LDCU": 30, "LDS": 30, "LDG": 300}
+LAT = {"DFMA": 23, "DMUL": 25, "DADD": 25, "DSETP": 23, "MUFU": 30, "LDC": 30, "LDCU": 30, "LDS": 30, "LDG": 300}
 DEFAULT_LAT = 5
 FP64 = ("DFMA", "DMUL", "DADD", "DSETP")
 
