@@ -108,3 +108,38 @@ def test_gpu_external_misuse_errors(gpu_bound):
         ext.plan(np.zeros(0), 0, np.zeros(10))  # the built-in entry point has no simulator to call
     with pytest.raises(EngineError, match="world_size|ext_action_size"):
         Engine(gpu_bound, policy="cemppi", env=_abi.ENV_EXTERNAL, num_samples=32, horizon=5, ext_action_size=0)
+
+
+def test_policy_functor_with_an_external_env(orc):
+    """pol(env::EnvpoolEnv) through the Python mirror: get_policy + ExternalEnv drive plan_external, and a closed loop
+    on a caller-side simulator (a point mass with quadratic cost, in numpy) makes progress. Oracle backend, no GPU."""
+    from mpopis_b200 import ExternalEnv, get_policy
+
+    class PointMass:  # the caller's batched simulator: x'' = a, cost = Σ_t (x − 1)² + 0.1 v²
+        def __init__(self):
+            self.x, self.v, self.dt = 0.0, 0.0, 0.1
+
+        def rollout(self, controls):  # [K, as=1, T] -> costs[K]; the simulator itself is not advanced (restore=true)
+            K, _, T = controls.shape
+            x, v, cost = np.full(K, self.x), np.full(K, self.v), np.zeros(K)
+            for t in range(T):
+                v = v + self.dt * controls[:, 0, t]
+                x = x + self.dt * v
+                cost += (x - 1.0) ** 2 + 0.1 * v ** 2
+            return cost
+
+        def step(self, a):
+            self.v += self.dt * float(a)
+            self.x += self.dt * self.v
+
+    sim = PointMass()
+    env = ExternalEnv([-2.0], [2.0], sim.rollout)
+    pol = get_policy("cemppi", env, 64, 12, 1.0, 1.0, [0.0], [1.0], False, 4, 20.0, 0.8, "mle", 0.75, 0.8,
+                     backend=orc.bound())
+    pol.seed(5)
+    assert pol.params.as_ == 1 and pol.params.ss == 0 and pol.params.cs == 12
+    for _ in range(40):
+        a = pol(env)
+        assert a.shape == (1,) and -2.0 <= a[0] <= 2.0  # clamped first action (UTL:88-101)
+        sim.step(a[0])
+    assert abs(sim.x - 1.0) < 0.25  # the controller drove the point mass to the target
