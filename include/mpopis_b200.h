@@ -128,6 +128,16 @@ int mpopis_b200_destroy(mpopis_t *h);
 int mpopis_b200_comm_id(void *nccl_id_out128);
 int mpopis_b200_comm_init(mpopis_t *h, const void *nccl_id128);
 
+/* Loop-back communicator: `world` VIRTUAL ranks on one device in one process — handles created with world_size =
+ * world, rank = 0..world-1 and the same device, attached to one group, each then driven from its own host thread (a
+ * collective blocks until every virtual rank has entered it). It exists so that the sharded code path (all-gathered
+ * costs -> identical elite selection on every rank, ownership-compacted elite moments, fixed-order reductions:
+ * SURVEY §8e; the reference itself has no multi-device path, POL:269 is its only parallel loop) can be verified on a
+ * single-GPU box against the unsharded engine and the oracle. Production sharding uses comm_init (NCCL). */
+int mpopis_b200_loopback_create(int32_t world, void **group_out);
+int mpopis_b200_loopback_destroy(void *group);
+int mpopis_b200_comm_init_loopback(mpopis_t *h, void *group);
+
 /* env.params (CAR:2-21, 18 doubles per car in declaration order), env.dt, env.δt (CAR:33-34),
  * env.track.x′, y′, lane_width′ (TRK:6-8). n_cars > 1 is MultiCarRacingEnv (MCR:2-12). */
 int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params18_per_car, double dt,
@@ -193,6 +203,14 @@ int mpopis_b200_rollout_costs(mpopis_t *h, const double *state, int64_t env_t, c
                               double *costs_out);
 /* compute_weights(Information_Theoretic(λ), costs) UTL:79-86. */
 int mpopis_b200_weights(mpopis_t *h, const double *costs, int64_t K, double lambda, double *w_out);
+/* Parity surface of the sort-free elite selection (csrc/select.cu): the elite SET order[1:m] of
+ * `order = sortperm(trajectory_cost)` (POL:455-456; ascending sample ids, 0-based, restricted to the ownership window
+ * [k0, k0 + kloc)) and the early-stop decision `maximum(abs.(diff(elite_traj_cost))) < 10e-3` (POL:458-461).
+ * tau_out4 (nullable): {cost of the m-th smallest, its sample id, smallest cost, buckets used by the gap test}. */
+int mpopis_b200_elite_select(mpopis_t *h, const double *costs, int64_t K, int64_t m, int64_t k0, int64_t kloc,
+                             int32_t early_stop, int64_t *elite_ids_out, int64_t *n_out, int32_t *stop_out,
+                             double *tau_out4);
+
 /* within_track(track, pos) TRK:68-92 for n positions (pos = 2 x n column-major):
  * idx/idx2 are the 0-based min_idx / min_idx_2, dist = dist_to_pt, within = 0/1. */
 int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *idx_out,

@@ -85,6 +85,9 @@ PRODUCT_ONLY = {
     "abi_version": (C.c_int, []),
     "comm_id": (C.c_int, [C.c_void_p]),
     "comm_init": (C.c_int, [_H, C.c_void_p]),
+    "loopback_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "loopback_destroy": (C.c_int, [C.c_void_p]),
+    "comm_init_loopback": (C.c_int, [_H, C.c_void_p]),
     "set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "resident_reset": (C.c_int, [_H, _D, C.c_int64, _D]),
     "resident_plan": (C.c_int, [_H, C.c_int32]),
@@ -92,6 +95,7 @@ PRODUCT_ONLY = {
     "resident_total_its": (C.c_int, [_H, _I64]),
     "measure_fp64_peak": (C.c_int, [_H, _D]),
     "sortperm": (C.c_int, [_H, _D, C.c_int64, _I64]),
+    "elite_select": (C.c_int, [_H, _D, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _I64, _I64, _I32, _D]),
     "bench_rowsum": (C.c_int, [_H, C.c_int32, _D, _D]),
     "launch_count": (C.c_int64, [_H]),
     "last_timing": (C.c_int, [_H, _D, _D, _I32]),

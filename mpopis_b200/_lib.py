@@ -47,3 +47,21 @@ def comm_id() -> bytes:
     if rc != 0:
         raise EngineUnavailable(f"mpopis_b200_comm_id failed ({rc}): {b.error()}")
     return buf.raw
+
+
+class LoopbackGroup:
+    """`world` virtual ranks on one device in one process (include/mpopis_b200.h: loopback_create). Every
+    handle of the group must be driven from its own host thread — see `sharding.run_virtual_ranks`."""
+
+    def __init__(self, world: int):
+        self.b = product()
+        self.ptr = C.c_void_p()
+        rc = self.b.loopback_create(int(world), C.byref(self.ptr))
+        if rc != 0:
+            raise EngineUnavailable(f"mpopis_b200_loopback_create failed ({rc}): {self.b.error()}")
+        self.world = int(world)
+
+    def close(self):
+        if self.ptr:
+            self.b.loopback_destroy(self.ptr)
+            self.ptr = C.c_void_p()

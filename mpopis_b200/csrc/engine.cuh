@@ -77,32 +77,31 @@ struct RolloutArgs {
   double *costs;        // [K_local]
   double *traj;         // nullptr or [K_local][ss][T] (logger, UTL:139-141)
   int K;                // samples of this shard
-  // work-queue variant (rollout_car_queue_kernel): per-rollout state between units of `unit_len` control steps,
-  // [head | done[batches]] counters (zeroed before every launch); queue_ctas = persistent grid size
-  double *ws;
-  int *ws_sync;
-  int unit_len, queue_ctas;
   long long *warp_cycles; // nullptr, or one slot per warp: clock64() spent in the kernel ("rollout_profile" option)
   int T;                // horizon
 };
 
-// Peer-memory mailboxes of a sharded policy (peer.cu): data[r] / flag[r] point into rank r's mailbox
-// (own memory for r == rank, cudaIpcOpenMemHandle mappings otherwise).
-struct PeerMailboxes {
-  double *data[64];             // 2 slots x capacity doubles each
-  unsigned long long *flag[64]; // 2 sequence flags each
-  unsigned int *arrive;         // 2 local CTA-arrival counters
-  long long capacity;
-  int rank, world;
-};
+#ifdef __CUDACC__
+// Order-preserving 64-bit image of a cost under Base.isless (the `lt` of sortperm, POL:455,563): negative doubles
+// reversed, −0.0 < +0.0, every NaN (either sign bit) above +Inf. Ties are broken by the sample index, which makes the
+// composite (key, index) unique — any comparison sort or selection on it reproduces the stable order.
+constexpr unsigned long long COST_KEY_NAN = 0xFFFFFFFFFFFFFFFEULL;  // below the padding key ~0
+__device__ __forceinline__ unsigned long long cost_key(double c) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(c);
+  if (c != c) return COST_KEY_NAN;
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double key_cost(unsigned long long k) {
+  if (k >= COST_KEY_NAN) return __longlong_as_double(0x7ff8000000000000LL);
+  k = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)k);
+}
+#endif
 
 // ---- launchers (host). Every kernel of the AIS loop takes the device-side `stop` flag ----------
 // rollout.cu  (variant 0 = fast math-equivalent formulation, 1 = literal libm call sequence)
 void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, int stage,
                         const int *stop, cudaStream_t s);
-// 0 when the work-queue kernel does not apply (then launch_rollout_car must be used)
-int rollout_queue_fields(int n_cars);  // doubles of scratch per rollout
-int launch_rollout_car_queue(const CarEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
                         unsigned char *within, int use_lut, cudaStream_t s);
@@ -133,8 +132,6 @@ void launch_rowsum_partial(const double *X, long long ld, int rows, int n, const
                            const int *stop, cudaStream_t s, const int *n_dev = nullptr, int sq = 0);
 void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop, cudaStream_t s,
                             int stride = 0);
-void launch_dinv_from_moments(const double *sum1, const double *sum2, const double *cnt, int p, int standardise,
-                              double *dinv, const int *stop, cudaStream_t s);
 void launch_finalize_mean(const double *sums, int rows, double *mu, double *U, const double *scale_dev,
                           const int *stop, cudaStream_t s);
 int syrk_nchunks(int n);
@@ -165,7 +162,7 @@ void launch_pmc_counts(const double *wglobal, int K, const double *u, double *cd
                        int Kloc, double *wloc, const int *stop, cudaStream_t s);
 void launch_ctrl_vec(const double *Sinv, int cs, const double *U_orig, double gamma, double *b, cudaStream_t s);
 void launch_finalize_control(const double *wsum, const double *U_orig, const double *U_cur, int cs, int as, int T,
-                             double *U_next, double *control, cudaStream_t s);
+                             double *U_next, double *control, const double *bounds, cudaStream_t s);
 // linalg.cu
 void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, double *Wglobal, int *info, int tag,
                  const int *stop, cudaStream_t s);
@@ -182,15 +179,28 @@ void launch_cma_lin_gather(const double *X, long long ldx, int cs, const int *or
 void launch_cma_vec(const double *dw, const double *C, const double *dvec, const double *ws, int K, int cs,
                     int n_iter, const mpopis_cma_t &c, double *psig, double *pSig, double *sigma_dev, double *U,
                     double *Sigma, const int *stop, cudaStream_t s);
-// peer.cu
-void launch_peer_allreduce(const PeerMailboxes &pm, double *buf, int n, unsigned long long seq, int *info,
-                           const int *stop, cudaStream_t s);
+// select.cu — :cemppi elite selection without a sort (radix select + bucketed early-stop test + compaction)
+constexpr int SELECT_MAX_CTAS = 592;
+constexpr size_t SELECT_WS_BYTES = 64 * 1024;
+int select_max_ctas(int num_sms);
+long long select_bucket_capacity(int m);  // entries of bmin / bmax
+void launch_select_init(void *ws, unsigned long long *bmin, unsigned long long *bmax, long long nb_cap, cudaStream_t s);
+// costs: the GLOBAL cost vector (Ktot); [k0, k0 + Kloc) = the samples this shard owns. Outputs: eidx[0:*m_loc] = local
+// ids of the owned elites in index order, *stop_flag raised when the reference would `break` (POL:459-461);
+// tau_out (nullable, 4 doubles): {τ cost, τ index, smallest cost, buckets used}. Returns a cudaError_t.
+int launch_ce_select(const double *costs, int Ktot, int m, long long k0, int Kloc, int early_stop, void *ws,
+                     unsigned long long *bmin, unsigned long long *bmax, long long nb_cap, int *eidx, int *m_loc,
+                     double *tau_out, int *stop_flag, const int *stop, int max_ctas, cudaStream_t s);
+int elite_gather_nchunks(int m_max);
+// X[r][j] = E[r][eidx[j]], partial[(2c + {0,1}) * cs + r] = Σ x, Σ x² over chunk c
+void launch_elite_gather_sums(const double *E, long long ldk, int cs, const int *eidx, const int *m_loc, int m_max,
+                              double *X, long long ldx, double *partial, const int *stop, cudaStream_t s);
+// sums = [Σx | n | Σx²]; finalize: μ, U += μ, dinv = 1/σ (standardise) or 1. nchunks = 0: sums already reduced.
+void launch_ce_sums(const double *partial, int nchunks, int cs, const int *m_loc, double *sums, int finalize,
+                    int standardise, double *mu, double *U, double *dinv, const int *stop, cudaStream_t s);
 // sort.cu
 int sort_launches(int K);
 int sort_max_ctas(int num_sms);
-void launch_global_rank(const unsigned long long *runs_k, const int *runs_v, int G, int me, int Kloc, int m,
-                        double *gap_partial, double *gap_out, int *m_loc, const int *stop, cudaStream_t s);
-void launch_stop_decide(const double *gaps, int G, int early_stop, int *stop, cudaStream_t s);
 // returns a cudaError_t (cooperative launch); stop_flag != nullptr: also run the elite early-stop test
 int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsigned long long *keys_b, int *order,
                     int *vals_b, int m, int early_stop, int *stop_flag, const int *stop, int max_ctas,

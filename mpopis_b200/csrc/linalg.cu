@@ -156,12 +156,8 @@ void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, do
   if (n <= 160) return (void)chol_reg_kernel<10><<<1, 256, 0, s>>>(A, n, sigma_dev, Lt, info, tag, stop);
   const int use_smem = n <= CHOL_SMEM_N;
   const size_t smem = use_smem ? sizeof(double) * n * (n | 1) : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(double) * CHOL_SMEM_N * (CHOL_SMEM_N | 1)));
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(sizeof(double) * CHOL_SMEM_N * (CHOL_SMEM_N | 1)));  // per device: set on every launch
   chol_kernel<<<1, 1024, smem, s>>>(A, n, sigma_dev, Lt, Wglobal, use_smem, info, tag, stop);
 }
 

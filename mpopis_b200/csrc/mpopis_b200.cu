@@ -5,9 +5,6 @@
 // inside: the CE/CMA early stop (POL:459-461, 567-569) is a device flag every later kernel checks,
 // Cholesky failure is a device flag read back with the result. Host <-> device traffic per step is
 // state (ss) + U (cs) in, control (as) + U (cs) + three ints out.
-#include <dlfcn.h>
-#include <nccl.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -16,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.cuh"
 #include "engine.cuh"
 
 using namespace mpopis;
@@ -38,50 +36,26 @@ int fail(int code, const char *fmt, ...) {
       return fail(MPOPIS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-// ---- NCCL through dlopen: the library has no link-time NCCL dependency (single-GPU users, and a
-// host process that already loaded its own libnccl.so.2, e.g. torch's, share that copy). ----------
-struct NcclApi {
-  void *lib = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-  const char *(*GetErrorString)(ncclResult_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  bool load() {
-    if (lib) return true;
-    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) return false;
-#define SYM(field, name) field = (decltype(field))dlsym(lib, name)
-    SYM(GetUniqueId, "ncclGetUniqueId");
-    SYM(CommInitRank, "ncclCommInitRank");
-    SYM(CommDestroy, "ncclCommDestroy");
-    SYM(AllReduce, "ncclAllReduce");
-    SYM(AllGather, "ncclAllGather");
-    SYM(GetErrorString, "ncclGetErrorString");
-    SYM(GroupStart, "ncclGroupStart");
-    SYM(GroupEnd, "ncclGroupEnd");
-#undef SYM
-    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GroupStart && GroupEnd;
-  }
-} g_nccl;
-
-#define NC(call)                                                                                          \
-  do {                                                                                                    \
-    ncclResult_t r_ = (call);                                                                             \
-    if (r_ != ncclSuccess)                                                                                \
-      return fail(MPOPIS_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
-  } while (0)
-
 template <class T>
 int dalloc(T **p, size_t n) {
   CU(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
   CU(cudaMemset(*p, 0, sizeof(T) * (n ? n : 1)));
   return 0;
 }
+
+// scratch of the parity-surface entry points: freed on every return path
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t n) { return dalloc(&p, n); }
+  operator T *() const { return p; }
+};
 
 }  // namespace
 
@@ -92,14 +66,14 @@ struct mpopis_handle {
   int dev = 0, world = 1, rank = 0;
   cudaStream_t st = nullptr, st2 = nullptr;  // main stream; side stream for the next iteration's normals
   cudaEvent_t ev_z_free = nullptr, ev_z_ready = nullptr;
-  ncclComm_t comm = nullptr;
+  Comm comm{};
   bool env_set = false, cma_set = false;
   CarEnvArgs car{};
   McEnvArgs mc{};
   double gamma = 0.0;
   uint64_t seed = 0;
   long long step = 0;
-  int rollout_variant = 3, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1;
+  int rollout_variant = 3, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1, sel_max = 1;
   bool moments_small = true;  // single-CTA moment chain for small n ("moments_small" option, A/B)
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
   bool L0_valid = false;
@@ -115,23 +89,19 @@ struct mpopis_handle {
          *d_cdf = nullptr, *d_wcnt = nullptr, *d_ws = nullptr, *d_sigma = nullptr, *d_psig = nullptr,
          *d_pSig = nullptr, *d_dw = nullptr, *d_C = nullptr, *d_ns = nullptr, *d_reward = nullptr,
          *d_ones = nullptr;
-  double *d_rq_ws = nullptr;  // work-queue rollout kernel: state scratch and [head | done[]] counters
-  int *d_rq_sync = nullptr;
-  int rollout_queue = 0, num_sms = 0;  // "rollout_queue" option: 0 off, n = persistent warps per SM
+  int num_sms = 0;
+  bool use_select = false;  // :cemppi: select.cu path (sharded, or K above the single-CTA sort)
   long long *d_env_t = nullptr, *d_warp_cycles = nullptr;  // d_warp_cycles: "rollout_profile" option
   unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
   int *d_order = nullptr, *d_vals_b = nullptr, *d_hist = nullptr, *d_counts = nullptr, *d_flags = nullptr;
   unsigned char *d_done = nullptr;
   uint4 *d_lut = nullptr;
-  unsigned long long *d_runs_k = nullptr;  // sharded :cemppi: all-gathered sorted runs
-  int *d_runs_v = nullptr, *d_mloc = nullptr;
-  double *d_gap = nullptr, *d_bvec2 = nullptr;  // d_bvec2: 1/σ_i of the sharded shrinkage
-  // peer-memory all-reduce (peer.cu)
-  bool peer_ok = false;
-  PeerMailboxes pm{};
-  void *d_mailbox = nullptr;
-  void *peer_base[64] = {};
-  unsigned long long peer_seq = 0;
+  // :cemppi selection without a sort (select.cu): workspace, bucket min/max keys, local elite ids, debug outputs
+  void *d_sel_ws = nullptr;
+  unsigned long long *d_bmin = nullptr, *d_bmax = nullptr;
+  long long nb_cap = 0;
+  int *d_eidx = nullptr, *d_mloc = nullptr;
+  double *d_tau = nullptr, *d_bvec2 = nullptr;  // d_bvec2: 1/σ_i of the :ss standardisation
   size_t part_doubles = 0;
   // d_flags: [0] stop, [1] its, [2] info
   int *stop() { return d_flags; }
@@ -202,84 +172,14 @@ bool adapts_sigma(int pol) {
 
 int allreduce_sum(mpopis_t *h, double *buf, size_t n) {
   if (h->world == 1) return 0;
-  if (h->peer_ok && (long long)n <= h->pm.capacity) {  // one-shot sum over NVLink peer memory (peer.cu)
-    launch_peer_allreduce(h->pm, buf, (int)n, ++h->peer_seq, h->info(), h->stop(), h->st);
-    h->launches += 1;
-    return 0;
-  }
-  NC(g_nccl.AllReduce(buf, buf, n, ncclFloat64, ncclSum, h->comm, h->st));
+  if (comm_allreduce_sum(h->comm, buf, n, h->st)) return fail(MPOPIS_ERR_NCCL, "all-reduce: %s", comm_error());
   return 0;
 }
-
-// Exports this rank's mailbox with CUDA IPC, exchanges the handles over the (already initialised) NCCL
-// communicator and maps every peer's mailbox. All ranks agree (all-reduce min) on whether the peer path is
-// usable; otherwise ncclAllReduce keeps being used.
-int setup_peer_mailboxes(mpopis_t *h) {
-  // Opt-in (MPOPIS_PEER_ALLREDUCE=1): at 2 GPUs the first version measured no faster than ncclAllReduce for
-  // these sizes (profiles/README.md), so NCCL stays the default until it wins.
-  const char *env = getenv("MPOPIS_PEER_ALLREDUCE");
-  int want = env && env[0] == '1';
-  const int G = h->world;
-  const long long cap = (long long)h->cs * h->cs + 256;
-  const size_t bytes = sizeof(double) * 2 * cap + 64;
-  int ok = want;
-  cudaIpcMemHandle_t mine{};
-  if (ok && cudaMalloc(&h->d_mailbox, bytes) != cudaSuccess) ok = 0;
-  if (ok && cudaMemset(h->d_mailbox, 0, bytes) != cudaSuccess) ok = 0;
-  if (ok && cudaIpcGetMemHandle(&mine, h->d_mailbox) != cudaSuccess) ok = 0;
-  cudaGetLastError();
-  // exchange handles (64 bytes each) + per-rank ok flags through NCCL
-  unsigned char *d_x = nullptr;
-  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
-  std::vector<unsigned char> host(rec * G, 0);
-  memcpy(host.data() + rec * h->rank, &mine, sizeof mine);
-  host[rec * h->rank + sizeof mine] = (unsigned char)ok;
-  CU(cudaMalloc((void **)&d_x, rec * G));
-  CU(cudaMemcpy(d_x, host.data(), rec * G, cudaMemcpyHostToDevice));
-  NC(g_nccl.AllGather(d_x + rec * h->rank, d_x, rec, ncclChar, h->comm, h->st));
-  CU(cudaStreamSynchronize(h->st));
-  CU(cudaMemcpy(host.data(), d_x, rec * G, cudaMemcpyDeviceToHost));
-  cudaFree(d_x);
-  for (int r = 0; r < G; ++r) ok = ok && host[rec * r + sizeof mine];
-  if (ok) {
-    for (int r = 0; r < G && ok; ++r) {
-      if (r == h->rank) {
-        h->peer_base[r] = h->d_mailbox;
-        continue;
-      }
-      cudaIpcMemHandle_t hd;
-      memcpy(&hd, host.data() + rec * r, sizeof hd);
-      if (cudaIpcOpenMemHandle(&h->peer_base[r], hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        h->peer_base[r] = nullptr;
-        ok = 0;
-      }
-    }
-  }
-  // second agreement round: did every rank manage to map every peer?
-  double *d_ok = nullptr;
-  double v = ok ? 1.0 : 0.0;
-  CU(cudaMalloc((void **)&d_ok, sizeof(double)));
-  CU(cudaMemcpy(d_ok, &v, sizeof v, cudaMemcpyHostToDevice));
-  NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclFloat64, ncclMin, h->comm, h->st));
-  CU(cudaStreamSynchronize(h->st));
-  CU(cudaMemcpy(&v, d_ok, sizeof v, cudaMemcpyDeviceToHost));
-  cudaFree(d_ok);
-  if (h->trace) fprintf(stderr, "[mpopis trace rank %d] peer-memory all-reduce: want=%d agreed=%d\n", h->rank, want, v >= 1.0);
-  if (v < 1.0) return 0;  // NCCL path stays in use
-  h->pm.capacity = cap, h->pm.rank = h->rank, h->pm.world = G;
-  for (int r = 0; r < G; ++r) {
-    unsigned char *base = (unsigned char *)h->peer_base[r];
-    h->pm.data[r] = (double *)base;
-    h->pm.flag[r] = (unsigned long long *)(base + sizeof(double) * 2 * cap);
-  }
-  h->pm.arrive = (unsigned int *)((unsigned char *)h->d_mailbox + sizeof(double) * 2 * cap + 16);
-  h->peer_ok = true;
-  return 0;
-}
+// in-place all-gather of the trajectory costs (8 B per sample): every rank then performs the identical selection
 int allgather_costs(mpopis_t *h) {
   if (h->world == 1) return 0;
-  NC(g_nccl.AllGather(h->d_costs + h->k0, h->d_costs, (size_t)h->Kloc, ncclFloat64, h->comm, h->st));
+  if (comm_allgather_f64(h->comm, h->d_costs, (size_t)h->Kloc, h->st))
+    return fail(MPOPIS_ERR_NCCL, "all-gather: %s", comm_error());
   return 0;
 }
 
@@ -287,10 +187,10 @@ int allgather_costs(mpopis_t *h) {
 // w: per-local-column weights or nullptr. Adds the mean to U_cur when update_U (scaled by *scale_dev).
 int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, bool want_cov, int corrected,
             int method, double ridge, bool update_U, const double *scale_dev, double *Sigma_out,
-            const int *n_dev = nullptr, bool sharded_stop = false, const int *cols = nullptr) {
+            const int *n_dev = nullptr, const int *cols = nullptr) {
   const int cs = h->cs;
   const int *stop = h->stop();
-  if (h->world == 1 && n <= MOMENTS_SMALL_MAX && cs <= 512 && !n_dev && !sharded_stop && h->moments_small) {
+  if (h->world == 1 && n <= MOMENTS_SMALL_MAX && cs <= 512 && !n_dev && h->moments_small) {
     // the reference's own problem sizes: one launch instead of eight
     launch_moments_small(X, ld, cs, n, w, cols, want_cov, corrected, method, ridge, h->d_mu, update_U ? h->d_U_cur : nullptr,
                          scale_dev, h->d_sums, h->d_Sraw, Sigma_out, h->d_lambda, stop, h->st);
@@ -298,27 +198,17 @@ int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, 
     mark(h, "moments.small");
     return 0;
   }
+  // The shrinkage estimators reach this chain only on one GPU (the sharded :cemppi update is ce_adapt below; the other
+  // policies fit with SimpleCovariance / mean_and_cov), so the shrinkage statistic needs no collective here.
   const int nch = rowsum_nchunks(n);
   const bool shrink = want_cov && (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS);
-  // Sharded shrinkage: the first all-reduce also carries Σx² so that the standardisation of the shrinkage
-  // statistic needs no collective of its own, and that statistic rides on the scatter-matrix all-reduce:
-  // 2 collectives per iteration instead of 3. d_sums = [Σx (cs) | n | per-rank stop statistics (64) | Σx² (cs)].
-  const bool fused = h->world > 1 && shrink;
-  const int width = fused ? 2 * cs + 1 : cs + 1;
-  launch_rowsum_partial(X, ld, cs, n, w, h->d_part, stop, h->st, n_dev, fused);
-  launch_reduce_partials(h->d_part, nch, cs + 1, h->d_sums, stop, h->st, width);
+  if (shrink && h->world > 1) return fail(MPOPIS_ERR_BAD_ARG, "shrinkage estimators are sharded through ce_adapt only");
+  launch_rowsum_partial(X, ld, cs, n, w, h->d_part, stop, h->st, n_dev, 0);
+  launch_reduce_partials(h->d_part, nch, cs + 1, h->d_sums, stop, h->st, cs + 1);
   h->launches += 2;
-  if (fused) {
-    launch_reduce_partials(h->d_part + cs + 1, nch, cs, h->d_sums + cs + 1 + 64, stop, h->st, width);
-    h->launches += 1;
-  }
   mark(h, "mean.local");
-  if (int rc = allreduce_sum(h, h->d_sums, cs + 1 + ((sharded_stop || fused) ? 64 : 0) + (fused ? cs : 0))) return rc;
+  if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
   mark(h, "mean.coll");
-  if (sharded_stop) {  // POL:458-461 on the all-reduced per-rank statistics, before anything is updated
-    launch_stop_decide(h->d_sums + cs + 1, h->world, h->cfg.early_stop, h->stop(), h->st);
-    h->launches += 1;
-  }
   launch_finalize_mean(h->d_sums, cs, h->d_mu, update_U ? h->d_U_cur : nullptr, scale_dev, stop, h->st);
   h->launches += 1;
   mark(h, "mean");
@@ -326,63 +216,72 @@ int moments(mpopis_t *h, const double *X, long long ld, int n, const double *w, 
   launch_syrk_partial(X, ld, cs, n, w, h->d_mu, h->d_P, stop, h->st, n_dev);
   launch_scatter_reduce(h->d_P, syrk_nchunks(n), cs, h->d_Sraw, stop, h->st);
   h->launches += 2;
-  double *qdst = h->d_q;
-  if (fused) {
-    qdst = h->d_Sraw + (size_t)cs * cs;  // travels with the scatter matrix
-    launch_dinv_from_moments(h->d_sums, h->d_sums + cs + 1 + 64, h->d_sums + cs, cs, method == MPOPIS_SIGMA_SS,
-                             h->d_bvec2, stop, h->st);
-    launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS,
-                            h->d_qpart, stop, h->st, n_dev, h->d_bvec2);
-    launch_reduce_partials(h->d_qpart, shrink_q_nblocks(n), 1, qdst, stop, h->st);
-    h->launches += 3;
-  }
   mark(h, "scatter.local");
-  if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs + (fused ? 1 : 0))) return rc;
+  if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs)) return rc;
   mark(h, "scatter.coll");
   int nq = 0;
   if (shrink) {
-    if (!fused) {
-      launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS,
-                              h->d_qpart, stop, h->st, n_dev);
-      launch_reduce_partials(h->d_qpart, shrink_q_nblocks(n), 1, h->d_q, stop, h->st);
-      h->launches += 2;
-    }
+    launch_shrink_q_partial(X, ld, cs, n, w, h->d_mu, h->d_Sraw, h->d_sums + cs, method == MPOPIS_SIGMA_SS, h->d_qpart,
+                            stop, h->st, n_dev);
+    launch_reduce_partials(h->d_qpart, shrink_q_nblocks(n), 1, h->d_q, stop, h->st);
+    h->launches += 2;
     nq = 1;
     mark(h, "shrinkq");
   }
-  launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, corrected, method, qdst, nq, ridge, Sigma_out, h->d_lambda,
-                      stop, h->st);
+  launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, corrected, method, h->d_q, nq, ridge, Sigma_out, h->d_lambda, stop,
+                      h->st);
   h->launches += 1;
   mark(h, "covfin");
   return 0;
 }
 
-// Sharded :cemppi selection (sort.cu: global_rank_kernel): local sort, all-gather of the sorted runs,
-// global positions by binary search, early-stop statistic by all-reduce(max), local elites gathered into X.
-// On return *d_mloc holds this rank's elite count (a prefix of its sorted run).
-int sharded_ce_select(mpopis_t *h, int m) {
-  const int Kloc = h->Kloc, cs = h->cs;
+// The cross-entropy adaptation (POL:455-465) without a sort (select.cu): exact radix select of the m-th smallest
+// (cost, sample id) on the (all-gathered) cost vector, the early-stop test on bucketed elite costs, the ids of the
+// elites THIS shard owns, then mean / covariance of those columns. Sharded: every rank selects redundantly on identical
+// input (no collective beyond the cost all-gather), the moments need two all-reduces:
+//   [Σx | n | Σx²] (2cs + 1)  and  [scatter matrix | shrinkage statistic] (cs² + 1).
+int ce_adapt(mpopis_t *h) {
+  const int cs = h->cs, K = h->K, Kloc = h->Kloc, m = h->m_elite, method = h->cfg.sigma_est;
   int *stop = h->stop();
   cudaStream_t st = h->st;
-  const cudaError_t e = (cudaError_t)launch_sortperm(h->d_costs + h->k0, Kloc, h->d_keys_a, h->d_keys_b, h->d_order,
-                                                     h->d_vals_b, 0, 0, nullptr, stop, h->sort_max, st);
+  const cudaError_t e = (cudaError_t)launch_ce_select(h->d_costs, K, m, h->k0, Kloc, h->cfg.early_stop, h->d_sel_ws,
+                                                      h->d_bmin, h->d_bmax, h->nb_cap, h->d_eidx, h->d_mloc, h->d_tau,
+                                                      stop, stop, h->sel_max, st);
   if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
-  mark(h, "sel.sort");
-  NC(g_nccl.GroupStart());  // one fused NCCL launch for keys + indices
-  NC(g_nccl.AllGather(h->d_keys_a, h->d_runs_k, (size_t)Kloc, ncclUint64, h->comm, st));
-  NC(g_nccl.AllGather(h->d_order, h->d_runs_v, (size_t)Kloc, ncclInt32, h->comm, st));
-  NC(g_nccl.GroupEnd());
-  mark(h, "sel.allgather");
-  CU(cudaMemsetAsync(h->d_mloc, 0, sizeof(int), st));
-  // this rank's early-stop statistic goes into slot `rank` of the (zeroed) tail of d_sums and rides on the
-  // all-reduce(sum) of the elite row sums (moments()): one collective less per iteration
-  CU(cudaMemsetAsync(h->d_sums + cs + 1, 0, sizeof(double) * h->world, st));
-  launch_global_rank(h->d_runs_k, h->d_runs_v, h->world, h->rank, Kloc, m, h->d_qpart, h->d_sums + cs + 1 + h->rank,
-                     h->d_mloc, stop, st);
-  mark(h, "sel.rank");
-  const int mmax = m < Kloc ? m : Kloc;
-  launch_gather_cols(h->d_E, h->ldk, cs, h->d_order, mmax, 0, Kloc, h->d_X, h->ldm, nullptr, stop, st, h->d_mloc);
-  h->launches += sort_launches(Kloc) + 4;
+  mark(h, "select");
+  const int mmax = m < Kloc ? m : Kloc, nch = elite_gather_nchunks(mmax);
+  const bool shrink = method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS, ss = method == MPOPIS_SIGMA_SS;
+  launch_elite_gather_sums(h->d_E, h->ldk, cs, h->d_eidx, h->d_mloc, mmax, h->d_X, h->ldm, h->d_part, stop, st);
+  h->launches += 2;
+  if (h->world == 1) {
+    launch_ce_sums(h->d_part, nch, cs, h->d_mloc, h->d_sums, 1, ss, h->d_mu, h->d_U_cur, h->d_bvec2, stop, st);
+    h->launches += 1;
+  } else {
+    launch_ce_sums(h->d_part, nch, cs, h->d_mloc, h->d_sums, 0, ss, h->d_mu, h->d_U_cur, h->d_bvec2, stop, st);
+    mark(h, "mean.local");
+    if (int rc = allreduce_sum(h, h->d_sums, 2 * (size_t)cs + 1)) return rc;
+    mark(h, "mean.coll");
+    launch_ce_sums(nullptr, 0, cs, h->d_mloc, h->d_sums, 1, ss, h->d_mu, h->d_U_cur, h->d_bvec2, stop, st);
+    h->launches += 2;
+  }
+  mark(h, "mean");
+  launch_syrk_partial(h->d_X, h->ldm, cs, mmax, nullptr, h->d_mu, h->d_P, stop, st, h->d_mloc);
+  launch_scatter_reduce(h->d_P, syrk_nchunks(mmax), cs, h->d_Sraw, stop, st);
+  h->launches += 2;
+  double *qdst = h->d_Sraw + (size_t)cs * cs;  // travels with the scatter matrix
+  if (shrink) {
+    launch_shrink_q_partial(h->d_X, h->ldm, cs, mmax, nullptr, h->d_mu, h->d_Sraw, h->d_sums + cs, ss, h->d_qpart, stop,
+                            st, h->d_mloc, h->d_bvec2);
+    launch_reduce_partials(h->d_qpart, shrink_q_nblocks(mmax), 1, qdst, stop, st);
+    h->launches += 2;
+  }
+  mark(h, "scatter.local");
+  if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs + (shrink ? 1 : 0))) return rc;
+  mark(h, "scatter.coll");
+  launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, 0, method, qdst, shrink ? 1 : 0, 10e-9, h->d_Sigma, h->d_lambda,
+                      stop, st);
+  h->launches += 1;
+  mark(h, "covfin");
   return 0;
 }
 
@@ -443,20 +342,8 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
   a.K = h->Kloc, a.T = h->T;
   a.warp_cycles = h->d_warp_cycles;
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING) {
-    bool queued = false;
-    // work queue: only when the rollouts are more than the persistent grid holds at once (otherwise every warp has
-    // exactly one batch and the plain kernel is the same thing without the bookkeeping)
-    if (h->rollout_queue > 0 && h->rollout_variant == 3 && h->cfg.n_cars == 1 && h->d_rq_ws &&
-        (h->Kloc + 31) / 32 > h->rollout_queue * h->num_sms) {
-      a.ws = h->d_rq_ws, a.ws_sync = h->d_rq_sync;
-      a.unit_len = h->T >= 20 ? 10 : (h->T + 1) / 2;
-      a.queue_ctas = h->rollout_queue * h->num_sms * 32 / h->rollout_block;
-      queued = launch_rollout_car_queue(h->car, a, h->rollout_block, h->stop(), h->st) != 0;
-    }
-    if (!queued)
-      launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->rollout_stage, h->stop(), h->st);
-  }
-  else
+    launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->rollout_stage, h->stop(), h->st);
+  } else
     launch_rollout_mc(h->mc, a, h->rollout_block, h->stop(), h->st);
   h->launches += 1;
   CU(cudaGetLastError());
@@ -543,9 +430,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
                             h->st2);
       CU(cudaEventRecord(h->ev_z_ready, h->st2));
     }
-    const bool local_select = h->world > 1 && pol == MPOPIS_POLICY_CEMPPI;  // no global cost vector needed
-    if (!local_select)
-      if (int rc = allgather_costs(h)) return rc;
+    if (int rc = allgather_costs(h)) return rc;
     if (n == N - 1) break;
     mark(h, "rollout+gather");
     // --- adaptation (the `if n < N` blocks) ---
@@ -575,12 +460,8 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       case MPOPIS_POLICY_CEMPPI:
       case MPOPIS_POLICY_CMAMPPI: {  // POL:455-465, 563-599
         const int m = h->m_elite;
-        if (h->world > 1 && pol == MPOPIS_POLICY_CEMPPI) {
-          if (int rc = sharded_ce_select(h, m)) return rc;
-          mark(h, "select");
-          if (int rc = moments(h, h->d_X, h->ldm, m < Kloc ? m : Kloc, nullptr, true, 0, h->cfg.sigma_est, 10e-9, true,
-                               nullptr, h->d_Sigma, h->d_mloc, true))
-            return rc;
+        if (pol == MPOPIS_POLICY_CEMPPI && h->use_select) {  // selection instead of a sort (select.cu)
+          if (int rc = ce_adapt(h)) return rc;
           break;
         }
         {  // order = sortperm(costs) + the elite early-stop test (POL:455-461, 563-569)
@@ -594,7 +475,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
           // small elite set: the single-CTA moment kernel reads the elite columns through `order` (no gather)
           mark(h, "select");
           if (int rc = moments(h, h->d_E, h->ldk, m, nullptr, true, 0, h->cfg.sigma_est, 10e-9, true, nullptr, h->d_Sigma,
-                               nullptr, false, h->d_order))
+                               nullptr, h->d_order))
             return rc;
           break;
         }
@@ -615,15 +496,14 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     }
   }
   h->last_its_launched = N;
-  if (h->world > 1 && pol == MPOPIS_POLICY_CEMPPI)  // costs of the last executed iteration, for the final weights
-    if (int rc = allgather_costs(h)) return rc;
   // --- final weights (always λ: POL:313,367,470,604,665,736,811), weighted noise, control, roll ---
   h->launches += launch_weights(h->d_costs, K, h->cfg.lambda, h->d_w, h->d_ones, nullptr, st);
   launch_rowsum_partial(h->d_E, h->ldk, cs, Kloc, h->d_w + h->k0, h->d_part, nullptr, st);
   launch_reduce_partials(h->d_part, rowsum_nchunks(Kloc), cs + 1, h->d_sums, nullptr, st);
   h->launches += 2;
   if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
-  launch_finalize_control(h->d_sums, h->d_U_orig, h->d_U_cur, cs, h->as, h->T, h->d_U_next, h->d_control, st);
+  launch_finalize_control(h->d_sums, h->d_U_orig, h->d_U_cur, cs, h->as, h->T, h->d_U_next, h->d_control,
+                          h->cfg.env == MPOPIS_ENV_EXTERNAL ? h->d_ext_bounds : nullptr, st);
   h->launches += 1;
   mark(h, "final");
   CU(cudaEventRecord(h->ev[1], st));
@@ -649,7 +529,6 @@ int finish_timing(mpopis_t *h) {
 }
 
 int check_info(mpopis_t *h, int info) {
-  if (info == 3000) return fail(MPOPIS_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank");
   if (info != 0)
     return fail(MPOPIS_ERR_NOT_PD, "PosDefException: matrix is not positive definite; Cholesky factorization failed (%s)",
                 info >= 1000 ? "initial Σ" : (std::string("AIS iteration ") + std::to_string(info)).c_str());
@@ -776,6 +655,9 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   if (cfg->num_samples < 1 || cfg->horizon < 1 || cfg->opt_its < 1 || cfg->num_samples > (1LL << 30))
     return fail(MPOPIS_ERR_BAD_ARG, "num_samples, horizon and opt_its must be positive");
   if (!(cfg->lambda > 0.0)) return fail(MPOPIS_ERR_BAD_ARG, "λ must be positive");
+  if ((cfg->policy == MPOPIS_POLICY_MUAISMPPI || cfg->policy == MPOPIS_POLICY_MUSIGMAAISMPPI ||
+       cfg->policy == MPOPIS_POLICY_PMCMPPI) && cfg->opt_its > 1 && !(cfg->lambda_ais > 0.0))
+    return fail(MPOPIS_ERR_BAD_ARG, "λ_ais must be positive (it divides the costs of the AIS weights, POL:660,730,803)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(MPOPIS_ERR_NO_DEVICE, "no CUDA device visible: the engine has no CPU fallback");
@@ -793,6 +675,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   mpopis_t *h = new mpopis_handle();
   h->cfg = *cfg;
   h->dev = cfg->device, h->world = world, h->rank = cfg->rank;
+  h->comm.world = world, h->comm.rank = cfg->rank;
   h->K = (int)cfg->num_samples, h->T = (int)cfg->horizon;
   h->N = (cfg->policy == MPOPIS_POLICY_MPPI || cfg->policy == MPOPIS_POLICY_GMPPI) ? 1 : (int)cfg->opt_its;
   if (cfg->env == MPOPIS_ENV_CAR_RACING) {
@@ -887,10 +770,26 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_qpart, (size_t)shrink_q_nblocks((int)nmax) + 1));
   if (cfg->policy == MPOPIS_POLICY_CEMPPI) TRY(ensure_elite_capacity(h, h->m_elite));
   TRY(dalloc(&h->d_mloc, 1));
-  TRY(dalloc(&h->d_gap, 1));
-  if (cfg->policy == MPOPIS_POLICY_CEMPPI && world > 1) {
-    TRY(dalloc(&h->d_runs_k, K));
-    TRY(dalloc(&h->d_runs_v, K));
+  // :cemppi selects its elites without a sort whenever the policy is sharded or K exceeds the single-CTA sort
+  // (K <= 2048 on one GPU keeps small_sort_kernel + the single-CTA moment chain: one launch each)
+  h->use_select = cfg->policy == MPOPIS_POLICY_CEMPPI && h->N > 1 && (world > 1 || h->K > 2048);
+  if (const char *e = getenv("MPOPIS_CE_SELECT")) h->use_select = h->use_select && atoi(e) != 0;  // 0: round-1 sort path (1 GPU)
+  if (world > 1 && cfg->policy == MPOPIS_POLICY_CEMPPI && h->N > 1) h->use_select = true;
+  if (cfg->policy == MPOPIS_POLICY_CEMPPI && h->N > 1) {
+    const size_t mmax = (size_t)std::min(h->m_elite, h->Kloc);
+    h->nb_cap = select_bucket_capacity(h->m_elite);
+    if (cudaMalloc(&h->d_sel_ws, SELECT_WS_BYTES) != cudaSuccess) return bail(fail(MPOPIS_ERR_CUDA, "cudaMalloc failed"));
+    TRY(dalloc(&h->d_bmin, (size_t)h->nb_cap));
+    TRY(dalloc(&h->d_bmax, (size_t)h->nb_cap));
+    TRY(dalloc(&h->d_eidx, mmax));
+    TRY(dalloc(&h->d_tau, 4));
+    launch_select_init(h->d_sel_ws, h->d_bmin, h->d_bmax, h->nb_cap, h->st);
+    const size_t need = (size_t)elite_gather_nchunks((int)mmax) * 2 * cs + 2 * cs + 2;
+    if (need > h->part_doubles) {
+      cudaFree(h->d_part);
+      h->d_part = nullptr, h->part_doubles = need;
+      TRY(dalloc(&h->d_part, need));
+    }
   }
   if (cfg->policy == MPOPIS_POLICY_PMCMPPI || cfg->policy == MPOPIS_POLICY_CMAMPPI) {
     TRY(dalloc(&h->d_u, K));
@@ -926,6 +825,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   h->num_sms = prop.multiProcessorCount;
   h->coop_max = inv_sqrt_max_ctas(prop.multiProcessorCount);
   h->sort_max = sort_max_ctas(prop.multiProcessorCount);
+  h->sel_max = select_max_ctas(prop.multiProcessorCount);
   {  // Σ defaults to the identity until set_sigma()
     std::vector<double> I(cs * cs, 0.0);
     for (size_t i = 0; i < cs; ++i) I[i * cs + i] = 1.0;
@@ -941,10 +841,7 @@ int mpopis_b200_destroy(mpopis_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->dev);
   if (h->st) cudaStreamSynchronize(h->st);
-  for (int r = 0; r < 64; ++r)
-    if (h->peer_base[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_base[r]);
-  if (h->d_mailbox) cudaFree(h->d_mailbox);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  comm_destroy(h->comm);
   void *ptrs[] = {h->d_trk,    h->d_state, h->d_U_orig, h->d_U_cur,  h->d_U_next, h->d_control, h->d_Sigma0,
                   h->d_Sigma,  h->d_Lt,    h->d_Lt0,    h->d_cholW,  h->d_bvec,   h->d_Z,       h->d_E,
                   h->d_stage,  h->d_costs, h->d_w,      h->d_sorted, h->d_X,      h->d_mask,    h->d_part,
@@ -952,13 +849,11 @@ int mpopis_b200_destroy(mpopis_t *h) {
                   h->d_traj,   h->d_u,     h->d_cdf,    h->d_wcnt,   h->d_ws,     h->d_sigma,   h->d_psig,
                   h->d_pSig,   h->d_C,     h->d_ns,     h->d_reward, h->d_env_t,  h->d_keys_a,  h->d_keys_b,
                   h->d_order,  h->d_vals_b, h->d_hist,  h->d_counts, h->d_flags,  h->d_done,   h->d_lut,
-                  h->d_ones,   h->d_runs_k, h->d_runs_v, h->d_mloc,  h->d_gap,
-                  h->d_bvec2};
+                  h->d_ones,   h->d_mloc,   h->d_bvec2,  h->d_sel_ws, h->d_bmin,  h->d_bmax,    h->d_eidx,
+                  h->d_tau};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->d_warp_cycles) cudaFree(h->d_warp_cycles);
-  if (h->d_rq_ws) cudaFree(h->d_rq_ws);
-  if (h->d_rq_sync) cudaFree(h->d_rq_sync);
   if (h->h_ext_controls) cudaFreeHost(h->h_ext_controls);
   if (h->h_ext_costs) cudaFreeHost(h->h_ext_costs);
   if (h->h_ext_stop) cudaFreeHost(h->h_ext_stop);
@@ -981,23 +876,40 @@ int mpopis_b200_destroy(mpopis_t *h) {
 
 int mpopis_b200_comm_id(void *out128) {
   if (!out128) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
-  if (!g_nccl.load()) return fail(MPOPIS_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
-  ncclUniqueId id;
-  NC(g_nccl.GetUniqueId(&id));
-  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-  memcpy(out128, &id, 128);
+  if (comm_unique_id(out128)) return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
   return 0;
 }
 
 int mpopis_b200_comm_init(mpopis_t *h, const void *id128) {
   if (!h || !id128) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (h->world == 1) return 0;
-  if (!g_nccl.load()) return fail(MPOPIS_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+  if (h->comm.nccl || h->comm.loop) return fail(MPOPIS_ERR_BAD_ARG, "communicator already initialised");
   if (int rc = set_device(h)) return rc;
-  ncclUniqueId id;
-  memcpy(&id, id128, 128);
-  NC(g_nccl.CommInitRank(&h->comm, h->world, id, h->rank));
-  return setup_peer_mailboxes(h);
+  if (comm_init_nccl(h->comm, id128)) return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
+  return 0;
+}
+
+// Loop-back group: `world` virtual ranks on ONE device in ONE process, each handle driven from its own host thread
+// (comm.cu). Verification of the sharded path on a single-GPU box; the production communicator is NCCL.
+int mpopis_b200_loopback_create(int32_t world, void **group_out) {
+  if (!group_out || world < 1 || world > COMM_MAX_WORLD) return fail(MPOPIS_ERR_BAD_ARG, "world must be 1..%d", COMM_MAX_WORLD);
+  *group_out = loop_group_create(world);
+  return *group_out ? 0 : fail(MPOPIS_ERR_BAD_ARG, "cannot create the loop-back group");
+}
+
+int mpopis_b200_loopback_destroy(void *group) {
+  loop_group_destroy((LoopGroup *)group);
+  return 0;
+}
+
+int mpopis_b200_comm_init_loopback(mpopis_t *h, void *group) {
+  if (!h || !group) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->world == 1) return 0;
+  if (h->comm.nccl || h->comm.loop) return fail(MPOPIS_ERR_BAD_ARG, "communicator already initialised");
+  if (int rc = set_device(h)) return rc;
+  const size_t cap = std::max((size_t)h->cs * h->cs + 64, (size_t)h->K) + 2 * (size_t)h->cs + 128;
+  if (comm_init_loopback(h->comm, (LoopGroup *)group, h->dev, cap)) return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
+  return 0;
 }
 
 int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params, double dt, double ddt,
@@ -1100,16 +1012,6 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
       return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1, 2 or 3");
     h->rollout_variant = (int)value;
-  }
-  else if (!strcmp(key, "rollout_queue")) {  // persistent warps per SM of the work-queue rollout kernel (0 = off)
-    const int n = (int)value;
-    if (n < 0 || n > 16 || (n * 32) % h->rollout_block) return fail(MPOPIS_ERR_BAD_ARG, "rollout_queue must be 0..16 warps per SM, a multiple of the CTA's warps");
-    if (n > 0 && !h->d_rq_ws && rollout_queue_fields(h->cfg.env == MPOPIS_ENV_CAR_RACING ? h->cfg.n_cars : 0) > 0) {
-      const size_t nb = ((size_t)h->Kloc + 31) / 32;
-      if (int rc = dalloc(&h->d_rq_ws, nb * 32 * (size_t)rollout_queue_fields(h->cfg.n_cars))) return rc;
-      if (int rc = dalloc(&h->d_rq_sync, nb + 1)) return rc;
-    }
-    h->rollout_queue = n;
   }
   else if (!strcmp(key, "rollout_profile")) {  // per-warp clock64() of the rollout kernel, read with warp_cycles()
     if (value != 0.0 && !h->d_warp_cycles) {
@@ -1251,30 +1153,27 @@ int mpopis_b200_rollout_costs(mpopis_t *h, const double *state, int64_t env_t, c
 int mpopis_b200_weights(mpopis_t *h, const double *costs, int64_t K, double lambda, double *w_out) {
   if (!h || !costs || !w_out || K < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (int rc = set_device(h)) return rc;
-  double *dc = nullptr, *dw = nullptr;
-  if (int rc = dalloc(&dc, (size_t)K)) return rc;
-  if (int rc = dalloc(&dw, (size_t)K)) return rc;
+  DevBuf<double> dc, dw;  // freed on every return path
+  if (int rc = dc.alloc((size_t)K)) return rc;
+  if (int rc = dw.alloc((size_t)K)) return rc;
   CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
   h->launches += launch_weights(dc, (int)K, lambda, dw, h->d_ones, nullptr, h->st);
   CU(cudaMemcpyAsync(w_out, dw, sizeof(double) * K, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
-  cudaFree(dc), cudaFree(dw);
   return 0;
 }
 
 int mpopis_b200_sortperm(mpopis_t *h, const double *costs, int64_t K, int64_t *perm_out) {
   if (!h || !costs || !perm_out || K < 1 || K > (1LL << 30)) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (int rc = set_device(h)) return rc;
-  double *dc = nullptr, *ds = nullptr;
-  unsigned long long *ka = nullptr, *kb = nullptr;
-  int *ord = nullptr, *vb = nullptr, *hist = nullptr;
-  if (int rc = dalloc(&dc, (size_t)K)) return rc;
-  if (int rc = dalloc(&ds, (size_t)K)) return rc;
-  if (int rc = dalloc(&ka, (size_t)K)) return rc;
-  if (int rc = dalloc(&kb, (size_t)K)) return rc;
-  if (int rc = dalloc(&ord, (size_t)K)) return rc;
-  if (int rc = dalloc(&vb, (size_t)K)) return rc;
-  if (int rc = dalloc(&hist, 1)) return rc;
+  DevBuf<double> dc;
+  DevBuf<unsigned long long> ka, kb;
+  DevBuf<int> ord, vb;
+  if (int rc = dc.alloc((size_t)K)) return rc;
+  if (int rc = ka.alloc((size_t)K)) return rc;
+  if (int rc = kb.alloc((size_t)K)) return rc;
+  if (int rc = ord.alloc((size_t)K)) return rc;
+  if (int rc = vb.alloc((size_t)K)) return rc;
   CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
   {
     const cudaError_t e = (cudaError_t)launch_sortperm(dc, (int)K, ka, kb, ord, vb, 0, 0, nullptr, nullptr, h->sort_max,
@@ -1287,7 +1186,50 @@ int mpopis_b200_sortperm(mpopis_t *h, const double *costs, int64_t K, int64_t *p
   CU(cudaStreamSynchronize(h->st));
   CU(cudaGetLastError());
   for (int64_t i = 0; i < K; ++i) perm_out[i] = tmp[(size_t)i];
-  cudaFree(dc), cudaFree(ds), cudaFree(ka), cudaFree(kb), cudaFree(ord), cudaFree(vb), cudaFree(hist);
+  return 0;
+}
+
+// Parity surface of select.cu: the elite set order[1:m] of sortperm(costs) (returned as ascending sample ids) and the
+// early-stop decision of POL:458-461, computed WITHOUT a sort. [k0, k0 + kloc) emulates the shard ownership window.
+int mpopis_b200_elite_select(mpopis_t *h, const double *costs, int64_t K, int64_t m, int64_t k0, int64_t kloc,
+                             int32_t early_stop, int64_t *elite_ids_out, int64_t *n_out, int32_t *stop_out,
+                             double *tau_out4) {
+  if (!h || !costs || !elite_ids_out || !n_out || !stop_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (K < 1 || K > (1LL << 30) || m < 1 || m > K || k0 < 0 || kloc < 1 || k0 + kloc > K)
+    return fail(MPOPIS_ERR_BAD_ARG, "bad sizes");
+  if (int rc = set_device(h)) return rc;
+  DevBuf<double> dc, dtau;
+  DevBuf<unsigned long long> bmin, bmax;
+  DevBuf<int> eidx, misc;
+  DevBuf<unsigned char> ws;
+  const long long cap = select_bucket_capacity((int)m);
+  const size_t mmax = (size_t)std::min(m, kloc);
+  if (int rc = dc.alloc((size_t)K)) return rc;
+  if (int rc = dtau.alloc(4)) return rc;
+  if (int rc = bmin.alloc((size_t)cap)) return rc;
+  if (int rc = bmax.alloc((size_t)cap)) return rc;
+  if (int rc = eidx.alloc(mmax)) return rc;
+  if (int rc = misc.alloc(2)) return rc;  // [m_loc, stop]
+  if (int rc = ws.alloc(SELECT_WS_BYTES)) return rc;
+  CU(cudaMemcpyAsync(dc, costs, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
+  launch_select_init(ws.p, bmin, bmax, cap, h->st);
+  for (int rep = 0; rep < 2; ++rep) {  // twice: the second run starts from the workspace the first one left behind
+    CU(cudaMemsetAsync(misc, 0, sizeof(int) * 2, h->st));
+    const cudaError_t e = (cudaError_t)launch_ce_select(dc, (int)K, (int)m, k0, (int)kloc, early_stop, ws.p, bmin, bmax, cap,
+                                                        eidx, misc.p, dtau, misc.p + 1, nullptr, h->sel_max, h->st);
+    if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  }
+  h->launches += 3;
+  int hm[2] = {0, 0};
+  CU(cudaMemcpyAsync(hm, misc, sizeof hm, cudaMemcpyDeviceToHost, h->st));
+  if (tau_out4) CU(cudaMemcpyAsync(tau_out4, dtau, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+  if (hm[0] < 0 || (size_t)hm[0] > mmax) return fail(MPOPIS_ERR_CUDA, "selection returned %d local elites", hm[0]);
+  std::vector<int> tmp((size_t)hm[0] + 1);
+  CU(cudaMemcpy(tmp.data(), eidx, sizeof(int) * (size_t)hm[0], cudaMemcpyDeviceToHost));
+  for (int i = 0; i < hm[0]; ++i) elite_ids_out[i] = tmp[(size_t)i] + k0;
+  *n_out = hm[0], *stop_out = hm[1];
   return 0;
 }
 
@@ -1296,14 +1238,14 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
   if (!h || !pos || n < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (!h->env_set || h->cfg.env != MPOPIS_ENV_CAR_RACING) return fail(MPOPIS_ERR_BAD_ARG, "car env not set");
   if (int rc = set_device(h)) return rc;
-  double *dp = nullptr, *dd = nullptr;
-  int *di = nullptr, *dj = nullptr;
-  unsigned char *dw = nullptr;
-  if (int rc = dalloc(&dp, 2 * (size_t)n)) return rc;
-  if (int rc = dalloc(&dd, (size_t)n)) return rc;
-  if (int rc = dalloc(&di, (size_t)n)) return rc;
-  if (int rc = dalloc(&dj, (size_t)n)) return rc;
-  if (int rc = dalloc(&dw, (size_t)n)) return rc;
+  DevBuf<double> dp, dd;
+  DevBuf<int> di, dj;
+  DevBuf<unsigned char> dw;
+  if (int rc = dp.alloc(2 * (size_t)n)) return rc;
+  if (int rc = dd.alloc((size_t)n)) return rc;
+  if (int rc = di.alloc((size_t)n)) return rc;
+  if (int rc = dj.alloc((size_t)n)) return rc;
+  if (int rc = dw.alloc((size_t)n)) return rc;
   CU(cudaMemcpyAsync(dp, pos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->st));
   launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->rollout_variant == 0 || h->rollout_variant == 3, h->st);
   h->launches += 1;
@@ -1313,7 +1255,6 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
   if (within_out) CU(cudaMemcpyAsync(within_out, dw, n, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   CU(cudaGetLastError());
-  cudaFree(dp), cudaFree(dd), cudaFree(di), cudaFree(dj), cudaFree(dw);
   return 0;
 }
 
@@ -1388,14 +1329,14 @@ int mpopis_b200_cov_estimate(mpopis_t *h, int32_t sigma_est, const double *X, in
   if (h->world != 1) return fail(MPOPIS_ERR_BAD_ARG, "cov_estimate is a single-shard parity surface");
   if (int rc = set_device(h)) return rc;
   const long long ld = ((long long)n + 31) / 32 * 32;
-  double *dcm = nullptr, *dX = nullptr, *dw = nullptr, *dS = nullptr;
-  if (int rc = dalloc(&dcm, (size_t)p * n)) return rc;
-  if (int rc = dalloc(&dX, (size_t)p * ld)) return rc;
-  if (int rc = dalloc(&dS, (size_t)p * p)) return rc;
+  DevBuf<double> dcm, dX, dw, dS;
+  if (int rc = dcm.alloc((size_t)p * n)) return rc;
+  if (int rc = dX.alloc((size_t)p * ld)) return rc;
+  if (int rc = dS.alloc((size_t)p * p)) return rc;
   CU(cudaMemcpyAsync(dcm, X, sizeof(double) * p * n, cudaMemcpyHostToDevice, h->st));
   launch_transpose_in(dcm, dX, (int)p, (int)n, ld, h->st);
   if (w) {
-    if (int rc = dalloc(&dw, (size_t)n)) return rc;
+    if (int rc = dw.alloc((size_t)n)) return rc;
     CU(cudaMemcpyAsync(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
   }
   CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3, h->st));
@@ -1405,8 +1346,6 @@ int mpopis_b200_cov_estimate(mpopis_t *h, int32_t sigma_est, const double *X, in
   if (cov_out) CU(cudaMemcpyAsync(cov_out, dS, sizeof(double) * p * p, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   CU(cudaGetLastError());
-  cudaFree(dcm), cudaFree(dX), cudaFree(dS);
-  if (dw) cudaFree(dw);
   return 0;
 }
 
@@ -1430,13 +1369,14 @@ int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out) {
 int mpopis_b200_cholesky(mpopis_t *h, const double *A, int64_t n, double *L_out) {
   if (!h || !A || !L_out || n < 1 || n > 4096) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (int rc = set_device(h)) return rc;
-  double *dA = nullptr, *dLt = nullptr, *dW = nullptr;
-  int *dinfo = nullptr, info = 0;
+  DevBuf<double> dA, dLt, dW;
+  DevBuf<int> dinfo;
+  int info = 0;
   const size_t nn = (size_t)n * n;
-  if (int rc = dalloc(&dA, nn)) return rc;
-  if (int rc = dalloc(&dLt, nn)) return rc;
-  if (int rc = dalloc(&dW, nn + (size_t)n)) return rc;
-  if (int rc = dalloc(&dinfo, 1)) return rc;
+  if (int rc = dA.alloc(nn)) return rc;
+  if (int rc = dLt.alloc(nn)) return rc;
+  if (int rc = dW.alloc(nn + (size_t)n)) return rc;
+  if (int rc = dinfo.alloc(1)) return rc;
   CU(cudaMemcpyAsync(dA, A, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
   launch_chol(dA, (int)n, nullptr, dLt, dW, dinfo, 1, nullptr, h->st);
   launch_transpose_sq(dLt, dA, (int)n, h->st);  // row-major L -> column-major L
@@ -1445,7 +1385,6 @@ int mpopis_b200_cholesky(mpopis_t *h, const double *A, int64_t n, double *L_out)
   CU(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   CU(cudaGetLastError());
-  cudaFree(dA), cudaFree(dLt), cudaFree(dW), cudaFree(dinfo);
   if (info) return fail(MPOPIS_ERR_NOT_PD, "PosDefException: matrix is not positive definite; Cholesky factorization failed.");
   return 0;
 }
@@ -1453,13 +1392,14 @@ int mpopis_b200_cholesky(mpopis_t *h, const double *A, int64_t n, double *L_out)
 int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out) {
   if (!h || !A || !C_out || n < 1 || n > 4096) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (int rc = set_device(h)) return rc;
-  double *dA = nullptr, *dC = nullptr, *dws = nullptr;
-  int *dinfo = nullptr, info = 0;
+  DevBuf<double> dA, dC, dws;
+  DevBuf<int> dinfo;
+  int info = 0;
   const size_t nn = (size_t)n * n;
-  if (int rc = dalloc(&dA, nn)) return rc;
-  if (int rc = dalloc(&dC, nn)) return rc;
-  if (int rc = dalloc(&dws, 5 * nn + 8)) return rc;
-  if (int rc = dalloc(&dinfo, 1)) return rc;
+  if (int rc = dA.alloc(nn)) return rc;
+  if (int rc = dC.alloc(nn)) return rc;
+  if (int rc = dws.alloc(5 * nn + 8)) return rc;
+  if (int rc = dinfo.alloc(1)) return rc;
   CU(cudaMemcpyAsync(dA, A, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
   cudaError_t e = (cudaError_t)launch_inv_sqrt(dA, (int)n, dC, dws, dinfo, 1, nullptr, h->coop_max, h->st);
   if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
@@ -1468,7 +1408,6 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
   CU(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   CU(cudaGetLastError());
-  cudaFree(dA), cudaFree(dC), cudaFree(dws), cudaFree(dinfo);
   if (info) return fail(MPOPIS_ERR_NOT_PD, "Σ^-0.5: matrix is not positive definite");
   return 0;
 }
@@ -1504,8 +1443,8 @@ int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, h->dev));
   const int grid = prop.multiProcessorCount * 8;  // 2048 threads / SM
-  double *out = nullptr;
-  if (int rc = dalloc(&out, (size_t)grid * 256)) return rc;
+  DevBuf<double> out;
+  if (int rc = out.alloc((size_t)grid * 256)) return rc;
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
@@ -1522,7 +1461,7 @@ int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out) {
     if (rate > best) best = rate;
   }
   h->launches += 6;
-  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(out);
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
   *dfma_per_s_out = best;
   return 0;
 }

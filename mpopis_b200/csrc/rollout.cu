@@ -33,120 +33,6 @@
 
 namespace mpopis {
 
-// ---- work-queue variant ------------------------------------------------------------------------------------------
-// tools/warp_cycles.py (clock64 per warp) shows what bounds a launch at K = 65 536: 2048 warps over 592 sub-partitions
-// is 3.46 per scheduler, i.e. {4,4,3,3} per SM; the warp scheduler favours the OLDER warps, so on every SM the two
-// warps of the last-placed CTA run at what is left and then alone — per-warp cycles: median 377 k, but 13.3 % of the
-// warps (exactly 2 x 136 SMs) need 505 k, and they are the kernel's duration (540 k). The work does not come in units
-// that divide evenly, so this kernel makes the units smaller and hands them out dynamically: a persistent grid of
-// 3 warps per scheduler pulls (batch of 32 rollouts, unit of `unit_len` control steps) pairs from an atomic counter in
-// unit-major order; the rollout state (s, cost, control cost, carried sin/cos) travels through a scratch buffer between
-// units (L2-resident, 15 doubles per rollout per unit), the successor unit spins on a per-batch counter published with
-// release/acquire. Whoever finishes early takes the next unit of ANY batch, so all batches advance at the same rate.
-// A unit's predecessor was handed out earlier to a warp that is running, so the spin cannot deadlock whatever the
-// residency.
-__device__ __forceinline__ int ld_acquire(const int *p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int *p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <int NCARS, int MODE>
-__global__ void __launch_bounds__(128, NCARS == 1 ? 4 : 1) rollout_car_queue_kernel(const __grid_constant__ CarEnvArgs env,
-                                                                const __grid_constant__ RolloutArgs a,
-                                                                const int *stop) {
-  extern __shared__ double smem[];
-  constexpr int AS = 2 * NCARS, SS = 8 * NCARS, NF = SS + 3 + 4 * NCARS;  // s | cost | cc | trig_valid | trig
-  if (stop && *stop) return;
-  const long long t_begin = a.warp_cycles ? clock64() : 0;
-  const TrackView tr = stage_track(env, smem);
-  const int lane = threadIdx.x & 31;
-  const int nb = (a.K + 31) >> 5, nu = (a.T + a.unit_len - 1) / a.unit_len;
-  const int total = nb * nu;
-  int *head = a.ws_sync, *done = a.ws_sync + 1;
-  for (;;) {
-    int i = 0;
-    if (lane == 0) i = atomicAdd(head, 1);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= total) break;
-    const int u = i / nb, b = i - u * nb;
-    const int k = b * 32 + lane;
-    double *wsb = a.ws + (size_t)b * NF * 32 + lane;  // field f of this lane at wsb[f * 32]
-    double s[SS], cost = 0.0, cc = 0.0, trig[4 * NCARS];
-    bool trig_valid = false;
-    if (u == 0) {
-#pragma unroll
-      for (int q = 0; q < SS; ++q) s[q] = __ldg(a.state0 + q);
-    } else {
-      while (ld_acquire(done + b) < u) {
-      }
-#pragma unroll
-      for (int q = 0; q < SS; ++q) s[q] = wsb[q * 32];
-      cost = wsb[SS * 32], cc = wsb[(SS + 1) * 32], trig_valid = wsb[(SS + 2) * 32] != 0.0;
-#pragma unroll
-      for (int q = 0; q < 4 * NCARS; ++q) trig[q] = wsb[(SS + 3 + q) * 32];
-    }
-    const int t0 = u * a.unit_len, t1 = min(a.T, t0 + a.unit_len);
-    const double *Ek = a.E + min(k, a.K - 1);  // lanes past K (last batch) integrate a copy of the last rollout
-    double e_next[AS];
-#pragma unroll
-    for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)(t0 * AS + r) * a.ldk];
-    for (int t = t0; t < t1; ++t) {
-      double act[AS], e_cur[AS];
-#pragma unroll
-      for (int r = 0; r < AS; ++r) e_cur[r] = e_next[r];
-      if (t + 1 < t1) {
-#pragma unroll
-        for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)((t + 1) * AS + r) * a.ldk];
-      }
-#pragma unroll
-      for (int r = 0; r < AS; ++r) {
-        const int row = t * AS + r;
-        const double v = __ldg(a.U + row) + e_cur[r];  // Vₖ = pol.U + E[:,k], POL:271
-        if (a.bvec) cc += __ldg(a.bvec + row) * (v - __ldg(a.U_orig + row));  // POL:272
-        act[r] = clamp1(v);                                                   // UTL:55-67
-      }
-      const bool resync = !trig_valid || (t % 5) == 0;
-      cost -= cars_step_reward<NCARS, MODE>(env, tr, s, act, trig, resync, &trig_valid);  // UTL:137-138
-      if (a.traj && k < a.K) {
-#pragma unroll
-        for (int q = 0; q < SS; ++q) a.traj[((size_t)k * SS + q) * a.T + t] = s[q];  // UTL:139-141
-      }
-    }
-    if (u == nu - 1) {
-      if (k < a.K) a.costs[k] = cost + cc;  // POL:274-275
-    } else {
-#pragma unroll
-      for (int q = 0; q < SS; ++q) wsb[q * 32] = s[q];
-      wsb[SS * 32] = cost, wsb[(SS + 1) * 32] = cc, wsb[(SS + 2) * 32] = trig_valid ? 1.0 : 0.0;
-#pragma unroll
-      for (int q = 0; q < 4 * NCARS; ++q) wsb[(SS + 3 + q) * 32] = trig[q];
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release(done + b, u + 1);
-    }
-  }
-  if (a.warp_cycles && lane == 0)
-    a.warp_cycles[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = clock64() - t_begin;
-}
-
-int rollout_queue_fields(int n_cars) { return n_cars == 1 ? 8 + 3 + 4 : 0; }
-
-// returns 1 if launched, 0 if the configuration is not covered (caller falls back to launch_rollout_car)
-int launch_rollout_car_queue(const CarEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t st) {
-  if (env.n_cars != 1 || !a.ws || !a.ws_sync || a.unit_len < 1 || a.queue_ctas < 1) return 0;
-  const size_t smem = sizeof(double) * 3 * env.n_trk;
-  if (smem > 40 * 1024)
-    cudaFuncSetAttribute(rollout_car_queue_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int nb = (a.K + 31) / 32;
-  cudaMemsetAsync(a.ws_sync, 0, sizeof(int) * (size_t)(nb + 1), st);
-  rollout_car_queue_kernel<1, 3><<<a.queue_ctas, block, smem, st>>>(env, a, stop);
-  return 1;
-}
-
 __global__ void __launch_bounds__(128) rollout_mc_kernel(const __grid_constant__ McEnvArgs env,
                                                          const __grid_constant__ RolloutArgs a,
                                                          const int *stop) {

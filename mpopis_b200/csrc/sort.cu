@@ -21,10 +21,7 @@ namespace {
 constexpr int TILE = 2048;
 constexpr unsigned long long KEY_PAD = ~0ULL;
 
-__device__ __forceinline__ unsigned long long key_of(double c) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(c);
-  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
-}
+__device__ __forceinline__ unsigned long long key_of(double c) { return cost_key(c); }  // engine.cuh
 __device__ __forceinline__ bool lt(unsigned long long ka, int ia, unsigned long long kb, int ib) {
   return ka < kb || (ka == kb && ia < ib);
 }
@@ -133,10 +130,9 @@ __device__ __forceinline__ void merge_tile(const unsigned long long *__restrict_
   }
 }
 
-__device__ __forceinline__ double cost_of(unsigned long long b) {
-  b = (b >> 63) ? (b & 0x7fffffffffffffffULL) : ~b;
-  return __longlong_as_double((long long)b);
-}
+__device__ __forceinline__ double cost_of(unsigned long long b) { return key_cost(b); }
+// maximum(abs.(diff(...))) propagates NaN in Julia (then `NaN < 10e-3` is false: no break): fmax alone would drop it
+__device__ __forceinline__ double gap_max(double mx, double d) { return (d != d || mx != mx) ? d + mx : fmax(mx, d); }
 
 // All merge passes in ONE cooperative kernel (grid-wide barrier between passes) followed by the elite
 // early-stop test maximum(abs.(diff(elite_traj_cost))) < 10e-3 (POL:458-461, 566-569) on the sorted keys:
@@ -164,13 +160,13 @@ __global__ void __launch_bounds__(256) merge_all_kernel(unsigned long long *kin,
   }
   if (blockIdx.x == 0 && stop_flag && m > 1) {
     double mx = -1.0;
-    for (int j = threadIdx.x; j + 1 < m; j += 256) mx = fmax(mx, fabs(cost_of(kin[j + 1]) - cost_of(kin[j])));
+    for (int j = threadIdx.x; j + 1 < m; j += 256) mx = gap_max(mx, fabs(cost_of(kin[j + 1]) - cost_of(kin[j])));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1) mx = gap_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+      for (int w = 1; w < 8; ++w) mx = gap_max(mx, red[w]);
       if (early_stop && mx < 10e-3) *stop_flag = 1;
     }
   }
@@ -210,13 +206,13 @@ __global__ void __launch_bounds__(1024) small_sort_kernel(const double *__restri
   for (int e = threadIdx.x; e < n; e += 1024) keys[e] = sk[e], vals[e] = sv[e];
   if (stop_flag && m > 1) {  // maximum(abs.(diff(elite_traj_cost))) < 10e-3, POL:458-461, 566-569
     double mx = -1.0;
-    for (int j = threadIdx.x; j + 1 < m; j += 1024) mx = fmax(mx, fabs(cost_of(sk[j + 1]) - cost_of(sk[j])));
+    for (int j = threadIdx.x; j + 1 < m; j += 1024) mx = gap_max(mx, fabs(cost_of(sk[j + 1]) - cost_of(sk[j])));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1) mx = gap_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < 32; ++w) mx = fmax(mx, red[w]);
+      for (int w = 1; w < 32; ++w) mx = gap_max(mx, red[w]);
       if (early_stop && mx < 10e-3) *stop_flag = 1;
     }
   }
@@ -249,97 +245,6 @@ int launch_sortperm(const double *costs, int K, unsigned long long *keys_a, unsi
   void *args[] = {(void *)&kin, (void *)&vin, (void *)&kout, (void *)&vout, (void *)&K,
                   (void *)&m,   (void *)&early_stop, (void *)&stop_flag, (void *)&stop};
   return (int)cudaLaunchCooperativeKernel((const void *)merge_all_kernel, dim3(grid), dim3(256), args, 0, s);
-}
-
-// ---- sharded elite selection (one rank of a K-sharded :cemppi policy) -----------------------------------
-// Every rank sorts only its own costs; the sorted runs (key, local index) are all-gathered. For element j of
-// this rank's run, its position in the GLOBAL stable order is j + Σ_{r != me} #{elements of run r below it}
-// (binary searches; the composite (key, global index) is unique). Elites (position < m) are therefore a
-// PREFIX of the local run (length *m_loc), and the early-stop statistic max|Δ sorted elite costs| is the
-// maximum over elites of (successor cost − own cost), the successor being the smallest element above it
-// over all runs. No global sort, no moment work on other ranks' elites.
-__global__ void __launch_bounds__(256) global_rank_kernel(const unsigned long long *__restrict__ runs_k,
-                                                           const int *__restrict__ runs_v, int G, int me, int Kloc,
-                                                           int m, double *__restrict__ gap_partial, int *m_loc,
-                                                           const int *stop) {
-  if (stop && *stop) return;
-  __shared__ double red[8];
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  double gap = -1.0;
-  if (j < Kloc) {
-    const unsigned long long *mk = runs_k + (size_t)me * Kloc;
-    const int *mv = runs_v + (size_t)me * Kloc;
-    const unsigned long long key = mk[j];
-    const int gid = mv[j] + me * Kloc;  // global sample id
-    long long pos = j;
-    unsigned long long sk = KEY_PAD;
-    int sv = 0x7fffffff;
-    if (j + 1 < Kloc) sk = mk[j + 1], sv = mv[j + 1] + me * Kloc;
-    for (int r = 0; r < G; ++r) {
-      if (r == me) continue;
-      // pos only grows: once it reaches m the element is not an elite and neither its exact position nor its
-      // successor matters. With G runs of similar distribution a non-elite (80 % of the elements) is recognised
-      // after ~0.2·G·Kloc/j − 1 runs instead of G − 1 — the searches are chains of dependent L2 round trips, and
-      // their number per element is what made this kernel grow linearly with the number of GPUs.
-      if (pos >= m) break;
-      const unsigned long long *rk = runs_k + (size_t)r * Kloc;
-      const int *rv = runs_v + (size_t)r * Kloc;
-      int lo = 0, hi = Kloc;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (lt(rk[mid], rv[mid] + r * Kloc, key, gid)) lo = mid + 1;
-        else hi = mid;
-      }
-      pos += lo;
-      if (lo < Kloc && lt(rk[lo], rv[lo] + r * Kloc, sk, sv)) sk = rk[lo], sv = rv[lo] + r * Kloc;
-    }
-    if (pos < m) {
-      atomicMax(m_loc, j + 1);
-      if (pos + 1 < m) gap = fabs(cost_of(sk) - cost_of(key));
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) gap = fmax(gap, __shfl_xor_sync(0xffffffffu, gap, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gap;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) gap = fmax(gap, red[w]);
-    gap_partial[blockIdx.x] = gap;
-  }
-}
-
-__global__ void __launch_bounds__(256) gap_finish_kernel(const double *__restrict__ part, int n, double *out,
-                                                          const int *stop) {
-  if (stop && *stop) return;
-  __shared__ double red[8];
-  double g = -1.0;
-  for (int i = threadIdx.x; i < n; i += 256) g = fmax(g, part[i]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) g = fmax(g, __shfl_xor_sync(0xffffffffu, g, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = g;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) g = fmax(g, red[w]);
-    *out = g;
-  }
-}
-
-// after the all-reduce(max) of the gap: maximum(abs.(diff(elite_traj_cost))) < 10e-3 -> break (POL:458-461)
-__global__ void stop_decide_kernel(const double *gaps, int G, int early_stop, int *stop) {
-  double g = gaps[0];
-  for (int r = 1; r < G; ++r) g = fmax(g, gaps[r]);
-  if (!*stop && early_stop && g < 10e-3) *stop = 1;
-}
-
-void launch_global_rank(const unsigned long long *runs_k, const int *runs_v, int G, int me, int Kloc, int m,
-                        double *gap_partial, double *gap_out, int *m_loc, const int *stop, cudaStream_t s) {
-  const int nb = (Kloc + 255) / 256;
-  global_rank_kernel<<<nb, 256, 0, s>>>(runs_k, runs_v, G, me, Kloc, m, gap_partial, m_loc, stop);
-  gap_finish_kernel<<<1, 256, 0, s>>>(gap_partial, nb, gap_out, stop);
-}
-
-void launch_stop_decide(const double *gaps, int G, int early_stop, int *stop, cudaStream_t s) {
-  stop_decide_kernel<<<1, 1, 0, s>>>(gaps, G, early_stop, stop);
 }
 
 int sort_max_ctas(int num_sms) {

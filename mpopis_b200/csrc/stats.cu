@@ -196,23 +196,6 @@ void launch_reduce_partials(const double *partial, int nchunks, int n, double *o
   reduce_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, nchunks, n, stride ? stride : n, out, stop);
 }
 
-// 1/σ_i from the all-reduced first and second raw moments (sharded shrinkage: one collective fewer):
-// σ_i² = Σx_i²/n − μ_i². The elites' noise mean is a fraction of their spread, so the cancellation costs at
-// most a few ulps; it only feeds the standardisation inside the shrinkage intensity λ̂.
-__global__ void dinv_from_moments_kernel(const double *__restrict__ sum1, const double *__restrict__ sum2,
-                                         const double *cnt, int p, int standardise, double *__restrict__ dinv,
-                                         const int *stop) {
-  if (stop && *stop) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p) return;
-  const double n = *cnt, mu = sum1[i] / n;
-  dinv[i] = standardise ? 1.0 / sqrt(sum2[i] / n - mu * mu) : 1.0;
-}
-void launch_dinv_from_moments(const double *sum1, const double *sum2, const double *cnt, int p, int standardise,
-                              double *dinv, const int *stop, cudaStream_t s) {
-  dinv_from_moments_kernel<<<(p + 127) / 128, 128, 0, s>>>(sum1, sum2, cnt, p, standardise, dinv, stop);
-}
-
 // μ = sums[0:rows] / sums[rows]; optionally U += scale * μ  (pol.U = pol.U + vec(μ′), POL:365,465,...)
 __global__ void finalize_mean_kernel(const double *__restrict__ sums, int rows, double *__restrict__ mu,
                                      double *__restrict__ U, const double *scale_dev, const int *stop) {
@@ -723,11 +706,8 @@ void launch_moments_small(const double *X, long long ld, int p, int n, const dou
   kc = kc < 1 ? 1 : (kc > n ? n : kc);
   const int pitch = kc | 1;  // odd: lanes over rows hit distinct banks
   const size_t smem = sizeof(double) * (2 * (size_t)p + 40 + kc + (size_t)p * pitch);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(moments_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
-  }
+  // function attributes are per device: set it on every launch (a host-side table lookup, like rollout_car does)
+  cudaFuncSetAttribute(moments_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   moments_small_kernel<<<1, 1024, smem, s>>>(X, ld, p, n, w, cols, want_cov, corrected, method, ridge, kc, pitch, mu_out,
                                              U, scale_dev, sums_out, Sraw, Sigma, lambda_out, stop);
 }
@@ -854,13 +834,16 @@ void launch_ctrl_vec(const double *Sinv, int cs, const double *U_orig, double ga
 // ---- final control: weighted_controls, clamp, roll (POL:226-231, UTL:88-101) -------------------------
 // wsum[r] = Σ_k w_k E[r][k] (un-shifted E), wsum[cs] = Σ_k w_k. The reference shifts E by
 // (pol.U − U_orig) before weighting (POL:468): Σ_k w_k (E[r,k] + Δ_r) = wsum[r] + Δ_r Σ_k w_k.
+// bounds (nullable): [lo(as) | hi(as)] of action_space(pol.env) — the external (EnvpoolEnv-style) env's own limits;
+// the built-in envs are ±1 per component (CAR:156-159, MCR:75-84, continuous MountainCar).
 __global__ void finalize_control_kernel(const double *__restrict__ wsum, const double *__restrict__ U_orig,
                                         const double *__restrict__ U_cur, int cs, int as, int T,
-                                        double *__restrict__ U_next, double *__restrict__ control) {
+                                        double *__restrict__ U_next, double *__restrict__ control,
+                                        const double *__restrict__ bounds) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= cs) return;
   const double wc = U_orig[r] + (wsum[r] + (U_cur[r] - U_orig[r]) * wsum[cs]);
-  if (r < as) control[r] = fmin(fmax(wc, -1.0), 1.0);  // UTL:91
+  if (r < as) control[r] = fmin(fmax(wc, bounds ? bounds[r] : -1.0), bounds ? bounds[as + r] : 1.0);  // UTL:91
   if (T > 1) {
     if (r >= as) U_next[r - as] = wc;                   // UTL:95
     if (r >= cs - as) U_next[r] = U_orig[r];            // UTL:96 is a no-op (App. B-2): tail keeps its values
@@ -869,8 +852,8 @@ __global__ void finalize_control_kernel(const double *__restrict__ wsum, const d
   }
 }
 void launch_finalize_control(const double *wsum, const double *U_orig, const double *U_cur, int cs, int as, int T,
-                             double *U_next, double *control, cudaStream_t s) {
-  finalize_control_kernel<<<(cs + 127) / 128, 128, 0, s>>>(wsum, U_orig, U_cur, cs, as, T, U_next, control);
+                             double *U_next, double *control, const double *bounds, cudaStream_t s) {
+  finalize_control_kernel<<<(cs + 127) / 128, 128, 0, s>>>(wsum, U_orig, U_cur, cs, as, T, U_next, control, bounds);
 }
 
 }  // namespace mpopis

@@ -295,9 +295,23 @@ class Engine:
         self._chk(self.b.sortperm(self.h, _d(c), c.size, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return out
 
+    def elite_select(self, costs, m, k0=0, kloc=None, early_stop=True):
+        """(ascending elite ids inside [k0, k0+kloc), stop, tau4) — select.cu's sort-free order[1:m] + POL:458-461."""
+        c = _f64(costs)
+        kloc = c.size - k0 if kloc is None else kloc
+        ids = np.zeros(min(m, kloc) + 1, dtype=np.int64)
+        n, stop, tau = C.c_int64(0), C.c_int32(0), np.zeros(4)
+        self._chk(self.b.elite_select(self.h, _d(c), c.size, int(m), int(k0), int(kloc), int(bool(early_stop)),
+                                      ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n), C.byref(stop), _d(tau)))
+        return ids[:n.value].copy(), bool(stop.value), tau
+
     def comm_init(self, nccl_id: bytes):
         buf = C.create_string_buffer(nccl_id, 128)
         self._chk(self.b.comm_init(self.h, buf))
+
+    def comm_init_loopback(self, group):
+        """Attach this handle (virtual rank) to a loop-back group (`_lib.LoopbackGroup`)."""
+        self._chk(self.b.comm_init_loopback(self.h, group.ptr))
 
     def warp_cycles(self) -> np.ndarray:
         """Per-warp clock64() cycles of the most recent rollout launch (needs set_option("rollout_profile", 1))."""

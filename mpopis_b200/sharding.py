@@ -31,6 +31,25 @@ def broadcast_comm_id(dist, rank: int, src: int = 0) -> bytes:
     return box[0]
 
 
+def run_virtual_ranks(fns):
+    """Run one callable per virtual rank of a loop-back group, each on its own host thread (the collectives of a
+    loop-back group block until every rank has entered them). Returns the results in rank order; the first
+    exception is re-raised after all threads have finished."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(fns)) as ex:
+        futs = [ex.submit(f) for f in fns]
+        out, err = [], None
+        for f in futs:
+            try:
+                out.append(f.result())
+            except Exception as e:  # keep draining: the other ranks unblock through the group's timeout/break
+                out.append(None)
+                err = err or e
+    if err is not None:
+        raise err
+    return out
+
+
 def sharded_elite_moments(E_local: np.ndarray, k0: int, order: np.ndarray, m: int, allreduce, method: str = "mle"):
     """numpy emulation of csrc/stats.cu for the CE update on one shard (POL:455-465).
 

@@ -705,7 +705,11 @@ static void apply_L(const double *L, int64_t n, const double *Z, int64_t K, doub
 /* get_controls_roll_U!, UTL:88-101 with the aliasing of SURVEY App. B-2: shift left by `as`,
  * the last `as` entries keep their values. */
 static void controls_roll_U(const orc_t *h, const double *wc, double *U, double *control) {
-  for (int64_t r = 0; r < h->as; ++r) control[r] = clampd(wc[r], -1.0, 1.0); /* UTL:91 */
+  /* UTL:91: clamp to action_space(pol.env) — ±1 for the built-in envs (CAR:156-159, MCR:75-84, continuous
+   * MountainCar), the caller's own bounds for the EnvpoolEnv-style external env */
+  const int ext = h->cfg.env == MPOPIS_ENV_EXTERNAL && h->ext_lo && h->ext_hi;
+  for (int64_t r = 0; r < h->as; ++r)
+    control[r] = clampd(wc[r], ext ? h->ext_lo[r] : -1.0, ext ? h->ext_hi[r] : 1.0);
   if (h->T > 1) {
     for (int64_t r = 0; r + h->as < h->cs; ++r) U[r] = wc[r + h->as]; /* UTL:95 */
     /* UTL:96 is a self-assignment (pol.U aliases pol.params.U₀): no-op */
@@ -892,9 +896,10 @@ static int plan_g(orc_t *h, const double *state, int64_t env_t, double *U_inout,
       for (int64_t j = 0; j < m_elite; ++j)
         memcpy(elite + cs * j, h->E + cs * order[j], sizeof(double) * cs); /* POL:456,564 */
       double maxdiff = -INFINITY; /* maximum(abs.(diff(elite_traj_cost))) < 10e-3, POL:458-461 */
-      for (int64_t j = 0; j + 1 < m_elite; ++j) {
+      for (int64_t j = 0; j + 1 < m_elite; ++j) { /* Julia's maximum propagates NaN (then NaN < 10e-3 is false) */
         double d = fabs(h->costs[order[j + 1]] - h->costs[order[j]]);
-        if (d > maxdiff) maxdiff = d;
+        if (isnan(d) || isnan(maxdiff)) maxdiff = NAN;
+        else if (d > maxdiff) maxdiff = d;
       }
       if (h->cfg.early_stop && maxdiff < 10e-3) break;
       if (pol == MPOPIS_POLICY_CEMPPI) { /* POL:464-465 */

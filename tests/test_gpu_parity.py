@@ -477,20 +477,26 @@ def test_tma_staged_noise_equals_register_prefetch(gpu_bound, n_cars, K):
     assert_costs_close(c1, c0)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("T", [50, 23])
-def test_work_queue_rollouts_equal_the_plain_kernel(gpu_bound, T):
-    """"rollout_queue" = 12: a persistent grid of 12 warps per SM pulls (32 rollouts x 10 control steps) units from an
-    atomic counter and carries the rollout state through a scratch buffer between units — same arithmetic as the
-    one-thread-per-rollout launch, including a last unit shorter than the others and a last batch that is not full."""
+def test_target_config_one_step_vs_oracle(gpu_bound, orc):
+    """The north-star configuration itself (K = 65 536, T = 50, :cemppi, Σ_est = :ss) against the oracle on injected
+    noise — N = 3 AIS iterations keeps the CPU side to a few seconds. Exercises select.cu (13 107 elites), the gathered
+    elite moments, the shrinkage estimate and the DMMA E = L·Z at the size the bench measures."""
     env = make_env("car")
-    K = 65536 - 13
-    g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, K, T, 1)), env, "gmppi")
-    rng = np.random.default_rng(7)
-    E = rng.standard_normal((g.cs, K)) * 0.3
-    U = rng.uniform(-0.3, 0.3, g.cs)
-    st = synthetic_states()[3]
-    c0 = g.rollout_costs(st, 0, U, U, E)
-    g.set_option("rollout_queue", 12)
-    c1 = g.rollout_costs(st, 0, U, U, E)
-    assert_costs_close(c1, c0)
+    K, T, N = 65536, 50, 3
+    g, c = pair(gpu_bound, orc, "cemppi", env, K, T, N, sigma_est="ss")
+    c.b.set_threads(c.h, 16)
+    rng = np.random.Generator(np.random.Philox(key=65536))
+    Z = rng.standard_normal((g.cs, K, N))
+    U = rng.uniform(-0.1, 0.1, g.cs)
+    st = synthetic_states()[2]
+    (cg, ug, ig), (cc, uc, ic) = g.plan(st, 0, U, Z=Z), c.plan(st, 0, U, Z=Z)
+    assert ig == ic == N
+    flips = assert_costs_close(g.fetch()["costs"], c.fetch()["costs"])
+    np.testing.assert_allclose(cg, cc, rtol=CONTROL_RTOL, atol=1e-8)
+    np.testing.assert_allclose(ug, uc, rtol=CONTROL_RTOL, atol=1e-8)
+    Sg, Ug = g.fetch_proposal()
+    Sc, Uc = c.fetch_proposal()
+    np.testing.assert_allclose(Ug, Uc, rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(Sg, Sc, rtol=1e-6, atol=1e-12)
+    assert abs(g.last_shrinkage() - c.last_shrinkage()) < 1e-8
+    print(f"K=65536: |Δcontrol|={np.max(np.abs(cg - cc)):.2e} |ΔU|={np.max(np.abs(ug - uc)):.2e} cost flips={flips}")
