@@ -102,6 +102,9 @@ __device__ __forceinline__ double key_cost(unsigned long long k) {
 // rollout.cu  (variant 0 = fast math-equivalent formulation, 1 = literal libm call sequence)
 void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, int stage,
                         const int *stop, cudaStream_t s);
+// rollout_split.cu ("v5", rollout_variant 4): velocity warps + pose/reward warps; returns 0 when not applicable
+int rollout_split_max_cars();
+int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, const int *stop, cudaStream_t s);
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
                         unsigned char *within, int use_lut, cudaStream_t s);
@@ -112,10 +115,11 @@ void launch_env_step_mc(const McEnvArgs &env, double *state, const double *actio
 void launch_env_reward_car(const CarEnvArgs &env, const double *state, double *reward, int variant, cudaStream_t s);
 void launch_env_reward_mc(const McEnvArgs &env, const double *state, int done, double *reward, cudaStream_t s);
 // sampling.cu
+// step_dev (nullable) overrides `step`: the control-step counter in device memory (graph replay)
 void launch_philox_normals(double *Z, long long ldk, int cs, int K, long long k0, uint64_t seed, uint32_t step,
-                           uint32_t iter, const int *stop, cudaStream_t s);
-void launch_philox_uniforms(double *u, int K, uint64_t seed, uint32_t step, uint32_t iter, const int *stop,
-                            cudaStream_t s);
+                           const unsigned *step_dev, uint32_t iter, const int *stop, cudaStream_t s);
+void launch_philox_uniforms(double *u, int K, uint64_t seed, uint32_t step, const unsigned *step_dev, uint32_t iter,
+                            const int *stop, cudaStream_t s);
 void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E, long long ldk, int K,
                     const int *stop, cudaStream_t s);
 void set_apply_L_path(int path);  // 0 DFMA tile, 1 DMMA row blocks, 2 DMMA column tiles (process-wide)
@@ -161,8 +165,10 @@ void launch_iter_begin(const int *stop, int *its, int *total_its, cudaStream_t s
 void launch_pmc_counts(const double *wglobal, int K, const double *u, double *cdf, int *counts, long long k0,
                        int Kloc, double *wloc, const int *stop, cudaStream_t s);
 void launch_ctrl_vec(const double *Sinv, int cs, const double *U_orig, double gamma, double *b, cudaStream_t s);
+// step_dev (nullable): incremented by one (the Philox control-step counter)
 void launch_finalize_control(const double *wsum, const double *U_orig, const double *U_cur, int cs, int as, int T,
-                             double *U_next, double *control, const double *bounds, cudaStream_t s);
+                             double *U_next, double *control, const double *bounds, unsigned *step_dev, cudaStream_t s);
+void launch_set_scalar(double *dst, double value, cudaStream_t s);
 // linalg.cu
 void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, double *Wglobal, int *info, int tag,
                  const int *stop, cudaStream_t s);

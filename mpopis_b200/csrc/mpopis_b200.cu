@@ -342,7 +342,10 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
   a.K = h->Kloc, a.T = h->T;
   a.warp_cycles = h->d_warp_cycles;
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING) {
-    launch_rollout_car(h->car, a, h->rollout_variant, h->rollout_block, h->rollout_stage, h->stop(), h->st);
+    // variant 4 ("v5"): the warp-specialised kernel; it covers 1..3 cars, the rest falls back to variant 3
+    if (!(h->rollout_variant == 4 && launch_rollout_car_split(h->car, a, h->stop(), h->st)))
+      launch_rollout_car(h->car, a, h->rollout_variant == 4 ? 3 : h->rollout_variant, h->rollout_block,
+                         h->rollout_stage, h->stop(), h->st);
   } else
     launch_rollout_mc(h->mc, a, h->rollout_block, h->stop(), h->st);
   h->launches += 1;
@@ -372,7 +375,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   const bool adapt = adapts_sigma(pol) && N > 1;
   if (adapt) CU(cudaMemcpyAsync(h->d_Sigma, h->d_Sigma0, sizeof(double) * cs * cs, cudaMemcpyDeviceToDevice, st));
   if (pol == MPOPIS_POLICY_CMAMPPI) {
-    CU(cudaMemcpyAsync(h->d_sigma, &h->cma.sigma, sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_set_scalar(h->d_sigma, h->cma.sigma, st);  // a kernel, not a pageable H2D copy: graph-capturable
     CU(cudaMemsetAsync(h->d_psig, 0, sizeof(double) * cs, st));
     CU(cudaMemsetAsync(h->d_pSig, 0, sizeof(double) * cs, st));
   }
@@ -408,7 +411,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       CU(cudaMemcpyAsync(h->d_stage, src, sizeof(double) * cs * Kloc, cudaMemcpyHostToDevice, st));
       launch_transpose_in(h->d_stage, h->d_Z, cs, Kloc, h->ldk, st);
     } else if (n == 0) {
-      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, (uint32_t)h->step, 0u, stop, st);
+      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, 0u, h->d_step, 0u, stop, st);
     } else {
       CU(cudaStreamWaitEvent(st, h->ev_z_ready, 0));  // Z of this iteration was drawn on the side stream
     }
@@ -426,7 +429,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       // them overlap slowed the rollouts by more than the 36 µs it hid (measured, profiles/README.md).
       CU(cudaEventRecord(h->ev_z_free, st));
       CU(cudaStreamWaitEvent(h->st2, h->ev_z_free, 0));
-      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, (uint32_t)h->step, (uint32_t)(n + 1), stop,
+      launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, 0u, h->d_step, (uint32_t)(n + 1), stop,
                             h->st2);
       CU(cudaEventRecord(h->ev_z_ready, h->st2));
     }
@@ -449,7 +452,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       case MPOPIS_POLICY_PMCMPPI: {  // POL:802-809
         h->launches += launch_weights(h->d_costs, K, h->cfg.lambda_ais, h->d_w, h->d_ones, stop, st) - 1;
         if (u_host) CU(cudaMemcpyAsync(h->d_u, u_host + (size_t)n * K, sizeof(double) * K, cudaMemcpyHostToDevice, st));
-        else launch_philox_uniforms(h->d_u, K, h->seed, (uint32_t)h->step, (uint32_t)n, stop, st);
+        else launch_philox_uniforms(h->d_u, K, h->seed, 0u, h->d_step, (uint32_t)n, stop, st);
         launch_pmc_counts(h->d_w, K, h->d_u, h->d_cdf, h->d_counts, h->k0, Kloc, h->d_wcnt, stop, st);
         h->launches += 5;
         if (int rc = moments(h, h->d_E, h->ldk, Kloc, h->d_wcnt, true, 1, MPOPIS_SIGMA_MLE, 10e-9, true, nullptr,
@@ -503,7 +506,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   h->launches += 2;
   if (int rc = allreduce_sum(h, h->d_sums, cs + 1)) return rc;
   launch_finalize_control(h->d_sums, h->d_U_orig, h->d_U_cur, cs, h->as, h->T, h->d_U_next, h->d_control,
-                          h->cfg.env == MPOPIS_ENV_EXTERNAL ? h->d_ext_bounds : nullptr, st);
+                          h->cfg.env == MPOPIS_ENV_EXTERNAL ? h->d_ext_bounds : nullptr, h->d_step, st);
   h->launches += 1;
   mark(h, "final");
   CU(cudaEventRecord(h->ev[1], st));
@@ -1009,8 +1012,8 @@ int mpopis_b200_seed(mpopis_t *h, uint64_t seed) {
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
   if (!h || !key) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (!strcmp(key, "rollout_variant")) {
-    if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
-      return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0, 1, 2 or 3");
+    if (value != 0.0 && value != 1.0 && value != 3.0 && value != 4.0)
+      return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0 (v3), 1 (literal), 3 (v4) or 4 (v5, warp-specialised)");
     h->rollout_variant = (int)value;
   }
   else if (!strcmp(key, "rollout_profile")) {  // per-warp clock64() of the rollout kernel, read with warp_cycles()
@@ -1247,7 +1250,7 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
   if (int rc = dj.alloc((size_t)n)) return rc;
   if (int rc = dw.alloc((size_t)n)) return rc;
   CU(cudaMemcpyAsync(dp, pos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->st));
-  launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->rollout_variant == 0 || h->rollout_variant == 3, h->st);
+  launch_track_query(h->car, dp, (int)n, di, dj, dd, dw, h->rollout_variant != 1, h->st);
   h->launches += 1;
   if (idx_out) CU(cudaMemcpyAsync(idx_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));
   if (idx2_out) CU(cudaMemcpyAsync(idx2_out, dj, sizeof(int) * n, cudaMemcpyDeviceToHost, h->st));
@@ -1260,7 +1263,8 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
 
 static int env_step_device(mpopis_t *h, const double *d_action) {
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
-    launch_env_step_car(h->car, h->d_state, d_action, h->d_env_t, h->d_reward, h->rollout_variant, h->st);
+    launch_env_step_car(h->car, h->d_state, d_action, h->d_env_t, h->d_reward, h->rollout_variant == 4 ? 3 : h->rollout_variant,
+                        h->st);
   else
     launch_env_step_mc(h->mc, h->d_state, d_action, h->d_env_t, h->d_reward, h->d_done, h->st);
   h->launches += 1;
@@ -1298,7 +1302,7 @@ int mpopis_b200_env_reward(mpopis_t *h, const double *state, uint8_t done, doubl
   if (int rc = set_device(h)) return rc;
   CU(cudaMemcpyAsync(h->d_state, state, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
-    launch_env_reward_car(h->car, h->d_state, h->d_reward, h->rollout_variant, h->st);
+    launch_env_reward_car(h->car, h->d_state, h->d_reward, h->rollout_variant == 4 ? 3 : h->rollout_variant, h->st);
   else
     launch_env_reward_mc(h->mc, h->d_state, done, h->d_reward, h->st);
   h->launches += 1;
@@ -1311,7 +1315,7 @@ int mpopis_b200_env_reward(mpopis_t *h, const double *state, uint8_t done, doubl
 int mpopis_b200_sample_normals(mpopis_t *h, int64_t step, int64_t iteration, double *Z_out) {
   if (!h || !Z_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (int rc = set_device(h)) return rc;
-  launch_philox_normals(h->d_Z, h->ldk, h->cs, h->Kloc, h->k0, h->seed, (uint32_t)step, (uint32_t)iteration, nullptr,
+  launch_philox_normals(h->d_Z, h->ldk, h->cs, h->Kloc, h->k0, h->seed, (uint32_t)step, nullptr, (uint32_t)iteration, nullptr,
                         h->st);
   launch_transpose_out(h->d_Z, h->d_stage, h->cs, h->Kloc, h->ldk, nullptr, nullptr, h->st);
   h->launches += 2;
@@ -1471,7 +1475,7 @@ int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out) {
 int mpopis_b200_bench_rowsum(mpopis_t *h, int32_t reps, double *ms_per_launch_out, double *bytes_per_launch_out) {
   if (!h || !ms_per_launch_out || reps < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (int rc = set_device(h)) return rc;
-  launch_philox_normals(h->d_E, h->ldk, h->cs, h->Kloc, h->k0, 1234u, 0u, 0u, nullptr, h->st);
+  launch_philox_normals(h->d_E, h->ldk, h->cs, h->Kloc, h->k0, 1234u, 0u, nullptr, 0u, nullptr, h->st);
   CU(cudaMemsetAsync(h->d_costs, 0, sizeof(double) * h->K, h->st));
   h->launches += 1 + launch_weights(h->d_costs, h->K, 1.0, h->d_w, h->d_ones, nullptr, h->st);
   cudaEvent_t e0, e1;

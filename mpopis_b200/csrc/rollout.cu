@@ -62,7 +62,7 @@ void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant
   if (variant == 3 && stage == 1 && env.n_cars <= 4) launch_rollout_car_v<3, 1>(env, a, block, stop, st);
   else if (variant == 3) launch_rollout_car_v<3, 0>(env, a, block, stop, st);
   else if (variant == 0 || env.n_cars > 4) launch_rollout_car_v<0, 0>(env, a, block, stop, st);
-  else launch_rollout_car_aux(env, a, variant, block, stop, st);  // variants 1 and 2 live in rollout_aux.cu
+  else launch_rollout_car_aux(env, a, variant, block, stop, st);  // the literal variant lives in rollout_aux.cu
 }
 
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t st) {

@@ -1,5 +1,5 @@
-// rollout_aux.cu — the non-production instantiations of the rollout kernel (MODE 1 "literal": the reference's libm
-// call sequence; MODE 2: the first fast cut) and the single-step parity surfaces (track query, env step, reward).
+// rollout_aux.cu — the non-production instantiation of the rollout kernel (MODE 1 "literal": the reference's libm
+// call sequence, the parity anchor) and the single-step parity surfaces (track query, env step, reward).
 // Split from rollout.cu only to halve the build's critical path; see rollout.cu for the description of the variants.
 #include "rollout_kernels.cuh"
 
@@ -7,8 +7,8 @@ namespace mpopis {
 
 void launch_rollout_car_aux(const CarEnvArgs &env, const RolloutArgs &a, int variant, int block, const int *stop,
                             cudaStream_t st) {
-  if (variant == 1) launch_rollout_car_v<1, 0>(env, a, block, stop, st);
-  else launch_rollout_car_v<2, 0>(env, a, block, stop, st);
+  (void)variant;  // only the literal variant lives here since the first fast cut (MODE 2) was retired
+  launch_rollout_car_v<1, 0>(env, a, block, stop, st);
 }
 
 // ---- parity surfaces -------------------------------------------------------------------------
@@ -73,7 +73,7 @@ void launch_env_step_car(const CarEnvArgs &env, double *state, const double *act
       cudaFuncSetAttribute(env_step_car_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     env_step_car_kernel<M><<<1, 32, smem, st>>>(env, state, action, env_t, reward);                          \
   }
-  if (variant == 0) MPOPIS_ES(0) else if (variant == 1) MPOPIS_ES(1) else if (variant == 3) MPOPIS_ES(3) else MPOPIS_ES(2)
+  if (variant == 0) MPOPIS_ES(0) else if (variant == 1) MPOPIS_ES(1) else MPOPIS_ES(3)
 #undef MPOPIS_ES
 }
 
@@ -105,7 +105,7 @@ void launch_env_reward_car(const CarEnvArgs &env, const double *state, double *r
       cudaFuncSetAttribute(env_reward_car_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     env_reward_car_kernel<M><<<1, 32, smem, st>>>(env, state, reward);                                       \
   }
-  if (variant == 0) MPOPIS_ER(0) else if (variant == 1) MPOPIS_ER(1) else if (variant == 3) MPOPIS_ER(3) else MPOPIS_ER(2)
+  if (variant == 0) MPOPIS_ER(0) else if (variant == 1) MPOPIS_ER(1) else MPOPIS_ER(3)
 #undef MPOPIS_ER
 }
 

@@ -1,0 +1,415 @@
+// rollout_split.cu — G2, "v5": the rollout kernel split by DATA DEPENDENCE into two warp roles.
+//
+// Round 1 left the thread-per-rollout kernel (rollout_kernels.cuh, MODE 3) at ≈52 % of the FP64 issue rate and traced
+// the rest to latency: a dependent FP64 instruction issues 23-25 cycles after its producer, K = 65 536 rollouts are
+// only 3.46 warps per scheduler, and inside one thread the in-order issue stalls on the recurrence
+//     (Vx, Vy, Ψ̇, δ)ᵢ -> slip ratios -> reciprocal -> brush-tyre cubic -> forces -> (Vx, Vy, Ψ̇)ᵢ₊₁       CAR:301-328
+// whose ≈15 dependent operations per Euler sub-step ARE the latency of a rollout. Everything else a control step
+// does hangs off that chain without feeding it: the pose (Ψ, x, y — CAR:329-332) only consumes (Vx, Vy, Ψ̇δt), and the
+// reward (CAR:201-213) with its nearest-point search, projection, IEEE sqrt/div (TRK:68-92) only consumes the pose.
+// ptxas cannot overlap them across the sub-step loop / control-step loop in one instruction stream, and at 3.46
+// warps per scheduler the hardware has nothing else to issue either. So the two halves become two warps:
+//
+//   VELOCITY warp (2 per CTA, one rollout per lane): noise load, clamp, control cost (POL:271-272, UTL:55-67), tyre
+//       constants, the velocity recurrence; publishes (Vx, Vy, Ψ̇δt) per sub-step into a shared-memory ring.
+//   POSE warp (1 per CTA, TWO rollouts per lane — one from each velocity warp, two independent chains in one
+//       instruction stream): heading/position integration, heading wrap, within_track + reward, running cost,
+//       trajectory log; writes the cost.
+//
+// 65 536 rollouts are then 2048 latency-bound warps whose chain is shorter (no pose/reward work in it) plus 1024
+// throughput-rich warps that fill the FP64 pipe while the former wait: 5.2 warps per scheduler instead of 3.46, with
+// the same arithmetic. The ring is sub-step granular (16 slots of 3 x 32 doubles per velocity warp, groups of 4 slots
+// handed over with mbarriers: full[4] / empty[4], one elected lane arrives after __syncwarp), so the pose warp trails
+// by a few sub-steps and nothing is ever rolled back: the velocity sub-step is written for every Vx != 0 as in MODE 3
+// (car_model.cuh: car_step_spec), its validity conditions are checked PER SUB-STEP, and a lane that leaves them
+// (Vx changes sign while braking, den·Vx denormal, |δ| > 0.78, a standstill) finishes the control step on the general
+// path (all branches, libm where the un-wrapped angle matters) — sub-step by sub-step, in place.
+// Arithmetic: identical to MODE 3 on every sub-step both consider valid (same expressions, same fma placement);
+// control steps MODE 3 would repair as a whole are here repaired from the offending sub-step on — both are the
+// reference's mathematics to ~1e-13, tests/test_gpu_parity.py pins each against the oracle.
+#include <cuda/ptx>
+#include <math_constants.h>
+
+#include "car_model.cuh"
+#include "engine.cuh"
+
+namespace mpopis {
+
+namespace {
+
+namespace ptx = cuda::ptx;
+
+constexpr int RING = 16, GROUP = 4, NGROUP = RING / GROUP;  // sub-step slots per velocity warp
+constexpr int VW = 2;                                       // velocity warps per CTA (= rollouts per pose lane)
+constexpr int CTA = 32 * (VW + 1);
+
+template <int NCARS>
+struct SplitSmem {
+  double ring[VW][RING][NCARS][3][32];  // (Vx, Vy, Ψ̇δt) after each sub-step
+  double ext[VW][2][NCARS][3][32];      // per control step (parity-buffered): Ψ̇, δ, pedal at its end (trajectory log)
+  double fin[VW][32];                   // control cost (POL:272) of the finished rollout
+  uint64_t full[VW][NGROUP], empty[VW][NGROUP];
+};
+
+__device__ __forceinline__ void bar_wait(uint64_t *bar, unsigned parity) {
+  while (!ptx::mbarrier_try_wait_parity(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+  (void)ptx::mbarrier_arrive(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar);
+}
+
+// One Euler sub-step of the velocity recurrence on the general path (car_step_fast's loop body, CAR:301-328, without
+// the pose): every branch the reference's arithmetic can take. Rare (a lane that left the straight-line conditions),
+// so it is kept out of line and recomputes the tyre constants instead of carrying them.
+struct VelOut {
+  double Vx, Vy, psid, sg;
+};
+__device__ __noinline__ VelOut vel_substep_general(const CarParams &P, double ddt, double accel, double bk, double split,
+                                                   double delta, double sg, double Vx, double Vy, double psid) {
+  double sd, cd;
+  sincos(delta, &sd, &cd);
+  if (!(Vx > 0.0 && sg > 0.0)) {
+    const double sg_now = jl_sign(Vx);
+    if (sg_now != sg) sg = sg_now;  // sign(Vx) flipped: the brake force changes direction (CAR:311)
+  }
+  const TireConsts tc = tire_consts_fast(P, accel, bk, split, sg);
+  const double inv_Izz = 1 / P.Izz, inv_m = 1 / P.m;
+  const double yf = Vy + P.l_f * psid, yr = Vy - P.l_r * psid;
+  double fyf, fyr, fx_aero;
+  if (Vx > 0.0) {
+    fyf = tire_fy_ratio<0>(yf * cd - Vx * sd, Vx * cd + yf * sd, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
+    fyr = tire_fy_ratio<0>(yr, Vx, P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
+  } else {  // reversing / standstill: the un-wrapped slip angle matters, keep the libm sequence (CAR:304-305)
+    fyf = tire_fy_literal(atan2(yf, Vx) - delta, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
+    fyr = tire_fy_literal(atan2(yr, Vx), P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
+  }
+  fx_aero = (P.C_D0 + P.C_D1 * fabs(Vx)) * sg;                                             // CAR:308
+  const double psidd = inv_Izz * (P.l_f * (tc.fxf * sd + fyf * cd) - P.l_r * fyr);        // CAR:322
+  const double Vy_dot = inv_m * (fyf * cd + tc.fxf * sd + fyr) - psid * Vx;               // CAR:323
+  const double Vx_dot = inv_m * (tc.fxf * cd - fyf * sd + tc.fxr - fx_aero) + psid * Vy;  // CAR:324
+  psid += psidd * ddt;  // CAR:326
+  Vx += Vx_dot * ddt;   // CAR:327
+  Vy += Vy_dot * ddt;   // CAR:328
+  return VelOut{Vx, Vy, psid, sg};
+}
+
+// sin/cos of a heading increment that left the short polynomial's range (a spinning car): rare, out of line
+struct SinCos {
+  double s, c;
+};
+__device__ __noinline__ SinCos sincos_increment_general(double dpsi) {
+  SinCos o;
+  if (fabs(dpsi) <= 0.8) sincos_kernel(dpsi, &o.s, &o.c);
+  else sincos(dpsi, &o.s, &o.c);
+  return o;
+}
+
+struct VelCar {  // velocity-side state of one car
+  double Vx, Vy, psid, delta, sd, cd;
+  bool trig_valid;
+};
+struct PoseCar {  // pose-side state of one car
+  double x, y, psi, sp, cp;
+};
+
+template <int NCARS>
+__device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm, int vw,
+                                              int k, int lane) {
+  constexpr int AS = 2 * NCARS;
+  const int nsub = env.nsub, T = a.T;
+  const double ddt = env.ddt;
+  VelCar car[NCARS];
+#pragma unroll
+  for (int c = 0; c < NCARS; ++c) {
+    car[c].Vx = __ldg(a.state0 + 8 * c + 3), car[c].Vy = __ldg(a.state0 + 8 * c + 4);
+    car[c].psid = __ldg(a.state0 + 8 * c + 5), car[c].delta = __ldg(a.state0 + 8 * c + 6);
+    car[c].sd = 0.0, car[c].cd = 1.0, car[c].trig_valid = false;
+  }
+  const double *Ek = a.E + k;
+  double cc = 0.0, e_next[AS];
+#pragma unroll
+  for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)r * a.ldk];
+  int g = 0;  // global sub-step counter of this rollout
+  for (int t = 0; t < T; ++t) {
+    double act[AS];
+#pragma unroll
+    for (int r = 0; r < AS; ++r) {
+      const int row = t * AS + r;
+      const double v = __ldg(a.U + row) + e_next[r];                          // Vₖ = pol.U + E[:,k], POL:271
+      if (a.bvec) cc += __ldg(a.bvec + row) * (v - __ldg(a.U_orig + row));    // POL:272
+      act[r] = clamp1(v);                                                     // UTL:55-67
+    }
+    if (t + 1 < T) {
+#pragma unroll
+      for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)((t + 1) * AS + r) * a.ldk];
+    }
+    // ---- per control step, per car: steering rate, tyre constants (CAR:295-297, 310-318) ----
+    TireConsts tc[NCARS];
+    double dlt[NCARS], sdl[NCARS], cdl[NCARS], dpsi[NCARS], accel[NCARS], bk[NCARS], split[NCARS], sg[NCARS];
+    int hvx0[NCARS], brake_mask[NCARS];
+    bool gen[NCARS];  // this lane integrates the rest of the control step on the general path
+#pragma unroll
+    for (int c = 0; c < NCARS; ++c) {
+      const CarParams &P = env.car[c];
+      const CarDerived &D = env.der[c];
+      const double a0 = act[2 * c], a1 = act[2 * c + 1];
+      const double tgt = a0 * P.d_max - car[c].delta;
+      const double rate = fmin(fast_div(fabs(tgt), env.dt), P.dd_max) * jl_sign(tgt);  // CAR:295-296
+      accel[c] = P.Fx_max * fmax(a1, 0.0);                                             // CAR:310
+      bk[c] = P.Fx_min * fmin(a1, 0.0);                                                // CAR:311 without sign(Vx)
+      split[c] = a1 <= 0.0 ? P.l_brake : P.l_drive;
+      sg[c] = jl_sign(car[c].Vx);
+      tc[c] = tire_consts_der(P, D, accel[c], bk[c], split[c], sg[c]);
+      dlt[c] = rate * ddt;
+      hvx0[c] = hi32(car[c].Vx), brake_mask[c] = bk[c] != 0.0 ? (int)0x80000000 : 0;
+      gen[c] = !((fmax(fabs(car[c].delta), fabs(a0 * P.d_max)) <= 0.78) & (car[c].Vx != 0.0) & (fabs(dlt[c]) <= 0.03));
+      sincos_tiny(dlt[c], &sdl[c], &cdl[c]);  // |rate·δt| <= δ̇_max·δt = 0.0157 for the default car
+      if (!car[c].trig_valid || (t % 5) == 0) sincos_kernel(car[c].delta, &car[c].sd, &car[c].cd);
+      dpsi[c] = car[c].psid * ddt;  // Ψ̇δt of the CURRENT Ψ̇: the −Ψ̇Vx / +Ψ̇Vy terms of the next sub-step
+    }
+    for (int i = 0; i < nsub; ++i, ++g) {
+      const int slot = g % RING, grp = slot / GROUP;
+      if ((g % GROUP) == 0 && g >= RING) bar_wait(&sm.empty[vw][grp], (unsigned)((g / RING - 1) & 1));
+#pragma unroll
+      for (int c = 0; c < NCARS; ++c) {
+        const CarParams &P = env.car[c];
+        const CarDerived &D = env.der[c];
+        double Vx = car[c].Vx, Vy = car[c].Vy, psid = car[c].psid, sd = car[c].sd, cd = car[c].cd;
+        // --- straight-line sub-step, valid for every Vx != 0 (car_model.cuh: car_step_spec, same expressions) ---
+        const double ns = fma(sd, cdl[c], cd * sdl[c]);  // sin/cos(δ + rate·δt), CAR:301
+        cd = fma(cd, cdl[c], -(sd * sdl[c]));
+        sd = ns;
+        const double yf = fma(P.l_f, psid, Vy), yr = fma(-P.l_r, psid, Vy);
+        const double num = fma(yf, cd, -(Vx * sd)), den = fma(Vx, cd, yf * sd);  // tan α_f = num/den, tan α_r = yr/Vx
+        const double dv = den * Vx;
+        const int hvx = hi32(Vx);
+        const bool fwd = hvx >= 0;
+        const int bad = ((hvx ^ hvx0[c]) & brake_mask[c]) | ((hi32(dv) & 0x7ff00000) - 0x00100000);
+        double r = rcp_seed(dv);  // 2^-23 seed
+        const double e = fma(-dv, r, 1.0);
+        r = fma(r, fma(e, e, e), r);  // r(1 + e + e²): error e³ = 2^-69
+        const double ta = (num * Vx) * r, ta_r = (yr * den) * r;
+        const double at = fabs(ta), atr = fabs(ta_r);
+        const double cubic = ta * fma(at, fma(-tc[c].c3_f, at, tc[c].c2_f), -P.C_af);  // CAR:256, Horner form
+        const double cubic_r = ta_r * fma(atr, fma(-tc[c].c3_r, atr, tc[c].c2_r), -P.C_ar);
+        const double fyf = ((hi32(den) >= 0) & (at < tc[c].thr_f))
+                               ? cubic  // CAR:255-259
+                               : with_opposite_sign(tc[c].fymax_f, fwd ? hi32(num) : hi32(yf));
+        const double fyr = (fwd & (atr < tc[c].thr_r)) ? cubic_r : with_opposite_sign(tc[c].fymax_r, hi32(yr));
+        const double A = fma(fyf, cd, tc[c].fxf * sd), B = fma(-fyf, sd, tc[c].fxf * cd);
+        double psid_n = fma(D.cI1, A, fma(-D.cI2, fyr, psid));                 // CAR:322,326
+        double Vy_n = fma(D.cm, A + fyr, fma(-dpsi[c], Vx, Vy));             // CAR:323,328
+        // CAR:308,324,327: −c_m·fx_aero = −c_m C_D1 Vx − copysign(c_m C_D0, Vx)
+        double Vx_n = fma(D.cm, B + tc[c].fxr, fma(dpsi[c], Vy, fma(Vx, D.kx, with_opposite_sign(D.cmCD0, hvx))));
+        gen[c] = gen[c] | (bad < 0);
+        if (gen[c]) {  // rare: redo THIS sub-step on the general path from the un-advanced state, stay there
+          const VelOut o = vel_substep_general(P, ddt, accel[c], bk[c], split[c],
+                                               fma((double)(i + 1), dlt[c], car[c].delta), sg[c], Vx, Vy, psid);
+          Vx_n = o.Vx, Vy_n = o.Vy, psid_n = o.psid, sg[c] = o.sg;
+        }
+        car[c].Vx = Vx_n, car[c].Vy = Vy_n, car[c].psid = psid_n, car[c].sd = sd, car[c].cd = cd;
+        dpsi[c] = psid_n * ddt;
+        sm.ring[vw][slot][c][0][lane] = Vx_n;
+        sm.ring[vw][slot][c][1][lane] = Vy_n;
+        sm.ring[vw][slot][c][2][lane] = dpsi[c];
+      }
+      const bool last = i + 1 == nsub;
+      if (last) {
+#pragma unroll
+        for (int c = 0; c < NCARS; ++c) {
+          car[c].delta = fma((double)nsub, dlt[c], car[c].delta);  // CAR:301 summed
+          car[c].trig_valid = !gen[c];                              // the δ recurrence was not advanced exactly: resync
+          // end-of-step extras for the trajectory log. ext[t & 1] was last read at the end of step t − 2, which the
+          // pose warp has passed: this warp is at most RING = 16 sub-steps ahead of it
+          sm.ext[vw][t & 1][c][0][lane] = car[c].psid;
+          sm.ext[vw][t & 1][c][1][lane] = car[c].delta;
+          sm.ext[vw][t & 1][c][2][lane] = act[2 * c + 1];  // pedal (CAR:297, state[8])
+        }
+        if (t + 1 == T) sm.fin[vw][lane] = cc;
+      }
+      if ((g % GROUP) == GROUP - 1 || (last && t + 1 == T)) {  // group complete (or the rollout is): hand it over
+        __syncwarp();
+        if (lane == 0) bar_arrive(&sm.full[vw][grp]);
+      }
+    }
+  }
+}
+
+template <int NCARS>
+__device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm,
+                                          const TrackView &tr, int kbase, int nvw, int lane) {
+  constexpr int SS = 8 * NCARS;
+  const int nsub = env.nsub, T = a.T;
+  const double ddt = env.ddt;
+  PoseCar pc[VW][NCARS];
+  double cost[VW];
+#pragma unroll
+  for (int v = 0; v < VW; ++v) {
+    cost[v] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCARS; ++c) {
+      pc[v][c].x = __ldg(a.state0 + 8 * c + 0), pc[v][c].y = __ldg(a.state0 + 8 * c + 1);
+      pc[v][c].psi = __ldg(a.state0 + 8 * c + 2), pc[v][c].sp = 0.0, pc[v][c].cp = 1.0;
+    }
+  }
+  int g = 0;
+  for (int t = 0; t < T; ++t) {
+    if ((t % 5) == 0) {  // re-synchronise the heading recurrence (as MODE 3 does every 5th control step)
+#pragma unroll
+      for (int v = 0; v < VW; ++v)
+#pragma unroll
+        for (int c = 0; c < NCARS; ++c) {
+          double psi = pc[v][c].psi;
+          if (fabs(psi) > CUDART_PI) {  // callers may hand in any heading; CAR:330 keeps it in (−π, π] afterwards
+            const double kk = rint(psi * 0.15915494309189535);
+            psi = fma(-kk, 6.283185307179586, psi);
+            psi = fma(-kk, 2.4492935982947064e-16, psi);
+            pc[v][c].psi = psi;
+          }
+          sincos_pi(psi, &pc[v][c].sp, &pc[v][c].cp);
+        }
+    }
+    double vx_end[VW][NCARS], vy_end[VW][NCARS];
+    for (int i = 0; i < nsub; ++i, ++g) {
+      const int slot = g % RING, grp = slot / GROUP;
+      if ((g % GROUP) == 0) {
+#pragma unroll
+        for (int v = 0; v < VW; ++v)
+          if (v < nvw) bar_wait(&sm.full[v][grp], (unsigned)((g / RING) & 1));
+      }
+#pragma unroll
+      for (int v = 0; v < VW; ++v)
+#pragma unroll
+        for (int c = 0; c < NCARS; ++c) {
+          const double Vx = sm.ring[v][slot][c][0][lane], Vy = sm.ring[v][slot][c][1][lane];
+          const double dpsi = sm.ring[v][slot][c][2][lane];
+          PoseCar &p = pc[v][c];
+          p.psi += dpsi;  // CAR:329 (wrapped once per step below)
+          double sdp, cdp;
+          sincos_tiny(dpsi, &sdp, &cdp);
+          if ((0x3F9EB851 - (hi32(dpsi) & 0x7fffffff)) < 0) {  // |Ψ̇δt| > 0.03 / NaN
+            const SinCos o = sincos_increment_general(dpsi);
+            sdp = o.s, cdp = o.c;
+          }
+          const double nsp = fma(p.sp, cdp, p.cp * sdp);
+          p.cp = fma(p.cp, cdp, -(p.sp * sdp));
+          p.sp = nsp;
+          p.x = fma(fma(Vx, p.cp, -(Vy * p.sp)), ddt, p.x);  // CAR:331
+          p.y = fma(fma(Vx, p.sp, Vy * p.cp), ddt, p.y);     // CAR:332
+          vx_end[v][c] = Vx, vy_end[v][c] = Vy;
+        }
+      const bool fin = i + 1 == nsub && t + 1 == T;
+      if ((g % GROUP) == GROUP - 1 || fin) {  // every lane has read the group: give it back
+        __syncwarp();
+        if (lane == 0 && !fin) {
+#pragma unroll
+          for (int v = 0; v < VW; ++v)
+            if (v < nvw) bar_arrive(&sm.empty[v][grp]);
+        }
+      }
+    }
+    // ---- end of the control step: heading wrap (CAR:330), reward (CAR:201-213 / MCR:145-158), log ----
+#pragma unroll
+    for (int v = 0; v < VW; ++v) {
+      double s[SS];
+#pragma unroll
+      for (int c = 0; c < NCARS; ++c) {
+        PoseCar &p = pc[v][c];
+        if (fabs(p.psi) > CUDART_PI) {
+          const double kk = rint(p.psi * 0.15915494309189535);
+          p.psi = fma(-kk, 6.283185307179586, p.psi);
+          p.psi = fma(-kk, 2.4492935982947064e-16, p.psi);
+        }
+        s[8 * c + 0] = p.x, s[8 * c + 1] = p.y, s[8 * c + 2] = p.psi;
+        s[8 * c + 3] = vx_end[v][c], s[8 * c + 4] = vy_end[v][c];
+      }
+      double rew = 0.0;
+#pragma unroll
+      for (int c = 0; c < NCARS; ++c) {
+        rew += car_reward<3>(env.car[c], env.cos_blimit[c], tr, s + 8 * c);
+#pragma unroll
+        for (int j = c + 1; j < NCARS; ++j) {
+          const double dx = s[8 * j] - s[8 * c], dy = s[8 * j + 1] - s[8 * c + 1];
+          const double dd = sqrt(dx * dx + dy * dy);
+          rew += -dd;
+          if (dd <= 4.0) rew += -11000.0;  // MCR:153-155 (docstring says −7000; code is −11000)
+        }
+      }
+      cost[v] -= rew;  // UTL:137-138
+      const int k = kbase + v * 32 + lane;
+      if (a.traj && v < nvw && k < a.K) {
+#pragma unroll
+        for (int c = 0; c < NCARS; ++c) {
+          s[8 * c + 5] = sm.ext[v][t & 1][c][0][lane], s[8 * c + 6] = sm.ext[v][t & 1][c][1][lane];
+          s[8 * c + 7] = sm.ext[v][t & 1][c][2][lane];
+        }
+#pragma unroll
+        for (int q = 0; q < SS; ++q) a.traj[((size_t)k * SS + q) * T + t] = s[q];  // UTL:139-141
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VW; ++v) {
+    const int k = kbase + v * 32 + lane;
+    if (v < nvw && k < a.K) a.costs[k] = cost[v] + sm.fin[v][lane];  // POL:274-275
+  }
+}
+
+template <int NCARS>
+__global__ void __launch_bounds__(CTA, NCARS == 1 ? 7 : 1) rollout_car_split_kernel(const __grid_constant__ CarEnvArgs env,
+                                                                 const __grid_constant__ RolloutArgs a,
+                                                                 const int *stop) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (stop && *stop) return;
+  SplitSmem<NCARS> &sm = *reinterpret_cast<SplitSmem<NCARS> *>(smem_raw);
+  double *trk_s = reinterpret_cast<double *>(smem_raw + sizeof(SplitSmem<NCARS>));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int kbase = blockIdx.x * (32 * VW);
+  const int nvw = min(VW, (a.K - kbase + 31) / 32);  // velocity warps of this CTA that own at least one rollout
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int v = 0; v < VW; ++v)
+#pragma unroll
+      for (int q = 0; q < NGROUP; ++q) ptx::mbarrier_init(&sm.full[v][q], 1), ptx::mbarrier_init(&sm.empty[v][q], 1);
+    ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+  }
+  const long long t_begin = a.warp_cycles ? clock64() : 0;
+  for (int i = threadIdx.x; i < 3 * env.n_trk; i += blockDim.x) trk_s[i] = env.trk[i];
+  __syncthreads();
+  const TrackView tr{trk_s, trk_s + env.n_trk, trk_s + 2 * env.n_trk, env.n_trk,
+                     env.lut, env.lut_x0, env.lut_y0, env.lut_inv_c, env.lut_nx, env.lut_ny};
+  if (w < VW) {
+    if (w < nvw) velocity_warp<NCARS>(env, a, sm, w, min(kbase + w * 32 + lane, a.K - 1), lane);  // padding lanes copy the last rollout
+  } else {
+    pose_warp<NCARS>(env, a, sm, tr, kbase, nvw, lane);
+  }
+  if (a.warp_cycles && lane == 0) a.warp_cycles[blockIdx.x * (VW + 1) + w] = clock64() - t_begin;
+}
+
+}  // namespace
+
+int rollout_split_max_cars() { return 3; }
+
+// returns 0 when the configuration is not covered (the caller falls back to the thread-per-rollout kernel)
+int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, const int *stop, cudaStream_t st) {
+  const int grid = (a.K + 32 * VW - 1) / (32 * VW);
+  const size_t trk = sizeof(double) * 3 * env.n_trk;
+#define MPOPIS_SPLIT(N)                                                                                              \
+  case N: {                                                                                                          \
+    const size_t smem = sizeof(SplitSmem<N>) + trk;                                                                  \
+    if (smem > 200 * 1024) return 0;                                                                                 \
+    cudaFuncSetAttribute(rollout_car_split_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    rollout_car_split_kernel<N><<<grid, CTA, smem, st>>>(env, a, stop);                                             \
+    return 1;                                                                                                        \
+  }
+  switch (env.n_cars) {
+    MPOPIS_SPLIT(1)
+    MPOPIS_SPLIT(2)
+    MPOPIS_SPLIT(3)
+  }
+#undef MPOPIS_SPLIT
+  return 0;
+}
+
+}  // namespace mpopis

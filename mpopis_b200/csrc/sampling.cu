@@ -37,10 +37,14 @@ __device__ __forceinline__ void philox_u2(uint64_t seed, uint32_t k, uint32_t j,
 }
 
 // grid: (ceil(K/256), ceil(cs/2)); thread -> (sample k, pair j); writes rows 2j, 2j+1 coalesced in k
+// step_dev (nullable): the control-step counter lives in device memory so that a captured CUDA graph of the control
+// step replays with the right counter; `step` is used when it is null (parity surface sample_normals).
 __global__ void __launch_bounds__(256) philox_normals_kernel(double *Z, long long ldk, int cs, int K,
                                                               long long k0, uint64_t seed, uint32_t step,
-                                                              uint32_t iter, const int *stop) {
+                                                              const unsigned *step_dev, uint32_t iter,
+                                                              const int *stop) {
   if (stop && *stop) return;
+  if (step_dev) step = *step_dev;
   const int k = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (k >= K) return;
   double u1, u2;
@@ -53,14 +57,16 @@ __global__ void __launch_bounds__(256) philox_normals_kernel(double *Z, long lon
 }
 
 void launch_philox_normals(double *Z, long long ldk, int cs, int K, long long k0, uint64_t seed,
-                           uint32_t step, uint32_t iter, const int *stop, cudaStream_t s) {
+                           uint32_t step, const unsigned *step_dev, uint32_t iter, const int *stop,
+                           cudaStream_t s) {
   dim3 grid((K + 255) / 256, (cs + 1) / 2);
-  philox_normals_kernel<<<grid, 256, 0, s>>>(Z, ldk, cs, K, k0, seed, step, iter, stop);
+  philox_normals_kernel<<<grid, 256, 0, s>>>(Z, ldk, cs, K, k0, seed, step, step_dev, iter, stop);
 }
 
-__global__ void philox_uniforms_kernel(double *u, int K, uint64_t seed, uint32_t step, uint32_t iter,
-                                       const int *stop) {
+__global__ void philox_uniforms_kernel(double *u, int K, uint64_t seed, uint32_t step, const unsigned *step_dev,
+                                       uint32_t iter, const int *stop) {
   if (stop && *stop) return;
+  if (step_dev) step = *step_dev;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
   double u1, u2;
@@ -68,9 +74,9 @@ __global__ void philox_uniforms_kernel(double *u, int K, uint64_t seed, uint32_t
   u[i] = u1;
 }
 
-void launch_philox_uniforms(double *u, int K, uint64_t seed, uint32_t step, uint32_t iter, const int *stop,
-                            cudaStream_t s) {
-  philox_uniforms_kernel<<<(K + 255) / 256, 256, 0, s>>>(u, K, seed, step, iter, stop);
+void launch_philox_uniforms(double *u, int K, uint64_t seed, uint32_t step, const unsigned *step_dev, uint32_t iter,
+                            const int *stop, cudaStream_t s) {
+  philox_uniforms_kernel<<<(K + 255) / 256, 256, 0, s>>>(u, K, seed, step, step_dev, iter, stop);
 }
 
 // E[r][k] = Σ_{j in block(r), j<=r} L[r][j] Z[j][k] for block-diagonal L with bs x bs blocks

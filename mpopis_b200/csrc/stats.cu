@@ -839,8 +839,9 @@ void launch_ctrl_vec(const double *Sinv, int cs, const double *U_orig, double ga
 __global__ void finalize_control_kernel(const double *__restrict__ wsum, const double *__restrict__ U_orig,
                                         const double *__restrict__ U_cur, int cs, int as, int T,
                                         double *__restrict__ U_next, double *__restrict__ control,
-                                        const double *__restrict__ bounds) {
+                                        const double *__restrict__ bounds, unsigned *step_dev) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0 && step_dev) *step_dev += 1;  // every Philox draw of this control step has been made
   if (r >= cs) return;
   const double wc = U_orig[r] + (wsum[r] + (U_cur[r] - U_orig[r]) * wsum[cs]);
   if (r < as) control[r] = fmin(fmax(wc, bounds ? bounds[r] : -1.0), bounds ? bounds[as + r] : 1.0);  // UTL:91
@@ -852,8 +853,13 @@ __global__ void finalize_control_kernel(const double *__restrict__ wsum, const d
   }
 }
 void launch_finalize_control(const double *wsum, const double *U_orig, const double *U_cur, int cs, int as, int T,
-                             double *U_next, double *control, const double *bounds, cudaStream_t s) {
-  finalize_control_kernel<<<(cs + 127) / 128, 128, 0, s>>>(wsum, U_orig, U_cur, cs, as, T, U_next, control, bounds);
+                             double *U_next, double *control, const double *bounds, unsigned *step_dev,
+                             cudaStream_t s) {
+  finalize_control_kernel<<<(cs + 127) / 128, 128, 0, s>>>(wsum, U_orig, U_cur, cs, as, T, U_next, control, bounds,
+                                                          step_dev);
 }
+
+__global__ void set_scalar_kernel(double *dst, double value) { *dst = value; }
+void launch_set_scalar(double *dst, double value, cudaStream_t s) { set_scalar_kernel<<<1, 1, 0, s>>>(dst, value); }
 
 }  // namespace mpopis

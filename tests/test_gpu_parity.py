@@ -44,7 +44,7 @@ def pair(gpu_bound, orc, policy, env, K, T, N=10, variant=None, **kw):
 # ---------------------------------------------------------------------------------------------------
 # 1. golden fixtures
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 def test_golden_rollout_costs(gpu_bound, variant):
     env = make_env("car")
     g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, 64, 50)), env, "gmppi")
@@ -93,7 +93,7 @@ def test_golden_control_step(gpu_bound, policy, envname):
 # ---------------------------------------------------------------------------------------------------
 # 2. live oracle, same seeded inputs
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 @pytest.mark.parametrize("n_cars", [1, 2, 3])
 def test_rollout_costs_vs_oracle(gpu_bound, orc, variant, n_cars):
     env = make_env("car", n_cars)
@@ -109,7 +109,7 @@ def test_rollout_costs_vs_oracle(gpu_bound, orc, variant, n_cars):
     print(f"threshold flips: {flips} of {K * len(states)}")
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 4])
 def test_rollout_costs_reversing_car_and_wrap(gpu_bound, orc, variant):
     """Vx <= 0 takes the literal slip-angle path (variant 0) or the quadrant-aware ratio form (variant 3, with
     the v3 repair when Vx changes sign while braking); |Ψ| crosses π (heading wrap)."""
@@ -500,3 +500,26 @@ def test_target_config_one_step_vs_oracle(gpu_bound, orc):
     np.testing.assert_allclose(Sg, Sc, rtol=1e-6, atol=1e-12)
     assert abs(g.last_shrinkage() - c.last_shrinkage()) < 1e-8
     print(f"K=65536: |Δcontrol|={np.max(np.abs(cg - cc)):.2e} |ΔU|={np.max(np.abs(ug - uc)):.2e} cost flips={flips}")
+
+
+@pytest.mark.parametrize("n_cars,K,T", [(1, 4099, 50), (1, 70, 23), (1, 33, 7), (2, 333, 30), (3, 375, 50), (3, 64, 11)])
+def test_warp_specialised_rollouts_equal_the_thread_per_rollout_kernel(gpu_bound, n_cars, K, T):
+    """rollout_variant 4 (rollout_split.cu: velocity warps + pose/reward warps through a shared-memory ring) against
+    variant 3 (one thread per rollout): the same expressions in the same order on every sub-step, so the costs agree to
+    rounding (1e-12) except on the rare control steps the two variants repair differently (whole step vs from the
+    offending sub-step on), and the trajectory log — the per-step states both write — agrees as well. Ragged K (partly
+    filled last warp / single velocity warp in the last CTA) and horizons that do not fill the ring's groups included."""
+    env = make_env("car", n_cars)
+    g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, K, T, log_trajectories=True)), env, "gmppi")
+    rng = np.random.Generator(np.random.Philox(key=K + T))
+    E = rng.standard_normal((g.cs, K)) * np.tile(np.array([0.25, 0.32] * n_cars), T)[:, None]
+    U = rng.uniform(-0.3, 0.3, g.cs)
+    out = {}
+    for variant in (3, 4):
+        g.set_option("rollout_variant", variant)
+        out[variant] = (g.rollout_costs(env.state, 0, U, U, E), g.fetch(costs=False, weights=False, traj=True)["traj"])
+    r = rel(out[4][0], out[3][0])
+    assert (r > 1e-12).sum() <= max(1, K // 200), f"{(r > 1e-12).sum()} of {K} costs differ (max rel {r.max():.2e})"
+    assert (r > TIGHT).sum() <= max(1, K // 1000)
+    tr = np.abs(out[4][1] - out[3][1]) / np.maximum(1.0, np.abs(out[3][1]))
+    assert np.quantile(tr, 0.999) < 1e-9, "trajectory logs differ"

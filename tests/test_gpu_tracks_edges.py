@@ -31,7 +31,7 @@ def test_track_lut_is_exact_on_every_track(gpu_bound, orc, name, sf):
         np.stack([trk.xs, trk.ys], 1) + rng.normal(0, 1e-9, (trk.xs.size, 2)),           # on the sampled points
         0.5 * (np.stack([trk.xs, trk.ys], 1) + np.roll(np.stack([trk.xs, trk.ys], 1), 1, 0)),  # equidistant mid-points
     ])
-    for variant in (0, 3, 1):  # with (0, 3) and without (1) the table
+    for variant in (0, 3, 4, 1):  # with (0, 3) and without (1) the table
         g.set_option("rollout_variant", variant)
         gi, gj, gd, gw = g.track_query(pos)
         ci, cj, cd, cw = c.track_query(pos)
