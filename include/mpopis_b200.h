@@ -249,6 +249,7 @@ int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out);
  * process-wide: 0 = DFMA register tile, 1 = DMMA 32-row blocks, 2 = DMMA column tiles with cp.async),
  * "moments_small" (1 = single-CTA moment chain for <= 512 columns, the default; 0 = the multi-kernel chain). */
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value);
+int mpopis_b200_get_option(mpopis_t *h, const char *key, double *value_out);
 
 /* Profiling aid: with set_option("rollout_profile", 1) every warp of the rollout kernel records the clock64() cycles
  * it spent in the kernel; this returns the values of the most recent rollout launch (ceil(K_local/32) entries at most

@@ -89,6 +89,7 @@ PRODUCT_ONLY = {
     "loopback_destroy": (C.c_int, [C.c_void_p]),
     "comm_init_loopback": (C.c_int, [_H, C.c_void_p]),
     "set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
+    "get_option": (C.c_int, [_H, C.c_char_p, _D]),
     "resident_reset": (C.c_int, [_H, _D, C.c_int64, _D]),
     "resident_plan": (C.c_int, [_H, C.c_int32]),
     "resident_read": (C.c_int, [_H, _D, _D, _D, _I32]),

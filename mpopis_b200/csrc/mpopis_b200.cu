@@ -90,6 +90,12 @@ struct mpopis_handle {
          *d_pSig = nullptr, *d_dw = nullptr, *d_C = nullptr, *d_ns = nullptr, *d_reward = nullptr,
          *d_ones = nullptr;
   int num_sms = 0;
+  // CUDA graph of one control step (plan without injected noise): the launch sequence is static — early stop and
+  // Cholesky failure are device flags, the Philox control-step counter lives in device memory (d_step)
+  cudaGraphExec_t gexec = nullptr;
+  bool graph_enabled = true, capturing = false;
+  long long graph_launches = 0;
+  unsigned *d_step = nullptr;
   bool use_select = false;  // :cemppi: select.cu path (sharded, or K above the single-CTA sort)
   long long *d_env_t = nullptr, *d_warp_cycles = nullptr;  // d_warp_cycles: "rollout_profile" option
   unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
@@ -128,6 +134,11 @@ struct mpopis_handle {
 };
 
 namespace {
+
+// timing events inside a captured control step are EXTERNAL event-record nodes: they can be timed after a replay
+cudaError_t record(mpopis_t *h, cudaEvent_t e) {
+  return h->capturing ? cudaEventRecordWithFlags(e, h->st, cudaEventRecordExternal) : cudaEventRecord(e, h->st);
+}
 
 void mark(mpopis_t *h, const char *name) {
   if (!h->trace) return;
@@ -355,6 +366,14 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
 
 int cma_update(mpopis_t *h, int n_iter);  // cma.cu-style section below
 
+// factor the initial Σ once per set_sigma() — outside the (possibly captured) control step
+void factor_sigma0(mpopis_t *h) {
+  if (h->L0_valid) return;
+  launch_chol(h->d_Sigma0, h->cs, nullptr, h->d_Lt0, h->d_cholW, h->info(), 1000, nullptr, h->st);
+  h->launches += 1;
+  h->L0_valid = true;
+}
+
 // The AIS loop + final control, entirely on h->st. Z_host: injected normals (cs x K x N col-major)
 // or nullptr for the Philox generator; u_host: injected PMC uniforms (K x (N-1)) or nullptr.
 int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
@@ -367,7 +386,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     return fail(MPOPIS_ERR_BAD_ARG, "BoundsError: CMA linear index exceeds cs*m_elite (POL:593)");
   if (pol == MPOPIS_POLICY_PMCMPPI && N > 1 && Z_host && !u_host)
     return fail(MPOPIS_ERR_BAD_ARG, "pmcmppi with injected noise needs resample_u");
-  CU(cudaEventRecord(h->ev[0], st));
+  CU(record(h, h->ev[0]));
   h->marks.clear();
   mark(h, "begin");
   CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 2, st));  // stop, its (info is sticky until read)
@@ -378,11 +397,6 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     launch_set_scalar(h->d_sigma, h->cma.sigma, st);  // a kernel, not a pageable H2D copy: graph-capturable
     CU(cudaMemsetAsync(h->d_psig, 0, sizeof(double) * cs, st));
     CU(cudaMemsetAsync(h->d_pSig, 0, sizeof(double) * cs, st));
-  }
-  if (!h->L0_valid) {  // factor the initial Σ once per set_sigma()
-    launch_chol(h->d_Sigma0, cs, nullptr, h->d_Lt0, h->d_cholW, h->info(), 1000, nullptr, st);
-    h->launches += 1;
-    h->L0_valid = true;
   }
   const double *Lt = h->d_Lt0;
   int bs = h->sigma_bs;
@@ -419,9 +433,9 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     h->launches += 2;
     mark(h, "sample");
     // --- rollouts (POL:452 -> POL:261-278) ---
-    CU(cudaEventRecord(h->ev[2 + 2 * n], st));
+    CU(record(h, h->ev[2 + 2 * n]));
     if (int rc = launch_rollouts(h, h->d_U_cur, h->d_U_orig, bvec)) return rc;
-    CU(cudaEventRecord(h->ev[3 + 2 * n], st));
+    CU(record(h, h->ev[3 + 2 * n]));
     if (!Z_host && n + 1 < N) {
       // The next iteration's normals depend on nothing but (seed, step, n+1): draw them on the side stream
       // while the latency-bound adaptation kernels (sort passes, Cholesky, moment finalisation) leave most
@@ -509,7 +523,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
                           h->cfg.env == MPOPIS_ENV_EXTERNAL ? h->d_ext_bounds : nullptr, h->d_step, st);
   h->launches += 1;
   mark(h, "final");
-  CU(cudaEventRecord(h->ev[1], st));
+  CU(record(h, h->ev[1]));
   CU(cudaGetLastError());
   h->step += 1;
   h->timing_valid = false;
@@ -528,6 +542,49 @@ int finish_timing(mpopis_t *h) {
   h->last_rollout_ms = r;
   h->timing_valid = true;
   dump_marks(h);
+  return 0;
+}
+
+void drop_graph(mpopis_t *h) {
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  h->gexec = nullptr;
+}
+
+// One control step on the engine's own Philox stream: replayed from a CUDA graph when the sequence is capturable
+// (no injected noise, no host callback, NCCL or no communicator, tracer off), launched kernel by kernel otherwise.
+// Any capture/instantiate failure falls back to eager launches for the lifetime of the handle.
+int plan_step(mpopis_t *h) {
+  factor_sigma0(h);
+  const bool can = h->graph_enabled && !h->trace && !h->comm.host_synchronous() && h->cfg.env != MPOPIS_ENV_EXTERNAL;
+  if (!can) return plan_core(h, nullptr, nullptr);
+  if (!h->gexec) {
+    const long long l0 = h->launches, step0 = h->step;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      h->graph_enabled = false;
+      return plan_core(h, nullptr, nullptr);
+    }
+    h->capturing = true;
+    const int rc = plan_core(h, nullptr, nullptr);
+    h->capturing = false;
+    const cudaError_t e = cudaStreamEndCapture(h->st, &g);
+    h->graph_launches = h->launches - l0;
+    h->launches = l0, h->step = step0;  // nothing ran yet
+    if (rc || e != cudaSuccess || !g || cudaGraphInstantiate(&h->gexec, g, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (g) cudaGraphDestroy(g);
+      h->gexec = nullptr, h->graph_enabled = false;
+      if (getenv("MPOPIS_GRAPH_VERBOSE")) fprintf(stderr, "[mpopis] graph capture failed (rc=%d, %s): eager launches\n", rc, cudaGetErrorString(e));
+      return plan_core(h, nullptr, nullptr);
+    }
+    cudaGraphDestroy(g);
+  }
+  CU(cudaGraphLaunch(h->gexec, h->st));
+  h->launches += h->graph_launches;
+  h->last_its_launched = h->N;
+  h->step += 1;
+  h->timing_valid = false;
   return 0;
 }
 
@@ -735,6 +792,8 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   const size_t cs = h->cs, K = h->K, Kloc = h->Kloc, ld = h->ldk;
   TRY(dalloc(&h->d_state, h->ss));
   TRY(dalloc(&h->d_env_t, 1));
+  TRY(dalloc(&h->d_step, 1));
+  if (const char *e = getenv("MPOPIS_GRAPH")) h->graph_enabled = atoi(e) != 0;
   TRY(dalloc(&h->d_U_orig, cs));
   TRY(dalloc(&h->d_U_cur, cs));
   TRY(dalloc(&h->d_U_next, cs));
@@ -844,7 +903,9 @@ int mpopis_b200_destroy(mpopis_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->dev);
   if (h->st) cudaStreamSynchronize(h->st);
+  drop_graph(h);
   comm_destroy(h->comm);
+  if (h->d_step) cudaFree(h->d_step);
   void *ptrs[] = {h->d_trk,    h->d_state, h->d_U_orig, h->d_U_cur,  h->d_U_next, h->d_control, h->d_Sigma0,
                   h->d_Sigma,  h->d_Lt,    h->d_Lt0,    h->d_cholW,  h->d_bvec,   h->d_Z,       h->d_E,
                   h->d_stage,  h->d_costs, h->d_w,      h->d_sorted, h->d_X,      h->d_mask,    h->d_part,
@@ -930,6 +991,7 @@ int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params, d
   }
   h->car.dt = dt, h->car.ddt = ddt, h->car.nsub = (int)lrint(dt / ddt);  // CAR:299
   for (int c = 0; c < n_cars; ++c) h->car.der[c] = derive_car(h->car.car[c], ddt);
+  drop_graph(h);  // the env arguments are kernel parameters of the captured step
   h->car.n_cars = n_cars, h->car.n_trk = (int)n_trk;
   if (h->d_trk) cudaFree(h->d_trk), h->d_trk = nullptr;
   if (int rc = dalloc(&h->d_trk, 3 * (size_t)n_trk)) return rc;
@@ -956,6 +1018,7 @@ int mpopis_b200_set_mountaincar_env(mpopis_t *h, const double *p, int64_t max_st
   if (!h || !p) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (h->cfg.env != MPOPIS_ENV_MOUNTAIN_CAR)
     return fail(MPOPIS_ERR_BAD_ARG, "handle was created for a different environment");
+  drop_graph(h);
   h->mc = McEnvArgs{p[0], p[1], p[2], p[3], p[4], p[5], p[6], (long long)max_steps};
   h->env_set = true;
   return 0;
@@ -985,6 +1048,7 @@ int mpopis_b200_set_sigma(mpopis_t *h, const double *Sigma, int64_t n) {
   if (int rc = set_device(h)) return rc;
   CU(cudaMemcpy(h->d_Sigma0, S.data(), sizeof(double) * cs * cs, cudaMemcpyHostToDevice));
   h->L0_valid = false;
+  drop_graph(h);  // sigma_bs selects the E = L·Z kernel of the first iteration
   return 0;
 }
 
@@ -994,6 +1058,7 @@ int mpopis_b200_set_cma(mpopis_t *h, const mpopis_cma_t *cma, const double *ws, 
   if (n_ws != h->K) return fail(MPOPIS_ERR_BAD_ARG, "ws must have num_samples entries");
   if (h->N > 1 && (cma->m_elite < 2 || cma->m_elite > h->K)) return fail(MPOPIS_ERR_BAD_ARG, "m_elite out of range");
   if (int rc = set_device(h)) return rc;
+  drop_graph(h);
   h->cma = *cma;
   h->m_elite = (int)cma->m_elite;
   if (int rc = ensure_elite_capacity(h, h->m_elite)) return rc;
@@ -1004,13 +1069,21 @@ int mpopis_b200_set_cma(mpopis_t *h, const mpopis_cma_t *cma, const double *ws, 
 
 int mpopis_b200_seed(mpopis_t *h, uint64_t seed) {
   if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
-  h->seed = seed;
+  if (int rc = set_device(h)) return rc;
+  h->seed = seed;  // a kernel argument of the captured step: re-capture
   h->step = 0;
+  drop_graph(h);
+  CU(cudaMemsetAsync(h->d_step, 0, sizeof(unsigned), h->st));
   return 0;
 }
 
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
   if (!h || !key) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  drop_graph(h);  // every option changes the captured launch sequence
+  if (!strcmp(key, "graph")) {  // 0: launch every kernel of a control step individually (A/B, debugging)
+    h->graph_enabled = value != 0.0;
+    return 0;
+  }
   if (!strcmp(key, "rollout_variant")) {
     if (value != 0.0 && value != 1.0 && value != 3.0 && value != 4.0)
       return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0 (v3), 1 (literal), 3 (v4) or 4 (v5, warp-specialised)");
@@ -1018,7 +1091,7 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
   }
   else if (!strcmp(key, "rollout_profile")) {  // per-warp clock64() of the rollout kernel, read with warp_cycles()
     if (value != 0.0 && !h->d_warp_cycles) {
-      if (int rc = dalloc(&h->d_warp_cycles, (size_t)h->Kloc / 32 + 2)) return rc;
+      if (int rc = dalloc(&h->d_warp_cycles, 4 * ((size_t)h->Kloc / 32 + 2))) return rc;  // split kernel: 3 warps x 2 per 64
     } else if (value == 0.0 && h->d_warp_cycles) {
       cudaFree(h->d_warp_cycles), h->d_warp_cycles = nullptr;
     }
@@ -1042,6 +1115,19 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
   return 0;
 }
 
+int mpopis_b200_get_option(mpopis_t *h, const char *key, double *value_out) {
+  if (!h || !key || !value_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (!strcmp(key, "rollout_variant")) *value_out = h->rollout_variant;
+  else if (!strcmp(key, "rollout_block")) *value_out = h->rollout_block;
+  else if (!strcmp(key, "rollout_stage")) *value_out = h->rollout_stage;
+  else if (!strcmp(key, "moments_small")) *value_out = h->moments_small;
+  else if (!strcmp(key, "graph")) *value_out = h->graph_enabled;
+  else if (!strcmp(key, "graph_active")) *value_out = h->gexec != nullptr;
+  else if (!strcmp(key, "ce_select")) *value_out = h->use_select;
+  else return fail(MPOPIS_ERR_BAD_ARG, "unknown option %s", key);
+  return 0;
+}
+
 int mpopis_b200_plan_with_noise(mpopis_t *h, const double *state, int64_t env_t, double *U_inout,
                                 const double *Z, const double *resample_u, double *control_out,
                                 int32_t *its_run_out) {
@@ -1049,7 +1135,8 @@ int mpopis_b200_plan_with_noise(mpopis_t *h, const double *state, int64_t env_t,
   if (int rc = set_device(h)) return rc;
   CU(cudaMemsetAsync(h->info(), 0, sizeof(int), h->st));
   if (int rc = upload_inputs(h, state, env_t, U_inout)) return rc;
-  if (int rc = plan_core(h, Z, resample_u)) {
+  if (Z || resample_u) factor_sigma0(h);
+  if (int rc = (Z || resample_u) ? plan_core(h, Z, resample_u) : plan_step(h)) {
     cudaStreamSynchronize(h->st);
     return rc;
   }
@@ -1081,6 +1168,7 @@ int mpopis_b200_plan_external(mpopis_t *h, double *U_inout, mpopis_rollout_fn ro
   CU(cudaMemsetAsync(h->info(), 0, sizeof(int), h->st));
   if (int rc = upload_inputs(h, nullptr, 0, U_inout)) return rc;
   h->ext_fn = rollout, h->ext_user = user;
+  factor_sigma0(h);
   const int rc = plan_core(h, Z, resample_u);
   h->ext_fn = nullptr, h->ext_user = nullptr;
   if (rc) {
@@ -1357,7 +1445,7 @@ int mpopis_b200_warp_cycles(mpopis_t *h, int64_t *cycles_out, int64_t n) {
   if (!h || !cycles_out || n < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (!h->d_warp_cycles) return fail(MPOPIS_ERR_BAD_ARG, "set_option(\"rollout_profile\", 1) first");
   if (int rc = set_device(h)) return rc;
-  const int64_t nw = (h->Kloc + 31) / 32;
+  const int64_t nw = 4 * ((int64_t)h->Kloc / 32 + 2);
   CU(cudaStreamSynchronize(h->st));
   CU(cudaMemcpy(cycles_out, h->d_warp_cycles, sizeof(long long) * (size_t)(n < nw ? n : nw), cudaMemcpyDeviceToHost));
   return 0;
@@ -1428,7 +1516,7 @@ int mpopis_b200_resident_reset(mpopis_t *h, const double *state, int64_t env_t, 
 int mpopis_b200_resident_plan(mpopis_t *h, int32_t advance_env) {
   if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (int rc = set_device(h)) return rc;
-  if (int rc = plan_core(h, nullptr, nullptr)) return rc;
+  if (int rc = plan_step(h)) return rc;
   if (advance_env) env_step_device(h, h->d_control);  // env(act), car_example.jl:205-207
   CU(cudaMemcpyAsync(h->d_U_orig, h->d_U_next, sizeof(double) * h->cs, cudaMemcpyDeviceToDevice, h->st));
   return 0;

@@ -18,14 +18,16 @@
 //
 // 65 536 rollouts are then 2048 latency-bound warps whose chain is shorter (no pose/reward work in it) plus 1024
 // throughput-rich warps that fill the FP64 pipe while the former wait: 5.2 warps per scheduler instead of 3.46, with
-// the same arithmetic. The ring is sub-step granular (16 slots of 3 x 32 doubles per velocity warp, groups of 4 slots
-// handed over with mbarriers: full[4] / empty[4], one elected lane arrives after __syncwarp), so the pose warp trails
-// by a few sub-steps and nothing is ever rolled back: the velocity sub-step is written for every Vx != 0 as in MODE 3
-// (car_model.cuh: car_step_spec), its validity conditions are checked PER SUB-STEP, and a lane that leaves them
-// (Vx changes sign while braking, den·Vx denormal, |δ| > 0.78, a standstill) finishes the control step on the general
-// path (all branches, libm where the un-wrapped angle matters) — sub-step by sub-step, in place.
+// the same arithmetic. The ring holds 15 sub-step slots of 3 x 32 doubles per velocity warp, handed over in groups of
+// 5 sub-steps with mbarriers (full[3] / empty[3], one elected lane arrives after __syncwarp): both roles run a group
+// as ONE straight-line block — the velocity warp with every constant in (uniform) registers and no call or barrier
+// inside, the pose warp with the 5 x 2 short sin/cos polynomials of a group overlapping. The velocity sub-step is
+// written for every Vx != 0 as in MODE 3 (car_model.cuh: car_step_spec); its validity conditions are accumulated over
+// the group BEFORE it is published, and a lane that leaves them (Vx changes sign while braking, den·Vx denormal,
+// |δ| > 0.78, a standstill) redoes that group — and the rest of the control step — on the general path (all branches,
+// libm where the un-wrapped angle matters). Nothing published is ever rolled back.
 // Arithmetic: identical to MODE 3 on every sub-step both consider valid (same expressions, same fma placement);
-// control steps MODE 3 would repair as a whole are here repaired from the offending sub-step on — both are the
+// control steps MODE 3 would repair as a whole are here repaired from the offending group on — both are the
 // reference's mathematics to ~1e-13, tests/test_gpu_parity.py pins each against the oracle.
 #include <cuda/ptx>
 #include <math_constants.h>
@@ -39,8 +41,8 @@ namespace {
 
 namespace ptx = cuda::ptx;
 
-constexpr int RING = 16, GROUP = 4, NGROUP = RING / GROUP;  // sub-step slots per velocity warp
-constexpr int VW = 2;                                       // velocity warps per CTA (= rollouts per pose lane)
+constexpr int GROUP = 5, NGROUP = 3, RING = GROUP * NGROUP;  // sub-step slots per velocity warp, handed over in groups
+constexpr int VW = 2;                                         // velocity warps per CTA (= rollouts per pose lane)
 constexpr int CTA = 32 * (VW + 1);
 
 template <int NCARS>
@@ -51,47 +53,56 @@ struct SplitSmem {
   uint64_t full[VW][NGROUP], empty[VW][NGROUP];
 };
 
-__device__ __forceinline__ void bar_wait(uint64_t *bar, unsigned parity) {
+__device__ __forceinline__ void bar_wait(uint64_t *bar, unsigned parity, long long *waited = nullptr) {
+  if (ptx::mbarrier_try_wait_parity(bar, parity)) return;
+  const long long t0 = waited ? clock64() : 0;
   while (!ptx::mbarrier_try_wait_parity(bar, parity)) {
   }
+  if (waited) *waited += clock64() - t0;
 }
 __device__ __forceinline__ void bar_arrive(uint64_t *bar) {
   (void)ptx::mbarrier_arrive(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar);
 }
 
-// One Euler sub-step of the velocity recurrence on the general path (car_step_fast's loop body, CAR:301-328, without
-// the pose): every branch the reference's arithmetic can take. Rare (a lane that left the straight-line conditions),
-// so it is kept out of line and recomputes the tyre constants instead of carrying them.
-struct VelOut {
+// GROUP Euler sub-steps of the velocity recurrence on the general path (car_step_fast's loop body, CAR:301-328, without
+// the pose): every branch the reference's arithmetic can take. Rare (a lane that left the straight-line conditions), so
+// it is kept out of line, recomputes the tyre constants instead of carrying them and writes its ring slots itself.
+struct VelState {
   double Vx, Vy, psid, sg;
 };
-__device__ __noinline__ VelOut vel_substep_general(const CarParams &P, double ddt, double accel, double bk, double split,
-                                                   double delta, double sg, double Vx, double Vy, double psid) {
-  double sd, cd;
-  sincos(delta, &sd, &cd);
-  if (!(Vx > 0.0 && sg > 0.0)) {
-    const double sg_now = jl_sign(Vx);
-    if (sg_now != sg) sg = sg_now;  // sign(Vx) flipped: the brake force changes direction (CAR:311)
-  }
-  const TireConsts tc = tire_consts_fast(P, accel, bk, split, sg);
+__device__ __noinline__ VelState vel_group_general(const CarParams &P, double ddt, double accel, double bk, double split,
+                                                   double delta0, double dlt, int i0, VelState st, double *slot0) {
+  double Vx = st.Vx, Vy = st.Vy, psid = st.psid, sg = st.sg;
   const double inv_Izz = 1 / P.Izz, inv_m = 1 / P.m;
-  const double yf = Vy + P.l_f * psid, yr = Vy - P.l_r * psid;
-  double fyf, fyr, fx_aero;
-  if (Vx > 0.0) {
-    fyf = tire_fy_ratio<0>(yf * cd - Vx * sd, Vx * cd + yf * sd, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
-    fyr = tire_fy_ratio<0>(yr, Vx, P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
-  } else {  // reversing / standstill: the un-wrapped slip angle matters, keep the libm sequence (CAR:304-305)
-    fyf = tire_fy_literal(atan2(yf, Vx) - delta, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
-    fyr = tire_fy_literal(atan2(yr, Vx), P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
+  for (int j = 0; j < GROUP; ++j) {
+    const double delta = fma((double)(i0 + j + 1), dlt, delta0);  // CAR:301
+    double sd, cd;
+    sincos(delta, &sd, &cd);
+    if (!(Vx > 0.0 && sg > 0.0)) {
+      const double sg_now = jl_sign(Vx);
+      if (sg_now != sg) sg = sg_now;  // sign(Vx) flipped: the brake force changes direction (CAR:311)
+    }
+    const TireConsts tc = tire_consts_fast(P, accel, bk, split, sg);
+    const double yf = Vy + P.l_f * psid, yr = Vy - P.l_r * psid;
+    double fyf, fyr;
+    if (Vx > 0.0) {
+      fyf = tire_fy_ratio<0>(yf * cd - Vx * sd, Vx * cd + yf * sd, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
+      fyr = tire_fy_ratio<0>(yr, Vx, P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
+    } else {  // reversing / standstill: the un-wrapped slip angle matters, keep the libm sequence (CAR:304-305)
+      fyf = tire_fy_literal(atan2(yf, Vx) - delta, P.C_af, tc.c2_f, tc.c3_f, tc.thr_f, tc.fymax_f);
+      fyr = tire_fy_literal(atan2(yr, Vx), P.C_ar, tc.c2_r, tc.c3_r, tc.thr_r, tc.fymax_r);
+    }
+    const double fx_aero = (P.C_D0 + P.C_D1 * fabs(Vx)) * sg;                              // CAR:308
+    const double psidd = inv_Izz * (P.l_f * (tc.fxf * sd + fyf * cd) - P.l_r * fyr);        // CAR:322
+    const double Vy_dot = inv_m * (fyf * cd + tc.fxf * sd + fyr) - psid * Vx;               // CAR:323
+    const double Vx_dot = inv_m * (tc.fxf * cd - fyf * sd + tc.fxr - fx_aero) + psid * Vy;  // CAR:324
+    psid += psidd * ddt;  // CAR:326
+    Vx += Vx_dot * ddt;   // CAR:327
+    Vy += Vy_dot * ddt;   // CAR:328
+    double *sl = slot0 + (size_t)j * (sizeof(((SplitSmem<1> *)0)->ring[0][0]) / sizeof(double));
+    sl[0] = Vx, sl[32] = Vy, sl[64] = psid * ddt;
   }
-  fx_aero = (P.C_D0 + P.C_D1 * fabs(Vx)) * sg;                                             // CAR:308
-  const double psidd = inv_Izz * (P.l_f * (tc.fxf * sd + fyf * cd) - P.l_r * fyr);        // CAR:322
-  const double Vy_dot = inv_m * (fyf * cd + tc.fxf * sd + fyr) - psid * Vx;               // CAR:323
-  const double Vx_dot = inv_m * (tc.fxf * cd - fyf * sd + tc.fxr - fx_aero) + psid * Vy;  // CAR:324
-  psid += psidd * ddt;  // CAR:326
-  Vx += Vx_dot * ddt;   // CAR:327
-  Vy += Vy_dot * ddt;   // CAR:328
-  return VelOut{Vx, Vy, psid, sg};
+  return VelState{Vx, Vy, psid, sg};
 }
 
 // sin/cos of a heading increment that left the short polynomial's range (a spinning car): rare, out of line
@@ -115,9 +126,9 @@ struct PoseCar {  // pose-side state of one car
 
 template <int NCARS>
 __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm, int vw,
-                                              int k, int lane) {
+                                              int k, int lane, long long *waited) {
   constexpr int AS = 2 * NCARS;
-  const int nsub = env.nsub, T = a.T;
+  const int gps = env.nsub / GROUP, T = a.T;  // groups per control step (the launcher guarantees nsub % GROUP == 0)
   const double ddt = env.ddt;
   VelCar car[NCARS];
 #pragma unroll
@@ -130,7 +141,7 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
   double cc = 0.0, e_next[AS];
 #pragma unroll
   for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)r * a.ldk];
-  int g = 0;  // global sub-step counter of this rollout
+  int gi = 0;  // global group counter of this rollout
   for (int t = 0; t < T; ++t) {
     double act[AS];
 #pragma unroll
@@ -168,79 +179,125 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
       if (!car[c].trig_valid || (t % 5) == 0) sincos_kernel(car[c].delta, &car[c].sd, &car[c].cd);
       dpsi[c] = car[c].psid * ddt;  // Ψ̇δt of the CURRENT Ψ̇: the −Ψ̇Vx / +Ψ̇Vy terms of the next sub-step
     }
-    for (int i = 0; i < nsub; ++i, ++g) {
-      const int slot = g % RING, grp = slot / GROUP;
-      if ((g % GROUP) == 0 && g >= RING) bar_wait(&sm.empty[vw][grp], (unsigned)((g / RING - 1) & 1));
+    for (int q = 0; q < gps; ++q, ++gi) {
+      const int grp = gi % NGROUP;
+      if (gi >= NGROUP) bar_wait(&sm.empty[vw][grp], (unsigned)((gi / NGROUP - 1) & 1), waited);
 #pragma unroll
       for (int c = 0; c < NCARS; ++c) {
         const CarParams &P = env.car[c];
         const CarDerived &D = env.der[c];
-        double Vx = car[c].Vx, Vy = car[c].Vy, psid = car[c].psid, sd = car[c].sd, cd = car[c].cd;
-        // --- straight-line sub-step, valid for every Vx != 0 (car_model.cuh: car_step_spec, same expressions) ---
-        const double ns = fma(sd, cdl[c], cd * sdl[c]);  // sin/cos(δ + rate·δt), CAR:301
-        cd = fma(cd, cdl[c], -(sd * sdl[c]));
-        sd = ns;
-        const double yf = fma(P.l_f, psid, Vy), yr = fma(-P.l_r, psid, Vy);
-        const double num = fma(yf, cd, -(Vx * sd)), den = fma(Vx, cd, yf * sd);  // tan α_f = num/den, tan α_r = yr/Vx
-        const double dv = den * Vx;
-        const int hvx = hi32(Vx);
-        const bool fwd = hvx >= 0;
-        const int bad = ((hvx ^ hvx0[c]) & brake_mask[c]) | ((hi32(dv) & 0x7ff00000) - 0x00100000);
-        double r = rcp_seed(dv);  // 2^-23 seed
-        const double e = fma(-dv, r, 1.0);
-        r = fma(r, fma(e, e, e), r);  // r(1 + e + e²): error e³ = 2^-69
-        const double ta = (num * Vx) * r, ta_r = (yr * den) * r;
-        const double at = fabs(ta), atr = fabs(ta_r);
-        const double cubic = ta * fma(at, fma(-tc[c].c3_f, at, tc[c].c2_f), -P.C_af);  // CAR:256, Horner form
-        const double cubic_r = ta_r * fma(atr, fma(-tc[c].c3_r, atr, tc[c].c2_r), -P.C_ar);
-        const double fyf = ((hi32(den) >= 0) & (at < tc[c].thr_f))
-                               ? cubic  // CAR:255-259
-                               : with_opposite_sign(tc[c].fymax_f, fwd ? hi32(num) : hi32(yf));
-        const double fyr = (fwd & (atr < tc[c].thr_r)) ? cubic_r : with_opposite_sign(tc[c].fymax_r, hi32(yr));
-        const double A = fma(fyf, cd, tc[c].fxf * sd), B = fma(-fyf, sd, tc[c].fxf * cd);
-        double psid_n = fma(D.cI1, A, fma(-D.cI2, fyr, psid));                 // CAR:322,326
-        double Vy_n = fma(D.cm, A + fyr, fma(-dpsi[c], Vx, Vy));             // CAR:323,328
-        // CAR:308,324,327: −c_m·fx_aero = −c_m C_D1 Vx − copysign(c_m C_D0, Vx)
-        double Vx_n = fma(D.cm, B + tc[c].fxr, fma(dpsi[c], Vy, fma(Vx, D.kx, with_opposite_sign(D.cmCD0, hvx))));
-        gen[c] = gen[c] | (bad < 0);
-        if (gen[c]) {  // rare: redo THIS sub-step on the general path from the un-advanced state, stay there
-          const VelOut o = vel_substep_general(P, ddt, accel[c], bk[c], split[c],
-                                               fma((double)(i + 1), dlt[c], car[c].delta), sg[c], Vx, Vy, psid);
-          Vx_n = o.Vx, Vy_n = o.Vy, psid_n = o.psid, sg[c] = o.sg;
+        double Vx = car[c].Vx, Vy = car[c].Vy, psid = car[c].psid, sd = car[c].sd, cd = car[c].cd, dp = dpsi[c];
+        int bad = 0;
+        // --- GROUP straight-line sub-steps, valid for every Vx != 0 and den != 0. The arithmetic is car_step_spec's
+        // (car_model.cuh), re-associated so that the loop-carried chain (Vx, Vy, Ψ̇) -> ... -> (Vx, Vy, Ψ̇) is as short as
+        // the mathematics allows (a dependent FP64 instruction issues 23-25 cycles after its producer on B200, and
+        // this chain IS the latency of a rollout):
+        //   * tan α_f = num/den and tan α_r = y_r/Vx through two reciprocal seeds (MUFU) instead of one of den·Vx — the
+        //     rear one starts from Vx, available when the sub-step begins; the Newton correction is applied to the
+        //     quotient, t = t₀(1 + e + e²) with t₀ = num·r₀, not to the reciprocal first (one operation fewer in series);
+        //   * the brush-tyre cubic (CAR:256) as fma(t|t|, c2 − c3|t|, −C t): depth 2 instead of 3;
+        //   * the Euler updates (CAR:322-328) written as ONE fma on each tyre force, everything else pre-summed:
+        //       Ψ̇' = (c₁cosδ)F_yf + [c₁F_xf sinδ + Ψ̇ − c₂F_yr],  Vy' = (c_m cosδ)F_yf + [c_m(F_xf sinδ + F_yr) + Vy − ΨδVx],
+        //       Vx' = −(c_m sinδ)F_yf + [c_m F_xf cosδ + ΨδVy + k_x Vx + c_m F_xr ∓ c_m C_D0].
+        // ≈ 10 dependent operations per sub-step instead of ≈ 16, for 3 more FP64 instructions. Differences to MODE 3 are
+        // re-association roundings (1e-16 relative per operation).
+        // The statements below are written LEVEL BY LEVEL of the dependence graph (everything that needs only the
+        // sub-step's inputs first, then what needs level 1, ...): a warp issues in order, ptxas largely keeps the order
+        // of independent instructions, and a level-ordered stream stalls once per level (≈ 24 cycles) instead of once
+        // per dependent pair — tools/sass_sched.py replays the SASS against the measured latencies.
+        const double cI1fxf = D.cI1 * tc[c].fxf, cmfxf = D.cm * tc[c].fxf, cmfxr = D.cm * tc[c].fxr;
+        const double nddt = -ddt;
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+          // level 0: the δ recurrence (independent of the velocities) and everything that needs the state only
+          const double ns = fma(sd, cdl[c], cd * sdl[c]);  // sin/cos(δ + rate·δt), CAR:301
+          const double nc = fma(cd, cdl[c], -(sd * sdl[c]));
+          sd = ns, cd = nc;
+          const int hvx = hi32(Vx);
+          const bool fwd = hvx >= 0;
+          const double rx = rcp_seed(Vx);  // 2^-23 seed of 1/Vx
+          const double yf = fma(P.l_f, psid, Vy), yr = fma(-P.l_r, psid, Vy);
+          const double wx = Vx * nddt, wy = Vy * ddt;                      // −δt·Vx, δt·Vy
+          const double k3 = fma(Vx, D.kx, cmfxr + with_opposite_sign(D.cmCD0, hvx));
+          // level 1
+          const double vxsd = Vx * sd, vxcd = Vx * cd;
+          const double ex = fma(-Vx, rx, 1.0);
+          const double t0r = yr * rx;
+          const double k2 = fma(psid, wx, Vy);                             // Vy − Ψ̇δt·Vx          (CAR:323)
+          const double k3b = fma(psid, wy, k3);                            // … + Ψ̇δt·Vy          (CAR:324)
+          const double k1 = fma(cI1fxf, sd, psid);                         // Ψ̇ + c₁F_xf sinδ      (CAR:322)
+          const double qI = D.cI1 * cd, qy = D.cm * cd, qx = D.cm * sd;
+          const double fxfsd = tc[c].fxf * sd;
+          // level 2
+          const double num = fma(yf, cd, -vxsd), den = fma(yf, sd, vxcd);  // tan α_f = num/den, tan α_r = yr/Vx
+          const double px = fma(ex, ex, ex);
+          const double Kx = fma(cmfxf, cd, k3b);
+          // level 3
+          const double r0 = rcp_seed(den);
+          const double ta_r = fma(t0r, px, t0r);  // t₀(1 + e + e²): relative error e³ = 2^-69
+          bad |= ((hvx ^ hvx0[c]) & brake_mask[c]) | ((hi32(den) & 0x7ff00000) - 0x00100000) |
+                 ((hvx & 0x7ff00000) - 0x00100000);
+          // level 4
+          const double e = fma(-den, r0, 1.0), t0 = num * r0;
+          const double atr = fabs(ta_r);
+          const double ur = ta_r * atr, vr = fma(-tc[c].c3_r, atr, tc[c].c2_r), x1r = -P.C_ar * ta_r;
+          const bool lin_r = fwd & (atr < tc[c].thr_r);
+          // level 5
+          const double pe = fma(e, e, e);
+          const double cubic_r = fma(ur, vr, x1r);  // CAR:256 as fma(t|t|, c2 − c3|t|, −C t)
+          // level 6
+          const double ta = fma(t0, pe, t0);
+          const double fyr = lin_r ? cubic_r : with_opposite_sign(tc[c].fymax_r, hi32(yr));  // CAR:255-259
+          // level 7
+          const double at = fabs(ta);
+          const double u = ta * at, v = fma(-tc[c].c3_f, at, tc[c].c2_f), x1 = -P.C_af * ta;
+          const bool lin_f = (hi32(den) >= 0) & (at < tc[c].thr_f);
+          const double Kp = fma(-D.cI2, fyr, k1);
+          const double Ky = fma(D.cm, fxfsd + fyr, k2);
+          // level 8
+          const double cubic = fma(u, v, x1);
+          const double fyf = lin_f ? cubic : with_opposite_sign(tc[c].fymax_f, fwd ? hi32(num) : hi32(yf));
+          // level 9: the new state — one fma on F_yf each (CAR:322-328)
+          psid = fma(qI, fyf, Kp), Vy = fma(qy, fyf, Ky), Vx = fma(-qx, fyf, Kx);
+          dp = psid * ddt;
+          sm.ring[vw][grp * GROUP + j][c][0][lane] = Vx;
+          sm.ring[vw][grp * GROUP + j][c][1][lane] = Vy;
+          sm.ring[vw][grp * GROUP + j][c][2][lane] = dp;
         }
-        car[c].Vx = Vx_n, car[c].Vy = Vy_n, car[c].psid = psid_n, car[c].sd = sd, car[c].cd = cd;
-        dpsi[c] = psid_n * ddt;
-        sm.ring[vw][slot][c][0][lane] = Vx_n;
-        sm.ring[vw][slot][c][1][lane] = Vy_n;
-        sm.ring[vw][slot][c][2][lane] = dpsi[c];
+        gen[c] = gen[c] | (bad < 0);
+        if (gen[c]) {  // rare: redo THIS group on the general path from its un-advanced state, stay there for the step
+          const VelState o = vel_group_general(P, ddt, accel[c], bk[c], split[c], car[c].delta, dlt[c], q * GROUP,
+                                               VelState{car[c].Vx, car[c].Vy, car[c].psid, sg[c]},
+                                               &sm.ring[vw][grp * GROUP][c][0][lane]);
+          Vx = o.Vx, Vy = o.Vy, psid = o.psid, sg[c] = o.sg;
+          dp = psid * ddt;
+        }
+        car[c].Vx = Vx, car[c].Vy = Vy, car[c].psid = psid, car[c].sd = sd, car[c].cd = cd, dpsi[c] = dp;
       }
-      const bool last = i + 1 == nsub;
-      if (last) {
+      if (q + 1 == gps) {
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
-          car[c].delta = fma((double)nsub, dlt[c], car[c].delta);  // CAR:301 summed
-          car[c].trig_valid = !gen[c];                              // the δ recurrence was not advanced exactly: resync
+          car[c].delta = fma((double)env.nsub, dlt[c], car[c].delta);  // CAR:301 summed
+          car[c].trig_valid = !gen[c];  // after a general step the δ recurrence restarts from δ itself
           // end-of-step extras for the trajectory log. ext[t & 1] was last read at the end of step t − 2, which the
-          // pose warp has passed: this warp is at most RING = 16 sub-steps ahead of it
+          // pose warp has passed: this warp is at most NGROUP = 3 groups ahead of it
           sm.ext[vw][t & 1][c][0][lane] = car[c].psid;
           sm.ext[vw][t & 1][c][1][lane] = car[c].delta;
           sm.ext[vw][t & 1][c][2][lane] = act[2 * c + 1];  // pedal (CAR:297, state[8])
         }
         if (t + 1 == T) sm.fin[vw][lane] = cc;
       }
-      if ((g % GROUP) == GROUP - 1 || (last && t + 1 == T)) {  // group complete (or the rollout is): hand it over
-        __syncwarp();
-        if (lane == 0) bar_arrive(&sm.full[vw][grp]);
-      }
+      __syncwarp();  // every lane's slots of the group are written: hand it over
+      if (lane == 0) bar_arrive(&sm.full[vw][grp]);
     }
   }
 }
 
 template <int NCARS>
 __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm,
-                                          const TrackView &tr, int kbase, int nvw, int lane) {
+                                          const TrackView &tr, int kbase, int nvw, int lane, long long *waited) {
   constexpr int SS = 8 * NCARS;
-  const int nsub = env.nsub, T = a.T;
+  const int gps = env.nsub / GROUP, T = a.T;
   const double ddt = env.ddt;
   PoseCar pc[VW][NCARS];
   double cost[VW];
@@ -253,7 +310,7 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
       pc[v][c].psi = __ldg(a.state0 + 8 * c + 2), pc[v][c].sp = 0.0, pc[v][c].cp = 1.0;
     }
   }
-  int g = 0;
+  int gi = 0;
   for (int t = 0; t < T; ++t) {
     if ((t % 5) == 0) {  // re-synchronise the heading recurrence (as MODE 3 does every 5th control step)
 #pragma unroll
@@ -271,42 +328,51 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
         }
     }
     double vx_end[VW][NCARS], vy_end[VW][NCARS];
-    for (int i = 0; i < nsub; ++i, ++g) {
-      const int slot = g % RING, grp = slot / GROUP;
-      if ((g % GROUP) == 0) {
+    for (int q = 0; q < gps; ++q, ++gi) {
+      const int grp = gi % NGROUP;
 #pragma unroll
-        for (int v = 0; v < VW; ++v)
-          if (v < nvw) bar_wait(&sm.full[v][grp], (unsigned)((g / RING) & 1));
-      }
+      for (int v = 0; v < VW; ++v)
+        if (v < nvw) bar_wait(&sm.full[v][grp], (unsigned)((gi / NGROUP) & 1), waited);
+      // GROUP sub-steps of VW x NCARS independent poses in one straight-line block: the short sin/cos polynomials of
+      // all increments overlap, only the heading rotation (two operations per sub-step) is sequential
 #pragma unroll
       for (int v = 0; v < VW; ++v)
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
-          const double Vx = sm.ring[v][slot][c][0][lane], Vy = sm.ring[v][slot][c][1][lane];
-          const double dpsi = sm.ring[v][slot][c][2][lane];
           PoseCar &p = pc[v][c];
-          p.psi += dpsi;  // CAR:329 (wrapped once per step below)
-          double sdp, cdp;
-          sincos_tiny(dpsi, &sdp, &cdp);
-          if ((0x3F9EB851 - (hi32(dpsi) & 0x7fffffff)) < 0) {  // |Ψ̇δt| > 0.03 / NaN
-            const SinCos o = sincos_increment_general(dpsi);
-            sdp = o.s, cdp = o.c;
-          }
-          const double nsp = fma(p.sp, cdp, p.cp * sdp);
-          p.cp = fma(p.cp, cdp, -(p.sp * sdp));
-          p.sp = nsp;
-          p.x = fma(fma(Vx, p.cp, -(Vy * p.sp)), ddt, p.x);  // CAR:331
-          p.y = fma(fma(Vx, p.sp, Vy * p.cp), ddt, p.y);     // CAR:332
-          vx_end[v][c] = Vx, vy_end[v][c] = Vy;
-        }
-      const bool fin = i + 1 == nsub && t + 1 == T;
-      if ((g % GROUP) == GROUP - 1 || fin) {  // every lane has read the group: give it back
-        __syncwarp();
-        if (lane == 0 && !fin) {
+          double Vx[GROUP], Vy[GROUP], dpsi[GROUP], sdp[GROUP], cdp[GROUP];
+          int wide = 0;
 #pragma unroll
-          for (int v = 0; v < VW; ++v)
-            if (v < nvw) bar_arrive(&sm.empty[v][grp]);
+          for (int j = 0; j < GROUP; ++j) {
+            Vx[j] = sm.ring[v][grp * GROUP + j][c][0][lane], Vy[j] = sm.ring[v][grp * GROUP + j][c][1][lane];
+            dpsi[j] = sm.ring[v][grp * GROUP + j][c][2][lane];
+            sincos_tiny(dpsi[j], &sdp[j], &cdp[j]);
+            wide |= 0x3F9EB851 - (hi32(dpsi[j]) & 0x7fffffff);  // |Ψ̇δt| > 0.03 or NaN
+          }
+          if (wide < 0) {  // a spinning car: the general sin/cos for the increments that need it (rare)
+#pragma unroll
+            for (int j = 0; j < GROUP; ++j)
+              if ((0x3F9EB851 - (hi32(dpsi[j]) & 0x7fffffff)) < 0) {
+                const SinCos o = sincos_increment_general(dpsi[j]);
+                sdp[j] = o.s, cdp[j] = o.c;
+              }
+          }
+#pragma unroll
+          for (int j = 0; j < GROUP; ++j) {
+            p.psi += dpsi[j];  // CAR:329 (wrapped once per step below)
+            const double nsp = fma(p.sp, cdp[j], p.cp * sdp[j]);
+            p.cp = fma(p.cp, cdp[j], -(p.sp * sdp[j]));
+            p.sp = nsp;
+            p.x = fma(fma(Vx[j], p.cp, -(Vy[j] * p.sp)), ddt, p.x);  // CAR:331
+            p.y = fma(fma(Vx[j], p.sp, Vy[j] * p.cp), ddt, p.y);     // CAR:332
+          }
+          vx_end[v][c] = Vx[GROUP - 1], vy_end[v][c] = Vy[GROUP - 1];
         }
+      __syncwarp();  // every lane has read the group: give it back
+      if (lane == 0 && !(q + 1 == gps && t + 1 == T)) {
+#pragma unroll
+        for (int v = 0; v < VW; ++v)
+          if (v < nvw) bar_arrive(&sm.empty[v][grp]);
       }
     }
     // ---- end of the control step: heading wrap (CAR:330), reward (CAR:201-213 / MCR:145-158), log ----
@@ -357,7 +423,7 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
 }
 
 template <int NCARS>
-__global__ void __launch_bounds__(CTA, NCARS == 1 ? 7 : 1) rollout_car_split_kernel(const __grid_constant__ CarEnvArgs env,
+__global__ void __launch_bounds__(CTA) __maxnreg__(NCARS == 1 ? 96 : 255) rollout_car_split_kernel(const __grid_constant__ CarEnvArgs env,
                                                                  const __grid_constant__ RolloutArgs a,
                                                                  const int *stop) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -379,12 +445,16 @@ __global__ void __launch_bounds__(CTA, NCARS == 1 ? 7 : 1) rollout_car_split_ker
   __syncthreads();
   const TrackView tr{trk_s, trk_s + env.n_trk, trk_s + 2 * env.n_trk, env.n_trk,
                      env.lut, env.lut_x0, env.lut_y0, env.lut_inv_c, env.lut_nx, env.lut_ny};
+  long long waited = 0, *wp = a.warp_cycles ? &waited : nullptr;
   if (w < VW) {
-    if (w < nvw) velocity_warp<NCARS>(env, a, sm, w, min(kbase + w * 32 + lane, a.K - 1), lane);  // padding lanes copy the last rollout
+    if (w < nvw) velocity_warp<NCARS>(env, a, sm, w, min(kbase + w * 32 + lane, a.K - 1), lane, wp);  // padding lanes copy the last rollout
   } else {
-    pose_warp<NCARS>(env, a, sm, tr, kbase, nvw, lane);
+    pose_warp<NCARS>(env, a, sm, tr, kbase, nvw, lane, wp);
   }
-  if (a.warp_cycles && lane == 0) a.warp_cycles[blockIdx.x * (VW + 1) + w] = clock64() - t_begin;
+  if (a.warp_cycles && lane == 0) {  // "rollout_profile": [total | waiting on the ring] cycles per warp, role = index % 3
+    a.warp_cycles[2 * (blockIdx.x * (VW + 1) + w)] = clock64() - t_begin;
+    a.warp_cycles[2 * (blockIdx.x * (VW + 1) + w) + 1] = waited;
+  }
 }
 
 }  // namespace
@@ -393,6 +463,7 @@ int rollout_split_max_cars() { return 3; }
 
 // returns 0 when the configuration is not covered (the caller falls back to the thread-per-rollout kernel)
 int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, const int *stop, cudaStream_t st) {
+  if (env.nsub < GROUP || env.nsub % GROUP) return 0;  // the ring hands over groups of GROUP sub-steps
   const int grid = (a.K + 32 * VW - 1) / (32 * VW);
   const size_t trk = sizeof(double) * 3 * env.n_trk;
 #define MPOPIS_SPLIT(N)                                                                                              \

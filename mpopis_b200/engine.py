@@ -150,6 +150,11 @@ class Engine:
     def set_option(self, key: str, value: float):
         self._chk(self.b.set_option(self.h, key.encode(), float(value)))
 
+    def get_option(self, key: str) -> float:
+        v = C.c_double(0.0)
+        self._chk(self.b.get_option(self.h, key.encode(), C.byref(v)))
+        return v.value
+
     # -- the hot path ---------------------------------------------------------------------------
     def plan(self, state, env_t, U, Z=None, resample_u=None):
         """(pol)(env): returns (control[as], U_rolled[cs], its_run). Z: (N, cs, K)-indexable noise
@@ -315,7 +320,7 @@ class Engine:
 
     def warp_cycles(self) -> np.ndarray:
         """Per-warp clock64() cycles of the most recent rollout launch (needs set_option("rollout_profile", 1))."""
-        n = (self.Kloc + 31) // 32
+        n = 4 * (self.Kloc // 32 + 2)  # variant 4 writes [total, waiting] per warp, 3 warps per 64 rollouts
         out = np.zeros(n, dtype=np.int64)
         self._chk(self.b.warp_cycles(self.h, out.ctypes.data_as(C.POINTER(C.c_int64)), n))
         return out

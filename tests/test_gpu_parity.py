@@ -505,10 +505,10 @@ def test_target_config_one_step_vs_oracle(gpu_bound, orc):
 @pytest.mark.parametrize("n_cars,K,T", [(1, 4099, 50), (1, 70, 23), (1, 33, 7), (2, 333, 30), (3, 375, 50), (3, 64, 11)])
 def test_warp_specialised_rollouts_equal_the_thread_per_rollout_kernel(gpu_bound, n_cars, K, T):
     """rollout_variant 4 (rollout_split.cu: velocity warps + pose/reward warps through a shared-memory ring) against
-    variant 3 (one thread per rollout): the same expressions in the same order on every sub-step, so the costs agree to
-    rounding (1e-12) except on the rare control steps the two variants repair differently (whole step vs from the
-    offending sub-step on), and the trajectory log — the per-step states both write — agrees as well. Ragged K (partly
-    filled last warp / single velocity warp in the last CTA) and horizons that do not fill the ring's groups included."""
+    variant 3 (one thread per rollout): the same mathematics with the velocity recurrence re-associated for a shorter
+    dependent chain, so costs and the logged per-step states agree to accumulated rounding (chaotic dynamics over 500
+    Euler sub-steps: 1e-9 with a handful of penalty-threshold flips), not bitwise. Ragged K (partly filled last warp /
+    single velocity warp in the last CTA) and short horizons included."""
     env = make_env("car", n_cars)
     g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, K, T, log_trajectories=True)), env, "gmppi")
     rng = np.random.Generator(np.random.Philox(key=K + T))
@@ -519,7 +519,7 @@ def test_warp_specialised_rollouts_equal_the_thread_per_rollout_kernel(gpu_bound
         g.set_option("rollout_variant", variant)
         out[variant] = (g.rollout_costs(env.state, 0, U, U, E), g.fetch(costs=False, weights=False, traj=True)["traj"])
     r = rel(out[4][0], out[3][0])
-    assert (r > 1e-12).sum() <= max(1, K // 200), f"{(r > 1e-12).sum()} of {K} costs differ (max rel {r.max():.2e})"
-    assert (r > TIGHT).sum() <= max(1, K // 1000)
+    assert (r > TIGHT).sum() <= max(1, K // 500), f"{(r > TIGHT).sum()} of {K} costs differ (max rel {r.max():.2e})"
+    print(f"variant 4 vs 3: median rel {np.median(r):.2e}, 99.9 % {np.quantile(r, 0.999):.2e}")
     tr = np.abs(out[4][1] - out[3][1]) / np.maximum(1.0, np.abs(out[3][1]))
     assert np.quantile(tr, 0.999) < 1e-9, "trajectory logs differ"

@@ -1,5 +1,6 @@
-"""Spread of per-warp run time inside ONE rollout launch (K = 65536 :cemppi, last AIS iteration of a control step):
-how much of the kernel's duration is tail — warps that repair steps or scan the whole track — rather than the mean."""
+"""Per-warp clock64() of one rollout launch (set_option("rollout_profile", 1)).
+variant 3: one entry per warp. variant 4 (rollout_split.cu): per CTA three warps (2 velocity, 1 pose), each
+[total cycles, cycles spent waiting on the ring's mbarriers]."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -7,22 +8,25 @@ import numpy as np
 from bench import make_engine
 from mpopis_b200 import _lib
 
-K = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-env, eng = make_engine(_lib.product(), K, 0, 1, 0, early_stop=False)
-eng.set_option("rollout_profile", 1)
-if len(sys.argv) > 2:
-    eng.set_option("rollout_queue", int(sys.argv[2]))
-U = np.zeros(eng.cs)
-st = env.state.copy()
-for i in range(12):
-    ctrl, U, its = eng.plan(st, i, U)
-    st, _, _, _ = eng.env_step(st, ctrl, i)
-    if i in (0, 5, 11):
-        c = eng.warp_cycles().astype(float)
+for K in [int(x) for x in (sys.argv[1:] or ["150", "65536"])]:
+    for variant in (3, 4):
+        env, eng = make_engine(_lib.product(), K, 0, 1, 0)
+        eng.set_option("rollout_variant", variant)
+        eng.set_option("rollout_profile", 1)
+        U, st = np.zeros(eng.cs), env.state.copy()
+        for i in range(3):
+            ctrl, U, its = eng.plan(st, i, U)
+        c = eng.warp_cycles()
+        if variant == 3:
+            c = c[: (K + 31) // 32]
+            print(f"K={K} variant 3: warps {c.size} cycles median {np.median(c):.0f} max {c.max()} min {c.min()}")
+        else:
+            n = (K + 63) // 64
+            c = c[: n * 6].reshape(n, 3, 2)
+            for role, sl in (("velocity", c[:, :2, :].reshape(-1, 2)), ("pose", c[:, 2, :])):
+                sl = sl[sl[:, 0] > 0]
+                print(f"K={K} variant 4 {role:8s}: warps {len(sl)} total median {np.median(sl[:, 0]):.0f} max {sl[:, 0].max()} "
+                      f"waiting median {np.median(sl[:, 1]):.0f} ({100 * np.median(sl[:, 1] / sl[:, 0]):.0f} %)")
         tm = eng.last_timing()
-        q = np.percentile(c, [0, 5, 50, 95, 99, 100])
-        print(f"step {i}: rollout launch {tm['rollout_ms'] / tm['rollout_launches'] * 1e3:.1f} us = "
-              f"{tm['rollout_ms'] / tm['rollout_launches'] * 1e-3 * 1.965e9:.0f} cycles at 1965 MHz; per-warp cycles "
-              f"min {q[0]:.0f} p5 {q[1]:.0f} median {q[2]:.0f} p95 {q[3]:.0f} p99 {q[4]:.0f} max {q[5]:.0f}; "
-              f"warps > 1.1 x median: {np.mean(c > 1.1 * q[2]) * 100:.1f} %, > 1.25 x: {np.mean(c > 1.25 * q[2]) * 100:.2f} %",
-              flush=True)
+        print(f"    rollout launch {tm['rollout_ms'] / tm['rollout_launches'] * 1e3:.1f} us, step {tm['total_ms']:.3f} ms")
+        eng.close()
