@@ -89,6 +89,25 @@ MPOPIS_HD double fast_div(double n, double d) {
   return fma(fma(-d, q, n), r, q);
 }
 
+// sqrt without the IEEE slow-path subroutine: reciprocal-square-root seed (MUFU.RSQ64H, 2^-23), one coupled Newton step
+// for (sqrt, 1/(2 sqrt)) and a final residual correction — the result is the correctly rounded square root except for
+// rare last-bit ties (≤ 1 ulp). Used where the reference takes norm(...) / sqrt of a sum of squares that feeds a smooth
+// cost term; a threshold comparison can flip only if the exact value sits within an ulp of the threshold.
+MPOPIS_HD double sqrt_fast(double x) {
+#ifdef __CUDA_ARCH__
+  if (!(x > 0.0) || !(x < 1.0e300)) return sqrt_rn(x);  // 0, negative, Inf, NaN: the exact routine (rare)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double y = x * r, h = 0.5 * r;
+  const double e = fma(-y, h, 0.5);
+  y = fma(y, e, y), h = fma(h, e, h);       // 2^-46
+  y = fma(fma(-y, y, x), h, y);             // 2^-92 before rounding
+  return fma(fma(-y, y, x), h, y);
+#else
+  return sqrt(x);
+#endif
+}
+
 struct TrackView {
   const double *x, *y, *w;
   int n;
@@ -99,7 +118,7 @@ struct TrackView {
 };
 
 // within_track(track, pos) TRK:68-92. Integer-exact: distances use un-fused mul/add.
-template <bool USE_LUT>
+template <bool USE_LUT, bool FAST = false>
 MPOPIS_HD bool within_track(const TrackView &tr, double px, double py, int *idx_out,
                                              int *idx2_out, double *dist_out) {
   int mi = 0;
@@ -142,9 +161,11 @@ MPOPIS_HD bool within_track(const TrackView &tr, double px, double py, int *idx_
   else m2 = sqrt_rn(qa) <= sqrt_rn(qb) ? m1 : p1;
   const double p1x = tr.x[mi], p1y = tr.y[mi];
   const double vx = tr.x[m2] - p1x, vy = tr.y[m2] - p1y, ux = px - p1x, uy = py - p1y;
-  const double t = (ux * vx + uy * vy) / (vx * vx + vy * vy);  // TRK:87 (projection on the infinite line)
+  // TRK:87 (projection on the infinite line); FAST: reciprocal-Newton division / rsqrt-Newton square root instead of
+  // the IEEE subroutines (≈ 35 instructions and a CALL each) — same value up to a last-bit tie
+  const double t = FAST ? fast_div(ux * vx + uy * vy, vx * vx + vy * vy) : (ux * vx + uy * vy) / (vx * vx + vy * vy);
   const double ex = p1x + t * vx - px, ey = p1y + t * vy - py; // TRK:88
-  const double dist = sqrt(ex * ex + ey * ey);                 // TRK:89
+  const double dist = FAST ? sqrt_fast(ex * ex + ey * ey) : sqrt(ex * ex + ey * ey);  // TRK:89
   if (idx_out) *idx_out = mi;
   if (idx2_out) *idx2_out = m2;
   *dist_out = dist;
@@ -587,8 +608,8 @@ template <int MODE>
 MPOPIS_HD double car_reward(const CarParams &P, double cos_bl, const TrackView &tr,
                                              const double *s) {
   double dist;
-  const bool within = within_track<MODE == 0 || MODE == 3>(tr, s[0], s[1], nullptr, nullptr, &dist);
-  const double speed = sqrt(s[3] * s[3] + s[4] * s[4]);
+  const bool within = within_track<MODE == 0 || MODE == 3, MODE == 3>(tr, s[0], s[1], nullptr, nullptr, &dist);
+  const double speed = MODE == 3 ? sqrt_fast(s[3] * s[3] + s[4] * s[4]) : sqrt(s[3] * s[3] + s[4] * s[4]);
   const bool exceed = MODE != 1 ? (s[3] < cos_bl * speed) : (fabs(atan2(s[4], s[3])) > P.b_limit);  // CAR:181-189
   double rew = 0.0;
   if (!within) rew += -1000000.0;

@@ -104,7 +104,8 @@ void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant
                         const int *stop, cudaStream_t s);
 // rollout_split.cu ("v5", rollout_variant 4): velocity warps + pose/reward warps; returns 0 when not applicable
 int rollout_split_max_cars();
-int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, const int *stop, cudaStream_t s);
+int rollout_split_capacity(int n_cars, int num_sms);  // rollouts one launch keeps resident (one wave)
+int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, int wide, const int *stop, cudaStream_t s);
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
                         unsigned char *within, int use_lut, cudaStream_t s);
@@ -172,6 +173,10 @@ void launch_set_scalar(double *dst, double value, cudaStream_t s);
 // linalg.cu
 void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, double *Wglobal, int *info, int tag,
                  const int *stop, cudaStream_t s);
+// cov_finalize + chol fused (n <= 160); q_dev: the shrinkage statistic (:lw / :ss). Returns 0 when not applicable.
+int launch_chol_cov(const double *Sraw, int n, const double *cnt_dev, int corrected, int method, const double *q_dev,
+                    double ridge, double *Sigma, double *Lt, double *lambda_out, int *info, int tag, const int *stop,
+                    cudaStream_t s);
 void launch_chol_solve(const double *Lt, int n, const double *u, double gamma, double *b, const int *stop,
                        cudaStream_t s);
 void launch_transpose_sq(const double *in, double *out, int n, cudaStream_t s);

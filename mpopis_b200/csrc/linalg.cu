@@ -145,6 +145,177 @@ __global__ void __launch_bounds__(256) chol_reg_kernel(const double *__restrict_
     }
 }
 
+// cov_finalize (stats.cu) + chol_reg in ONE launch for the :cemppi update: Σ′ = shrink(method, Sraw/denom) + ridge·I is
+// formed in the registers that the factorisation starts from — the p x p matrix is read once, the trace / correlation
+// sums of the shrinkage intensity are block reductions over the register tile, and Σ′ is written out only for
+// fetch_proposal. Replaces two single-CTA latency kernels (≈16 + 31 µs at p = 100) and the launch gap between them.
+// Same formulas as cov_finalize_kernel; the sums run in register-tile order instead of row order.
+__device__ __forceinline__ double block_sum_256(double v, double *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) chol_cov_kernel(const double *__restrict__ Sraw, int n, const double *cnt_dev,
+                                                        int corrected, int method, const double *__restrict__ q_dev,
+                                                        double ridge, double *__restrict__ Sigma,
+                                                        double *__restrict__ Lt, double *lambda_out, int *info, int tag,
+                                                        const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double col[2][16 * R];
+  __shared__ double dg[16 * R];
+  __shared__ double dinv[16 * R];
+  __shared__ double red[8];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const double cnt = *cnt_dev, inv = 1.0 / (cnt - (corrected ? 1.0 : 0.0));
+  double w[R][R];
+#pragma unroll
+  for (int a = 0; a < R; ++a)
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      const int i = ty + 16 * a, k = tx + 16 * b;
+      w[a][b] = (i < n && k <= i) ? Sraw[(size_t)i * n + k] * inv : 0.0;  // S = Sraw / denom, lower triangle
+      if (i < n && k == i) dg[i] = w[a][b];
+    }
+  __syncthreads();
+  double lam = 0.0, F = 0.0;
+  if (method == MPOPIS_SIGMA_LW || method == MPOPIS_SIGMA_SS) {
+    const bool ss = method == MPOPIS_SIGMA_SS;
+    for (int i = threadIdx.x; i < n; i += 256) dinv[i] = ss ? 1.0 / sqrt(dg[i]) : 1.0;  // 1/σ_i once, not per element
+    __syncthreads();
+    double r2 = 0.0;  // Σ_{i≠j} (s_ij d_i d_j)², d = 1/σ (:ss) or 1 (:lw): twice the strictly-lower sum
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        const int i = ty + 16 * a, k = tx + 16 * b;
+        if (i < n && k < i) {
+          const double v = w[a][b] * dinv[i] * dinv[k];
+          r2 = fma(v, v, r2);
+        }
+      }
+    r2 = 2.0 * block_sum_256(r2, red);
+    const double num = (*q_dev - cnt * r2) * cnt / ((cnt - 1.0) * cnt * cnt);
+    lam = fmin(fmax(num / r2, 0.0), 1.0);
+  } else if (method == MPOPIS_SIGMA_RBLW || method == MPOPIS_SIGMA_OAS) {
+    double tr = 0.0, tr2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        const int i = ty + 16 * a, k = tx + 16 * b;
+        if (i < n && k <= i) {
+          const double v = w[a][b];
+          tr2 = fma(k == i ? 1.0 : 2.0, v * v, tr2);
+          if (k == i) tr += v;
+        }
+      }
+    tr = block_sum_256(tr, red);
+    tr2 = block_sum_256(tr2, red);
+    const double pd = (double)n, trsq = tr * tr;
+    if (method == MPOPIS_SIGMA_RBLW) lam = ((cnt - 2) / cnt * tr2 + trsq) / ((cnt + 2) * (tr2 - trsq / pd));
+    else lam = ((1.0 - 2.0 / pd) * tr2 + trsq) / ((cnt + 1.0 - 2.0 / pd) * (tr2 - trsq / pd));
+    lam = fmin(fmax(lam, 0.0), 1.0);
+    F = tr / pd;
+  }
+  const bool common = method == MPOPIS_SIGMA_RBLW || method == MPOPIS_SIGMA_OAS;
+#pragma unroll
+  for (int a = 0; a < R; ++a)
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      const int i = ty + 16 * a, k = tx + 16 * b;
+      if (i < n && k <= i) {
+        const double v = w[a][b];
+        // diag(S) target: the diagonal is kept; tr(S)/p·I target: it is shrunk as well (cov_finalize_kernel)
+        const double s = k == i ? (common ? (1.0 - lam) * v + lam * F : v) + ridge : (1.0 - lam) * v;
+        w[a][b] = s;
+        Sigma[(size_t)i * n + k] = s;
+        Sigma[(size_t)k * n + i] = s;
+      }
+    }
+  if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
+  __syncthreads();
+  bool failed = false;
+#pragma unroll
+  for (int jb = 0; jb < R; ++jb) {  // identical to chol_reg_kernel from here on
+    for (int jt = 0; jt < 16; ++jt) {
+      const int j = 16 * jb + jt, pb = jt & 1;
+      if (j >= n || failed) break;
+      if (tx == jt) {
+#pragma unroll
+        for (int a = jb; a < R; ++a) col[pb][ty + 16 * a] = w[a][jb];
+      }
+      __syncthreads();
+      const double d = col[pb][j];
+      if (!(d > 0.0)) {
+        failed = true;
+        break;
+      }
+      if (threadIdx.x == 0) dg[j] = d;
+      double inv_d;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv_d) : "d"(d));
+      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
+      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
+      double ck[R];
+#pragma unroll
+      for (int b = jb; b < R; ++b) ck[b] = col[pb][tx + 16 * b];
+#pragma unroll
+      for (int a = jb; a < R; ++a) {
+        double ci = col[pb][ty + 16 * a] * inv_d;
+        if (a == jb && ty <= jt) ci = 0.0;
+#pragma unroll
+        for (int b = jb; b <= a; ++b) {
+          bool on = true;
+          if (b == jb) on = tx > jt;
+          if (b == a) on = on && (tx <= ty);
+          if (on) w[a][b] = fma(-ci, ck[b], w[a][b]);
+        }
+      }
+    }
+  }
+  if (failed) {
+    if (threadIdx.x == 0) atomicCAS(info, 0, tag);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < R; ++a)
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      const int i = ty + 16 * a, k = tx + 16 * b;
+      if (i < n && k < n) {
+        double v = 0.0;
+        if (k <= i) {
+          const double r = sqrt(dg[k]);
+          v = k == i ? r : w[a][b] / r;
+        }
+        Lt[(size_t)i * n + k] = v;
+      }
+    }
+}
+
+// returns 0 when n is beyond the register-tiled kernels (the caller then runs cov_finalize + chol separately)
+int launch_chol_cov(const double *Sraw, int n, const double *cnt_dev, int corrected, int method, const double *q_dev,
+                    double ridge, double *Sigma, double *Lt, double *lambda_out, int *info, int tag, const int *stop,
+                    cudaStream_t s) {
+#define MPOPIS_CC(R) chol_cov_kernel<R><<<1, 256, 0, s>>>(Sraw, n, cnt_dev, corrected, method, q_dev, ridge, Sigma, Lt, lambda_out, info, tag, stop)
+  if (n <= 16) MPOPIS_CC(1);
+  else if (n <= 64) MPOPIS_CC(4);
+  else if (n <= 112) MPOPIS_CC(7);
+  else if (n <= 160) MPOPIS_CC(10);
+  else return 0;
+#undef MPOPIS_CC
+  return 1;
+}
+
 constexpr int CHOL_SMEM_N = 160;  // 160 · 161 · 8 B = 201 KB
 
 // Wglobal: scratch of n (n|1) doubles, used when n > CHOL_SMEM_N

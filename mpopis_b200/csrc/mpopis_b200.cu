@@ -73,7 +73,7 @@ struct mpopis_handle {
   double gamma = 0.0;
   uint64_t seed = 0;
   long long step = 0;
-  int rollout_variant = 3, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1, sel_max = 1;
+  int rollout_variant = 6, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1, sel_max = 1;
   bool moments_small = true;  // single-CTA moment chain for small n ("moments_small" option, A/B)
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
   bool L0_valid = false;
@@ -96,7 +96,7 @@ struct mpopis_handle {
   bool graph_enabled = true, capturing = false;
   long long graph_launches = 0;
   unsigned *d_step = nullptr;
-  bool use_select = false;  // :cemppi: select.cu path (sharded, or K above the single-CTA sort)
+  bool use_select = false, cov_pending = false, fuse_cov = true;  // fuse_cov: cov_finalize folded into the Cholesky kernel  // :cemppi: select.cu path (sharded, or K above the single-CTA sort)
   long long *d_env_t = nullptr, *d_warp_cycles = nullptr;  // d_warp_cycles: "rollout_profile" option
   unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
   int *d_order = nullptr, *d_vals_b = nullptr, *d_hist = nullptr, *d_counts = nullptr, *d_flags = nullptr;
@@ -289,6 +289,10 @@ int ce_adapt(mpopis_t *h) {
   mark(h, "scatter.local");
   if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs + (shrink ? 1 : 0))) return rc;
   mark(h, "scatter.coll");
+  if (cs <= 160 && h->fuse_cov) {  // Σ′ = shrink(S) + 1e-8 I is formed inside the next iteration's factorisation
+    h->cov_pending = true;
+    return 0;
+  }
   launch_cov_finalize(h->d_Sraw, cs, h->d_sums + cs, 0, method, qdst, shrink ? 1 : 0, 10e-9, h->d_Sigma, h->d_lambda,
                       stop, st);
   h->launches += 1;
@@ -353,9 +357,15 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
   a.K = h->Kloc, a.T = h->T;
   a.warp_cycles = h->d_warp_cycles;
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING) {
-    // variant 4 ("v5"): the warp-specialised kernel; it covers 1..3 cars, the rest falls back to variant 3
-    if (!(h->rollout_variant == 4 && launch_rollout_car_split(h->car, a, h->stop(), h->st)))
-      launch_rollout_car(h->car, a, h->rollout_variant == 4 ? 3 : h->rollout_variant, h->rollout_block,
+    // variants 4 / 5 ("v5"): the warp-specialised kernel (rollout_split.cu; 1..3 cars, nsub = 10 — anything else falls
+    // back to variant 3). 6 = automatic (the default): the wide split kernel while one launch keeps every rollout
+    // resident (latency regime: K <= 28 416 one-car rollouts on 148 SMs), the thread-per-rollout kernel beyond.
+    int variant = h->rollout_variant;
+    if (variant == 6)
+      variant = (h->cfg.n_cars <= rollout_split_max_cars() && h->Kloc <= rollout_split_capacity(h->cfg.n_cars, h->num_sms) &&
+                 !h->rollout_stage) ? 5 : 3;
+    if (!(variant >= 4 && launch_rollout_car_split(h->car, a, variant == 5, h->stop(), h->st)))
+      launch_rollout_car(h->car, a, variant >= 4 ? 3 : variant, h->rollout_block,
                          h->rollout_stage, h->stop(), h->st);
   } else
     launch_rollout_mc(h->mc, a, h->rollout_block, h->stop(), h->st);
@@ -407,8 +417,13 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     // --- proposal factor L of Σ′ (POL:447; CMA samples from σ²Σ, POL:550-554) ---
     const bool cma_scaled = pol == MPOPIS_POLICY_CMAMPPI && N > 1;
     if ((adapt && n > 0) || cma_scaled) {
-      launch_chol(adapt && n > 0 ? h->d_Sigma : h->d_Sigma0, cs, cma_scaled ? h->d_sigma : nullptr, h->d_Lt,
-                  h->d_cholW, h->info(), n + 1, stop, st);
+      // ce_adapt leaves Σ′ un-finalised when the shrinkage + ridge can be folded into the factorisation (one launch)
+      if (!(h->cov_pending &&
+            launch_chol_cov(h->d_Sraw, cs, h->d_sums + cs, 0, h->cfg.sigma_est, h->d_Sraw + (size_t)cs * cs, 10e-9,
+                            h->d_Sigma, h->d_Lt, h->d_lambda, h->info(), n + 1, stop, st)))
+        launch_chol(adapt && n > 0 ? h->d_Sigma : h->d_Sigma0, cs, cma_scaled ? h->d_sigma : nullptr, h->d_Lt,
+                    h->d_cholW, h->info(), n + 1, stop, st);
+      h->cov_pending = false;
       h->launches += 1;
       Lt = h->d_Lt;
       if (n > 0) bs = cs;
@@ -1085,13 +1100,13 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     return 0;
   }
   if (!strcmp(key, "rollout_variant")) {
-    if (value != 0.0 && value != 1.0 && value != 3.0 && value != 4.0)
-      return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0 (v3), 1 (literal), 3 (v4) or 4 (v5, warp-specialised)");
+    if (value != 0.0 && value != 1.0 && value != 3.0 && value != 4.0 && value != 5.0 && value != 6.0)
+      return fail(MPOPIS_ERR_BAD_ARG, "rollout_variant must be 0 (v3), 1 (literal), 3 (v4), 4 / 5 (v5, warp-specialised) or 6 (auto)");
     h->rollout_variant = (int)value;
   }
   else if (!strcmp(key, "rollout_profile")) {  // per-warp clock64() of the rollout kernel, read with warp_cycles()
     if (value != 0.0 && !h->d_warp_cycles) {
-      if (int rc = dalloc(&h->d_warp_cycles, 4 * ((size_t)h->Kloc / 32 + 2))) return rc;  // split kernel: 3 warps x 2 per 64
+      if (int rc = dalloc(&h->d_warp_cycles, 8 * ((size_t)h->Kloc / 32 + 2))) return rc;  // split kernel: 3 warps x 2 per 64 + phases
     } else if (value == 0.0 && h->d_warp_cycles) {
       cudaFree(h->d_warp_cycles), h->d_warp_cycles = nullptr;
     }
@@ -1106,6 +1121,8 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     h->rollout_block = b;
   } else if (!strcmp(key, "moments_small")) {
     h->moments_small = value != 0.0;
+  } else if (!strcmp(key, "fuse_cov")) {
+    h->fuse_cov = value != 0.0;
   } else if (!strcmp(key, "apply_l")) {
     if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
       return fail(MPOPIS_ERR_BAD_ARG, "apply_l must be 0, 1, 2 or 3");
@@ -1351,8 +1368,7 @@ int mpopis_b200_track_query(mpopis_t *h, const double *pos, int64_t n, int32_t *
 
 static int env_step_device(mpopis_t *h, const double *d_action) {
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
-    launch_env_step_car(h->car, h->d_state, d_action, h->d_env_t, h->d_reward, h->rollout_variant == 4 ? 3 : h->rollout_variant,
-                        h->st);
+    launch_env_step_car(h->car, h->d_state, d_action, h->d_env_t, h->d_reward, h->rollout_variant >= 4 ? 3 : h->rollout_variant, h->st);
   else
     launch_env_step_mc(h->mc, h->d_state, d_action, h->d_env_t, h->d_reward, h->d_done, h->st);
   h->launches += 1;
@@ -1390,7 +1406,7 @@ int mpopis_b200_env_reward(mpopis_t *h, const double *state, uint8_t done, doubl
   if (int rc = set_device(h)) return rc;
   CU(cudaMemcpyAsync(h->d_state, state, sizeof(double) * h->ss, cudaMemcpyHostToDevice, h->st));
   if (h->cfg.env == MPOPIS_ENV_CAR_RACING)
-    launch_env_reward_car(h->car, h->d_state, h->d_reward, h->rollout_variant == 4 ? 3 : h->rollout_variant, h->st);
+    launch_env_reward_car(h->car, h->d_state, h->d_reward, h->rollout_variant >= 4 ? 3 : h->rollout_variant, h->st);
   else
     launch_env_reward_mc(h->mc, h->d_state, done, h->d_reward, h->st);
   h->launches += 1;
@@ -1445,7 +1461,7 @@ int mpopis_b200_warp_cycles(mpopis_t *h, int64_t *cycles_out, int64_t n) {
   if (!h || !cycles_out || n < 1) return fail(MPOPIS_ERR_BAD_ARG, "bad argument");
   if (!h->d_warp_cycles) return fail(MPOPIS_ERR_BAD_ARG, "set_option(\"rollout_profile\", 1) first");
   if (int rc = set_device(h)) return rc;
-  const int64_t nw = 4 * ((int64_t)h->Kloc / 32 + 2);
+  const int64_t nw = 8 * ((int64_t)h->Kloc / 32 + 2);
   CU(cudaStreamSynchronize(h->st));
   CU(cudaMemcpy(cycles_out, h->d_warp_cycles, sizeof(long long) * (size_t)(n < nw ? n : nw), cudaMemcpyDeviceToHost));
   return 0;

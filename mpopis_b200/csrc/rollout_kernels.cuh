@@ -46,7 +46,7 @@ __device__ __forceinline__ double cars_step_reward(const CarEnvArgs &env, const 
 #pragma unroll
     for (int j = c + 1; j < NCARS; ++j) {
       const double dx = s[8 * j] - s[8 * c], dy = s[8 * j + 1] - s[8 * c + 1];
-      const double dd = sqrt(dx * dx + dy * dy);
+      const double dd = MODE == 3 ? sqrt_fast(dx * dx + dy * dy) : sqrt(dx * dx + dy * dy);
       rew += -dd;
       if (dd <= 4.0) rew += -11000.0;  // MCR:153-155 (docstring says −7000; code is −11000)
     }

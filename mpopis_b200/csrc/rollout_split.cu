@@ -42,8 +42,8 @@ namespace {
 namespace ptx = cuda::ptx;
 
 constexpr int GROUP = 5, NGROUP = 3, RING = GROUP * NGROUP;  // sub-step slots per velocity warp, handed over in groups
-constexpr int VW = 2;                                         // velocity warps per CTA (= rollouts per pose lane)
-constexpr int CTA = 32 * (VW + 1);
+constexpr int GPS = 2;                                        // groups per control step: the kernel requires nsub == 10
+constexpr int VW = 2;                                         // velocity warps per CTA
 
 template <int NCARS>
 struct SplitSmem {
@@ -71,7 +71,8 @@ struct VelState {
   double Vx, Vy, psid, sg;
 };
 __device__ __noinline__ VelState vel_group_general(const CarParams &P, double ddt, double accel, double bk, double split,
-                                                   double delta0, double dlt, int i0, VelState st, double *slot0) {
+                                                   double delta0, double dlt, int i0, VelState st, double *slot0,
+                                                   int slot_stride) {
   double Vx = st.Vx, Vy = st.Vy, psid = st.psid, sg = st.sg;
   const double inv_Izz = 1 / P.Izz, inv_m = 1 / P.m;
   for (int j = 0; j < GROUP; ++j) {
@@ -99,7 +100,7 @@ __device__ __noinline__ VelState vel_group_general(const CarParams &P, double dd
     psid += psidd * ddt;  // CAR:326
     Vx += Vx_dot * ddt;   // CAR:327
     Vy += Vy_dot * ddt;   // CAR:328
-    double *sl = slot0 + (size_t)j * (sizeof(((SplitSmem<1> *)0)->ring[0][0]) / sizeof(double));
+    double *sl = slot0 + (size_t)j * slot_stride;  // ring[vw][slot][car][{Vx, Vy, Ψ̇δt}][lane]
     sl[0] = Vx, sl[32] = Vy, sl[64] = psid * ddt;
   }
   return VelState{Vx, Vy, psid, sg};
@@ -124,12 +125,44 @@ struct PoseCar {  // pose-side state of one car
   double x, y, psi, sp, cp;
 };
 
+// Everything a control step needs that does NOT depend on the velocities: action (clamped U + noise), steering rate,
+// tyre constants for an assumed sign(Vx), sin/cos of the steering increment and of δ at the step's start. δ advances
+// by nsub·rate·δt, so δ(t+1) is known when step t begins: the constants of step t+1 are computed DURING step t (inside
+// the straight-line block of its first sub-step group, where ptxas interleaves them with the recurrence) instead of
+// in front of it — ≈ 850 of ≈ 3100 cycles per control step of a lone velocity warp were this prologue (ablations:
+// tools/ablate.py, profiles/r2_split_ablation.txt).
+struct StepK {
+  TireConsts tc;
+  double dlt, sdl, cdl, accel, bk, split, sgp, sd0, cd0, pedal, delta0;
+  bool pre_ok;
+};
+
+__device__ __forceinline__ StepK make_step(const CarParams &P, const CarDerived &D, double dt, double ddt, double v0,
+                                           double v1, double delta0, double sg_guess) {
+  StepK k;
+  const double a0 = clamp1(v0), a1 = clamp1(v1);                                  // UTL:55-67
+  const double tgt = a0 * P.d_max - delta0;
+  const double rate = fmin(fast_div(fabs(tgt), dt), P.dd_max) * jl_sign(tgt);     // CAR:295-296
+  k.accel = P.Fx_max * fmax(a1, 0.0);                                             // CAR:310
+  k.bk = P.Fx_min * fmin(a1, 0.0);                                                // CAR:311 without sign(Vx)
+  k.split = a1 <= 0.0 ? P.l_brake : P.l_drive;
+  k.sgp = sg_guess;
+  k.tc = tire_consts_der(P, D, k.accel, k.bk, k.split, sg_guess);
+  k.dlt = rate * ddt;
+  k.pre_ok = (fmax(fabs(delta0), fabs(a0 * P.d_max)) <= 0.78) & (fabs(k.dlt) <= 0.03);
+  sincos_tiny(k.dlt, &k.sdl, &k.cdl);       // |rate·δt| <= δ̇_max·δt = 0.0157 for the default car
+  sincos_kernel(delta0, &k.sd0, &k.cd0);    // used when the δ recurrence is re-synchronised (every 5th step / after a repair)
+  k.pedal = a1, k.delta0 = delta0;
+  return k;
+}
+
 template <int NCARS>
-__device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm, int vw,
-                                              int k, int lane, long long *waited) {
+__device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm,
+                                              const double *Us, int vw, int k, int lane, long long *waited) {
   constexpr int AS = 2 * NCARS;
-  const int gps = env.nsub / GROUP, T = a.T;  // groups per control step (the launcher guarantees nsub % GROUP == 0)
+  const int T = a.T, cs = AS * T;
   const double ddt = env.ddt;
+  const double *Uc = Us, *Uo = Us + cs, *Bv = Us + 2 * cs;  // pol.U, U_orig, (γ U_origᵀ Σ⁻¹) staged in shared memory
   VelCar car[NCARS];
 #pragma unroll
   for (int c = 0; c < NCARS; ++c) {
@@ -138,60 +171,66 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
     car[c].sd = 0.0, car[c].cd = 1.0, car[c].trig_valid = false;
   }
   const double *Ek = a.E + k;
-  double cc = 0.0, e_next[AS];
+  double cc = 0.0, e1[AS], e2[AS];  // noise of the next step (its constants are built one step ahead) and the one after
 #pragma unroll
-  for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)r * a.ldk];
+  for (int r = 0; r < AS; ++r) {
+    e1[r] = Ek[(size_t)r * a.ldk];
+    e2[r] = T > 1 ? Ek[(size_t)(AS + r) * a.ldk] : 0.0;
+  }
+  StepK cur[NCARS], nxt[NCARS];
+#pragma unroll
+  for (int c = 0; c < NCARS; ++c) {
+    const double v0 = Uc[2 * c] + e1[2 * c], v1 = Uc[2 * c + 1] + e1[2 * c + 1];  // Vₖ = pol.U + E[:,k], POL:271
+    if (a.bvec) cc += Bv[2 * c] * (v0 - Uo[2 * c]) + Bv[2 * c + 1] * (v1 - Uo[2 * c + 1]);  // POL:272
+    cur[c] = make_step(env.car[c], env.der[c], env.dt, ddt, v0, v1, car[c].delta, jl_sign(car[c].Vx));
+    nxt[c] = cur[c];
+  }
   int gi = 0;  // global group counter of this rollout
   for (int t = 0; t < T; ++t) {
-    double act[AS];
 #pragma unroll
-    for (int r = 0; r < AS; ++r) {
-      const int row = t * AS + r;
-      const double v = __ldg(a.U + row) + e_next[r];                          // Vₖ = pol.U + E[:,k], POL:271
-      if (a.bvec) cc += __ldg(a.bvec + row) * (v - __ldg(a.U_orig + row));    // POL:272
-      act[r] = clamp1(v);                                                     // UTL:55-67
-    }
-    if (t + 1 < T) {
+    for (int r = 0; r < AS; ++r) e1[r] = e2[r];  // E(t+1)
+    if (t + 2 < T) {
 #pragma unroll
-      for (int r = 0; r < AS; ++r) e_next[r] = Ek[(size_t)((t + 1) * AS + r) * a.ldk];
+      for (int r = 0; r < AS; ++r) e2[r] = Ek[(size_t)((t + 2) * AS + r) * a.ldk];
     }
-    // ---- per control step, per car: steering rate, tyre constants (CAR:295-297, 310-318) ----
-    TireConsts tc[NCARS];
-    double dlt[NCARS], sdl[NCARS], cdl[NCARS], dpsi[NCARS], accel[NCARS], bk[NCARS], split[NCARS], sg[NCARS];
+    // ---- what DOES depend on the velocities at the step's start ----
+    double dpsi[NCARS], sg[NCARS];
     int hvx0[NCARS], brake_mask[NCARS];
     bool gen[NCARS];  // this lane integrates the rest of the control step on the general path
 #pragma unroll
     for (int c = 0; c < NCARS; ++c) {
-      const CarParams &P = env.car[c];
-      const CarDerived &D = env.der[c];
-      const double a0 = act[2 * c], a1 = act[2 * c + 1];
-      const double tgt = a0 * P.d_max - car[c].delta;
-      const double rate = fmin(fast_div(fabs(tgt), env.dt), P.dd_max) * jl_sign(tgt);  // CAR:295-296
-      accel[c] = P.Fx_max * fmax(a1, 0.0);                                             // CAR:310
-      bk[c] = P.Fx_min * fmin(a1, 0.0);                                                // CAR:311 without sign(Vx)
-      split[c] = a1 <= 0.0 ? P.l_brake : P.l_drive;
       sg[c] = jl_sign(car[c].Vx);
-      tc[c] = tire_consts_der(P, D, accel[c], bk[c], split[c], sg[c]);
-      dlt[c] = rate * ddt;
-      hvx0[c] = hi32(car[c].Vx), brake_mask[c] = bk[c] != 0.0 ? (int)0x80000000 : 0;
-      gen[c] = !((fmax(fabs(car[c].delta), fabs(a0 * P.d_max)) <= 0.78) & (car[c].Vx != 0.0) & (fabs(dlt[c]) <= 0.03));
-      sincos_tiny(dlt[c], &sdl[c], &cdl[c]);  // |rate·δt| <= δ̇_max·δt = 0.0157 for the default car
-      if (!car[c].trig_valid || (t % 5) == 0) sincos_kernel(car[c].delta, &car[c].sd, &car[c].cd);
-      dpsi[c] = car[c].psid * ddt;  // Ψ̇δt of the CURRENT Ψ̇: the −Ψ̇Vx / +Ψ̇Vy terms of the next sub-step
+      if (cur[c].bk != 0.0 && sg[c] != cur[c].sgp)  // rare: the car changed direction while the constants were in flight
+        cur[c].tc = tire_consts_der(env.car[c], env.der[c], cur[c].accel, cur[c].bk, cur[c].split, sg[c]);
+      hvx0[c] = hi32(car[c].Vx), brake_mask[c] = cur[c].bk != 0.0 ? (int)0x80000000 : 0;
+      gen[c] = !(cur[c].pre_ok & (car[c].Vx != 0.0));
+      if (!car[c].trig_valid || (t % 5) == 0) car[c].sd = cur[c].sd0, car[c].cd = cur[c].cd0;
+      dpsi[c] = car[c].psid * ddt;
     }
-    for (int q = 0; q < gps; ++q, ++gi) {
+#pragma unroll
+    for (int q = 0; q < GPS; ++q, ++gi) {
       const int grp = gi % NGROUP;
       if (gi >= NGROUP) bar_wait(&sm.empty[vw][grp], (unsigned)((gi / NGROUP - 1) & 1), waited);
+      if (q == 0 && t + 1 < T) {  // constants of step t + 1, overlapped with this group's recurrence
+#pragma unroll
+        for (int c = 0; c < NCARS; ++c) {
+          const int row = (t + 1) * AS + 2 * c;
+          const double v0 = Uc[row] + e1[2 * c], v1 = Uc[row + 1] + e1[2 * c + 1];
+          if (a.bvec) cc += Bv[row] * (v0 - Uo[row]) + Bv[row + 1] * (v1 - Uo[row + 1]);
+          nxt[c] = make_step(env.car[c], env.der[c], env.dt, ddt, v0, v1, fma((double)env.nsub, cur[c].dlt, car[c].delta),
+                             sg[c]);
+        }
+      }
 #pragma unroll
       for (int c = 0; c < NCARS; ++c) {
         const CarParams &P = env.car[c];
         const CarDerived &D = env.der[c];
+        const TireConsts &tc = cur[c].tc;
+        const double sdl = cur[c].sdl, cdl = cur[c].cdl;
         double Vx = car[c].Vx, Vy = car[c].Vy, psid = car[c].psid, sd = car[c].sd, cd = car[c].cd, dp = dpsi[c];
         int bad = 0;
         // --- GROUP straight-line sub-steps, valid for every Vx != 0 and den != 0. The arithmetic is car_step_spec's
-        // (car_model.cuh), re-associated so that the loop-carried chain (Vx, Vy, Ψ̇) -> ... -> (Vx, Vy, Ψ̇) is as short as
-        // the mathematics allows (a dependent FP64 instruction issues 23-25 cycles after its producer on B200, and
-        // this chain IS the latency of a rollout):
+        // (car_model.cuh), re-associated so that the loop-carried chain (Vx, Vy, Ψ̇) -> ... -> (Vx, Vy, Ψ̇) is short:
         //   * tan α_f = num/den and tan α_r = y_r/Vx through two reciprocal seeds (MUFU) instead of one of den·Vx — the
         //     rear one starts from Vx, available when the sub-step begins; the Newton correction is applied to the
         //     quotient, t = t₀(1 + e + e²) with t₀ = num·r₀, not to the reciprocal first (one operation fewer in series);
@@ -199,19 +238,17 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
         //   * the Euler updates (CAR:322-328) written as ONE fma on each tyre force, everything else pre-summed:
         //       Ψ̇' = (c₁cosδ)F_yf + [c₁F_xf sinδ + Ψ̇ − c₂F_yr],  Vy' = (c_m cosδ)F_yf + [c_m(F_xf sinδ + F_yr) + Vy − ΨδVx],
         //       Vx' = −(c_m sinδ)F_yf + [c_m F_xf cosδ + ΨδVy + k_x Vx + c_m F_xr ∓ c_m C_D0].
-        // ≈ 10 dependent operations per sub-step instead of ≈ 16, for 3 more FP64 instructions. Differences to MODE 3 are
-        // re-association roundings (1e-16 relative per operation).
-        // The statements below are written LEVEL BY LEVEL of the dependence graph (everything that needs only the
-        // sub-step's inputs first, then what needs level 1, ...): a warp issues in order, ptxas largely keeps the order
-        // of independent instructions, and a level-ordered stream stalls once per level (≈ 24 cycles) instead of once
-        // per dependent pair — tools/sass_sched.py replays the SASS against the measured latencies.
-        const double cI1fxf = D.cI1 * tc[c].fxf, cmfxf = D.cm * tc[c].fxf, cmfxr = D.cm * tc[c].fxr;
+        // A lone warp runs one such sub-step in ≈ 150 cycles (tools/chain_bench.cu: 168 with, 137 without the validity
+        // bookkeeping; DFMA -> DFMA issues after ≈ 9 cycles, DMUL -> DFMA ≈ 17, MUFU.RCP64H -> DFMA ≈ 27 on B200).
+        // Differences to MODE 3 are re-association roundings (1e-16 relative per operation). The statements are
+        // written level by level of the dependence graph, the order ptxas largely keeps.
+        const double cI1fxf = D.cI1 * tc.fxf, cmfxf = D.cm * tc.fxf, cmfxr = D.cm * tc.fxr;
         const double nddt = -ddt;
 #pragma unroll
         for (int j = 0; j < GROUP; ++j) {
           // level 0: the δ recurrence (independent of the velocities) and everything that needs the state only
-          const double ns = fma(sd, cdl[c], cd * sdl[c]);  // sin/cos(δ + rate·δt), CAR:301
-          const double nc = fma(cd, cdl[c], -(sd * sdl[c]));
+          const double ns = fma(sd, cdl, cd * sdl);  // sin/cos(δ + rate·δt), CAR:301
+          const double nc = fma(cd, cdl, -(sd * sdl));
           sd = ns, cd = nc;
           const int hvx = hi32(Vx);
           const bool fwd = hvx >= 0;
@@ -227,7 +264,7 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
           const double k3b = fma(psid, wy, k3);                            // … + Ψ̇δt·Vy          (CAR:324)
           const double k1 = fma(cI1fxf, sd, psid);                         // Ψ̇ + c₁F_xf sinδ      (CAR:322)
           const double qI = D.cI1 * cd, qy = D.cm * cd, qx = D.cm * sd;
-          const double fxfsd = tc[c].fxf * sd;
+          const double fxfsd = tc.fxf * sd;
           // level 2
           const double num = fma(yf, cd, -vxsd), den = fma(yf, sd, vxcd);  // tan α_f = num/den, tan α_r = yr/Vx
           const double px = fma(ex, ex, ex);
@@ -240,23 +277,23 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
           // level 4
           const double e = fma(-den, r0, 1.0), t0 = num * r0;
           const double atr = fabs(ta_r);
-          const double ur = ta_r * atr, vr = fma(-tc[c].c3_r, atr, tc[c].c2_r), x1r = -P.C_ar * ta_r;
-          const bool lin_r = fwd & (atr < tc[c].thr_r);
+          const double ur = ta_r * atr, vr = fma(-tc.c3_r, atr, tc.c2_r), x1r = -P.C_ar * ta_r;
+          const bool lin_r = fwd & (atr < tc.thr_r);
           // level 5
           const double pe = fma(e, e, e);
           const double cubic_r = fma(ur, vr, x1r);  // CAR:256 as fma(t|t|, c2 − c3|t|, −C t)
           // level 6
           const double ta = fma(t0, pe, t0);
-          const double fyr = lin_r ? cubic_r : with_opposite_sign(tc[c].fymax_r, hi32(yr));  // CAR:255-259
+          const double fyr = lin_r ? cubic_r : with_opposite_sign(tc.fymax_r, hi32(yr));  // CAR:255-259
           // level 7
           const double at = fabs(ta);
-          const double u = ta * at, v = fma(-tc[c].c3_f, at, tc[c].c2_f), x1 = -P.C_af * ta;
-          const bool lin_f = (hi32(den) >= 0) & (at < tc[c].thr_f);
+          const double u = ta * at, v = fma(-tc.c3_f, at, tc.c2_f), x1 = -P.C_af * ta;
+          const bool lin_f = (hi32(den) >= 0) & (at < tc.thr_f);
           const double Kp = fma(-D.cI2, fyr, k1);
           const double Ky = fma(D.cm, fxfsd + fyr, k2);
           // level 8
           const double cubic = fma(u, v, x1);
-          const double fyf = lin_f ? cubic : with_opposite_sign(tc[c].fymax_f, fwd ? hi32(num) : hi32(yf));
+          const double fyf = lin_f ? cubic : with_opposite_sign(tc.fymax_f, fwd ? hi32(num) : hi32(yf));
           // level 9: the new state — one fma on F_yf each (CAR:322-328)
           psid = fma(qI, fyf, Kp), Vy = fma(qy, fyf, Ky), Vx = fma(-qx, fyf, Kx);
           dp = psid * ddt;
@@ -266,43 +303,46 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
         }
         gen[c] = gen[c] | (bad < 0);
         if (gen[c]) {  // rare: redo THIS group on the general path from its un-advanced state, stay there for the step
-          const VelState o = vel_group_general(P, ddt, accel[c], bk[c], split[c], car[c].delta, dlt[c], q * GROUP,
-                                               VelState{car[c].Vx, car[c].Vy, car[c].psid, sg[c]},
-                                               &sm.ring[vw][grp * GROUP][c][0][lane]);
+          const VelState o = vel_group_general(P, ddt, cur[c].accel, cur[c].bk, cur[c].split, car[c].delta, cur[c].dlt,
+                                               q * GROUP, VelState{car[c].Vx, car[c].Vy, car[c].psid, sg[c]},
+                                               &sm.ring[vw][grp * GROUP][c][0][lane], NCARS * 3 * 32);
           Vx = o.Vx, Vy = o.Vy, psid = o.psid, sg[c] = o.sg;
           dp = psid * ddt;
         }
         car[c].Vx = Vx, car[c].Vy = Vy, car[c].psid = psid, car[c].sd = sd, car[c].cd = cd, dpsi[c] = dp;
       }
-      if (q + 1 == gps) {
+      if (q + 1 == GPS) {
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
-          car[c].delta = fma((double)env.nsub, dlt[c], car[c].delta);  // CAR:301 summed
+          car[c].delta = fma((double)env.nsub, cur[c].dlt, car[c].delta);  // CAR:301 summed (= nxt[c].delta0)
           car[c].trig_valid = !gen[c];  // after a general step the δ recurrence restarts from δ itself
           // end-of-step extras for the trajectory log. ext[t & 1] was last read at the end of step t − 2, which the
           // pose warp has passed: this warp is at most NGROUP = 3 groups ahead of it
           sm.ext[vw][t & 1][c][0][lane] = car[c].psid;
           sm.ext[vw][t & 1][c][1][lane] = car[c].delta;
-          sm.ext[vw][t & 1][c][2][lane] = act[2 * c + 1];  // pedal (CAR:297, state[8])
+          sm.ext[vw][t & 1][c][2][lane] = cur[c].pedal;  // CAR:297, state[8]
         }
         if (t + 1 == T) sm.fin[vw][lane] = cc;
       }
       __syncwarp();  // every lane's slots of the group are written: hand it over
       if (lane == 0) bar_arrive(&sm.full[vw][grp]);
     }
+#pragma unroll
+    for (int c = 0; c < NCARS; ++c) cur[c] = nxt[c];
   }
 }
 
-template <int NCARS>
+// NV rollouts per lane: the pose warp serves the velocity warps v0 .. v0 + NV − 1
+template <int NCARS, int NV>
 __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm,
-                                          const TrackView &tr, int kbase, int nvw, int lane, long long *waited) {
+                                          const TrackView &tr, int kbase, int v0, int nvw, int lane, long long *waited) {
   constexpr int SS = 8 * NCARS;
-  const int gps = env.nsub / GROUP, T = a.T;
+  const int T = a.T;
   const double ddt = env.ddt;
-  PoseCar pc[VW][NCARS];
-  double cost[VW];
+  PoseCar pc[NV][NCARS];
+  double cost[NV];
 #pragma unroll
-  for (int v = 0; v < VW; ++v) {
+  for (int v = 0; v < NV; ++v) {
     cost[v] = 0.0;
 #pragma unroll
     for (int c = 0; c < NCARS; ++c) {
@@ -314,7 +354,7 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
   for (int t = 0; t < T; ++t) {
     if ((t % 5) == 0) {  // re-synchronise the heading recurrence (as MODE 3 does every 5th control step)
 #pragma unroll
-      for (int v = 0; v < VW; ++v)
+      for (int v = 0; v < NV; ++v)
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
           double psi = pc[v][c].psi;
@@ -327,16 +367,17 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
           sincos_pi(psi, &pc[v][c].sp, &pc[v][c].cp);
         }
     }
-    double vx_end[VW][NCARS], vy_end[VW][NCARS];
-    for (int q = 0; q < gps; ++q, ++gi) {
+    double vx_end[NV][NCARS], vy_end[NV][NCARS];
+#pragma unroll
+    for (int q = 0; q < GPS; ++q, ++gi) {
       const int grp = gi % NGROUP;
 #pragma unroll
-      for (int v = 0; v < VW; ++v)
-        if (v < nvw) bar_wait(&sm.full[v][grp], (unsigned)((gi / NGROUP) & 1), waited);
-      // GROUP sub-steps of VW x NCARS independent poses in one straight-line block: the short sin/cos polynomials of
+      for (int v = 0; v < NV; ++v)
+        if (v0 + v < nvw) bar_wait(&sm.full[v0 + v][grp], (unsigned)((gi / NGROUP) & 1), waited);
+      // GROUP sub-steps of NV x NCARS independent poses in one straight-line block: the short sin/cos polynomials of
       // all increments overlap, only the heading rotation (two operations per sub-step) is sequential
 #pragma unroll
-      for (int v = 0; v < VW; ++v)
+      for (int v = 0; v < NV; ++v)
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
           PoseCar &p = pc[v][c];
@@ -344,8 +385,8 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
           int wide = 0;
 #pragma unroll
           for (int j = 0; j < GROUP; ++j) {
-            Vx[j] = sm.ring[v][grp * GROUP + j][c][0][lane], Vy[j] = sm.ring[v][grp * GROUP + j][c][1][lane];
-            dpsi[j] = sm.ring[v][grp * GROUP + j][c][2][lane];
+            Vx[j] = sm.ring[v0 + v][grp * GROUP + j][c][0][lane], Vy[j] = sm.ring[v0 + v][grp * GROUP + j][c][1][lane];
+            dpsi[j] = sm.ring[v0 + v][grp * GROUP + j][c][2][lane];
             sincos_tiny(dpsi[j], &sdp[j], &cdp[j]);
             wide |= 0x3F9EB851 - (hi32(dpsi[j]) & 0x7fffffff);  // |Ψ̇δt| > 0.03 or NaN
           }
@@ -369,15 +410,15 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
           vx_end[v][c] = Vx[GROUP - 1], vy_end[v][c] = Vy[GROUP - 1];
         }
       __syncwarp();  // every lane has read the group: give it back
-      if (lane == 0 && !(q + 1 == gps && t + 1 == T)) {
+      if (lane == 0 && !(q + 1 == GPS && t + 1 == T)) {
 #pragma unroll
-        for (int v = 0; v < VW; ++v)
-          if (v < nvw) bar_arrive(&sm.empty[v][grp]);
+        for (int v = 0; v < NV; ++v)
+          if (v0 + v < nvw) bar_arrive(&sm.empty[v0 + v][grp]);
       }
     }
     // ---- end of the control step: heading wrap (CAR:330), reward (CAR:201-213 / MCR:145-158), log ----
 #pragma unroll
-    for (int v = 0; v < VW; ++v) {
+    for (int v = 0; v < NV; ++v) {
       double s[SS];
 #pragma unroll
       for (int c = 0; c < NCARS; ++c) {
@@ -397,18 +438,18 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
 #pragma unroll
         for (int j = c + 1; j < NCARS; ++j) {
           const double dx = s[8 * j] - s[8 * c], dy = s[8 * j + 1] - s[8 * c + 1];
-          const double dd = sqrt(dx * dx + dy * dy);
+          const double dd = sqrt_fast(dx * dx + dy * dy);
           rew += -dd;
           if (dd <= 4.0) rew += -11000.0;  // MCR:153-155 (docstring says −7000; code is −11000)
         }
       }
       cost[v] -= rew;  // UTL:137-138
-      const int k = kbase + v * 32 + lane;
-      if (a.traj && v < nvw && k < a.K) {
+      const int k = kbase + (v0 + v) * 32 + lane;
+      if (a.traj && v0 + v < nvw && k < a.K) {
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
-          s[8 * c + 5] = sm.ext[v][t & 1][c][0][lane], s[8 * c + 6] = sm.ext[v][t & 1][c][1][lane];
-          s[8 * c + 7] = sm.ext[v][t & 1][c][2][lane];
+          s[8 * c + 5] = sm.ext[v0 + v][t & 1][c][0][lane], s[8 * c + 6] = sm.ext[v0 + v][t & 1][c][1][lane];
+          s[8 * c + 7] = sm.ext[v0 + v][t & 1][c][2][lane];
         }
 #pragma unroll
         for (int q = 0; q < SS; ++q) a.traj[((size_t)k * SS + q) * T + t] = s[q];  // UTL:139-141
@@ -416,21 +457,23 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
     }
   }
 #pragma unroll
-  for (int v = 0; v < VW; ++v) {
-    const int k = kbase + v * 32 + lane;
-    if (v < nvw && k < a.K) a.costs[k] = cost[v] + sm.fin[v][lane];  // POL:274-275
+  for (int v = 0; v < NV; ++v) {
+    const int k = kbase + (v0 + v) * 32 + lane;
+    if (v0 + v < nvw && k < a.K) a.costs[k] = cost[v] + sm.fin[v0 + v][lane];  // POL:274-275
   }
 }
 
-template <int NCARS>
-__global__ void __launch_bounds__(CTA) __maxnreg__(NCARS == 1 ? 96 : 255) rollout_car_split_kernel(const __grid_constant__ CarEnvArgs env,
-                                                                 const __grid_constant__ RolloutArgs a,
-                                                                 const int *stop) {
+// NV: rollouts per pose lane (pose warps per CTA = VW / NV). REGS: register budget per thread — the velocity chain's
+// schedule and the pose warp's unrolled groups want ≈ 150; 96 keeps every rollout of K = 65 536 resident at once.
+template <int NCARS, int NV, int REGS>
+__global__ void __launch_bounds__(32 * (VW + VW / NV)) __maxnreg__(REGS)
+    rollout_car_split_kernel(const __grid_constant__ CarEnvArgs env, const __grid_constant__ RolloutArgs a, const int *stop) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (stop && *stop) return;
   SplitSmem<NCARS> &sm = *reinterpret_cast<SplitSmem<NCARS> *>(smem_raw);
   double *trk_s = reinterpret_cast<double *>(smem_raw + sizeof(SplitSmem<NCARS>));
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double *Us = trk_s + 3 * env.n_trk;  // pol.U | U_orig | bvec, cs doubles each
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cs = 2 * NCARS * a.T;
   const int kbase = blockIdx.x * (32 * VW);
   const int nvw = min(VW, (a.K - kbase + 31) / 32);  // velocity warps of this CTA that own at least one rollout
   if (threadIdx.x == 0) {
@@ -442,18 +485,26 @@ __global__ void __launch_bounds__(CTA) __maxnreg__(NCARS == 1 ? 96 : 255) rollou
   }
   const long long t_begin = a.warp_cycles ? clock64() : 0;
   for (int i = threadIdx.x; i < 3 * env.n_trk; i += blockDim.x) trk_s[i] = env.trk[i];
+  for (int i = threadIdx.x; i < cs; i += blockDim.x) {
+    Us[i] = __ldg(a.U + i), Us[cs + i] = __ldg(a.U_orig + i);
+    Us[2 * cs + i] = a.bvec ? __ldg(a.bvec + i) : 0.0;
+  }
+  if (nvw < VW)  // a pose warp integrates its rollouts unconditionally: give the absent ones benign inputs
+    for (int i = threadIdx.x; i < (int)(sizeof(sm.ring) / sizeof(double)); i += blockDim.x) (&sm.ring[0][0][0][0][0])[i] = 0.0;
   __syncthreads();
   const TrackView tr{trk_s, trk_s + env.n_trk, trk_s + 2 * env.n_trk, env.n_trk,
                      env.lut, env.lut_x0, env.lut_y0, env.lut_inv_c, env.lut_nx, env.lut_ny};
   long long waited = 0, *wp = a.warp_cycles ? &waited : nullptr;
   if (w < VW) {
-    if (w < nvw) velocity_warp<NCARS>(env, a, sm, w, min(kbase + w * 32 + lane, a.K - 1), lane, wp);  // padding lanes copy the last rollout
+    if (w < nvw) velocity_warp<NCARS>(env, a, sm, Us, w, min(kbase + w * 32 + lane, a.K - 1), lane, wp);  // padding lanes copy the last rollout
   } else {
-    pose_warp<NCARS>(env, a, sm, tr, kbase, nvw, lane, wp);
+    const int v0 = (w - VW) * NV;
+    if (v0 < nvw) pose_warp<NCARS, NV>(env, a, sm, tr, kbase, v0, nvw, lane, wp);
   }
-  if (a.warp_cycles && lane == 0) {  // "rollout_profile": [total | waiting on the ring] cycles per warp, role = index % 3
-    a.warp_cycles[2 * (blockIdx.x * (VW + 1) + w)] = clock64() - t_begin;
-    a.warp_cycles[2 * (blockIdx.x * (VW + 1) + w) + 1] = waited;
+  if (a.warp_cycles && lane == 0) {  // "rollout_profile": [total | waiting on the ring] cycles per warp
+    constexpr int WPC = VW + VW / NV;
+    a.warp_cycles[2 * (blockIdx.x * WPC + w)] = clock64() - t_begin;
+    a.warp_cycles[2 * (blockIdx.x * WPC + w) + 1] = waited;
   }
 }
 
@@ -462,24 +513,31 @@ __global__ void __launch_bounds__(CTA) __maxnreg__(NCARS == 1 ? 96 : 255) rollou
 int rollout_split_max_cars() { return 3; }
 
 // returns 0 when the configuration is not covered (the caller falls back to the thread-per-rollout kernel)
-int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, const int *stop, cudaStream_t st) {
-  if (env.nsub < GROUP || env.nsub % GROUP) return 0;  // the ring hands over groups of GROUP sub-steps
+template <int N, int NV, int REGS>
+static int launch_split(const CarEnvArgs &env, const RolloutArgs &a, const int *stop, cudaStream_t st) {
   const int grid = (a.K + 32 * VW - 1) / (32 * VW);
-  const size_t trk = sizeof(double) * 3 * env.n_trk;
-#define MPOPIS_SPLIT(N)                                                                                              \
-  case N: {                                                                                                          \
-    const size_t smem = sizeof(SplitSmem<N>) + trk;                                                                  \
-    if (smem > 200 * 1024) return 0;                                                                                 \
-    cudaFuncSetAttribute(rollout_car_split_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    rollout_car_split_kernel<N><<<grid, CTA, smem, st>>>(env, a, stop);                                             \
-    return 1;                                                                                                        \
-  }
+  const size_t smem = sizeof(SplitSmem<N>) + sizeof(double) * (3 * (size_t)env.n_trk + 3 * (size_t)2 * N * a.T);
+  if (smem > 200 * 1024) return 0;
+  cudaFuncSetAttribute(rollout_car_split_kernel<N, NV, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // all of the SM's L1/shared array as shared memory: 7 CTAs x 28 KB must be resident together at K = 65 536
+  cudaFuncSetAttribute(rollout_car_split_kernel<N, NV, REGS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  rollout_car_split_kernel<N, NV, REGS><<<grid, 32 * (VW + VW / NV), smem, st>>>(env, a, stop);
+  return 1;
+}
+
+// Rollouts one launch keeps resident at once (one wave); beyond it the thread-per-rollout kernel (MODE 3, every rollout
+// of K = 65 536 resident at 128 registers) is the better shape. wide = 1: 4 warps x 160 registers per CTA of 64 rollouts.
+int rollout_split_capacity(int n_cars, int num_sms) { return n_cars == 1 ? num_sms * 3 * 32 * VW : num_sms * 2 * 32 * VW; }
+
+// wide: 0 = 2 velocity + 1 pose warp, 96 registers (7 CTAs per SM); 1 = 2 + 2 warps, 160 registers (3 CTAs per SM)
+int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, int wide, const int *stop, cudaStream_t st) {
+  if (env.nsub != GROUP * GPS) return 0;  // the ring hands over two groups of five sub-steps per control step
   switch (env.n_cars) {
-    MPOPIS_SPLIT(1)
-    MPOPIS_SPLIT(2)
-    MPOPIS_SPLIT(3)
+    case 1: return wide ? launch_split<1, 1, 160>(env, a, stop, st) : launch_split<1, 2, 96>(env, a, stop, st);
+    case 2: return launch_split<2, 1, 255>(env, a, stop, st);
+    case 3: return launch_split<3, 1, 255>(env, a, stop, st);
   }
-#undef MPOPIS_SPLIT
   return 0;
 }
 

@@ -320,7 +320,7 @@ class Engine:
 
     def warp_cycles(self) -> np.ndarray:
         """Per-warp clock64() cycles of the most recent rollout launch (needs set_option("rollout_profile", 1))."""
-        n = 4 * (self.Kloc // 32 + 2)  # variant 4 writes [total, waiting] per warp, 3 warps per 64 rollouts
+        n = 8 * (self.Kloc // 32 + 2)  # variant 4/5: [total, waiting] per warp (3 per 64 rollouts) + phase clocks
         out = np.zeros(n, dtype=np.int64)
         self._chk(self.b.warp_cycles(self.h, out.ctypes.data_as(C.POINTER(C.c_int64)), n))
         return out

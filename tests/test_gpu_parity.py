@@ -515,11 +515,12 @@ def test_warp_specialised_rollouts_equal_the_thread_per_rollout_kernel(gpu_bound
     E = rng.standard_normal((g.cs, K)) * np.tile(np.array([0.25, 0.32] * n_cars), T)[:, None]
     U = rng.uniform(-0.3, 0.3, g.cs)
     out = {}
-    for variant in (3, 4):
+    for variant in (3, 4, 5):
         g.set_option("rollout_variant", variant)
         out[variant] = (g.rollout_costs(env.state, 0, U, U, E), g.fetch(costs=False, weights=False, traj=True)["traj"])
-    r = rel(out[4][0], out[3][0])
-    assert (r > TIGHT).sum() <= max(1, K // 500), f"{(r > TIGHT).sum()} of {K} costs differ (max rel {r.max():.2e})"
-    print(f"variant 4 vs 3: median rel {np.median(r):.2e}, 99.9 % {np.quantile(r, 0.999):.2e}")
-    tr = np.abs(out[4][1] - out[3][1]) / np.maximum(1.0, np.abs(out[3][1]))
-    assert np.quantile(tr, 0.999) < 1e-9, "trajectory logs differ"
+    for variant in (4, 5):  # 5 = the same kernel compiled with 160 registers per thread
+        r = rel(out[variant][0], out[3][0])
+        assert (r > TIGHT).sum() <= max(1, K // 500), f"{(r > TIGHT).sum()} of {K} costs differ (max rel {r.max():.2e})"
+        print(f"variant {variant} vs 3: median rel {np.median(r):.2e}, 99.9 % {np.quantile(r, 0.999):.2e}")
+        tr = np.abs(out[variant][1] - out[3][1]) / np.maximum(1.0, np.abs(out[3][1]))
+        assert np.quantile(tr, 0.999) < 1e-9, "trajectory logs differ"

@@ -9,7 +9,7 @@ from mpopis_b200 import _lib
 
 bound = _lib.product()
 for K in [int(x) for x in (sys.argv[1:] or ["65536", "150", "4096", "262144"])]:
-    for variant in (3, 4):
+    for variant in (3, 4, 5):
         env, eng = make_engine(bound, K, 0, 1, 0)
         eng.set_option("rollout_variant", variant)
         U, st = np.zeros(eng.cs), env.state.copy()
