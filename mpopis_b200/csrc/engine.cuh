@@ -105,7 +105,8 @@ void launch_rollout_car(const CarEnvArgs &env, const RolloutArgs &a, int variant
 // rollout_split.cu ("v5", rollout_variant 4): velocity warps + pose/reward warps; returns 0 when not applicable
 int rollout_split_max_cars();
 int rollout_split_capacity(int n_cars, int num_sms);  // rollouts one launch keeps resident (one wave)
-int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, int wide, const int *stop, cudaStream_t s);
+int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, int wide, int spin, const int *stop,
+                             cudaStream_t s);
 void launch_rollout_mc(const McEnvArgs &env, const RolloutArgs &a, int block, const int *stop, cudaStream_t s);
 void launch_track_query(const CarEnvArgs &env, const double *pos, int n, int *idx, int *idx2, double *dist,
                         unsigned char *within, int use_lut, cudaStream_t s);

@@ -73,6 +73,7 @@ struct mpopis_handle {
   double gamma = 0.0;
   uint64_t seed = 0;
   long long step = 0;
+  int rollout_spin = -1;  // split kernel hand-over: -1 auto, 0 mbarrier, 1 spin on shared-memory counters
   int rollout_variant = 6, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1, sel_max = 1;
   bool moments_small = true;  // single-CTA moment chain for small n ("moments_small" option, A/B)
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
@@ -364,7 +365,9 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
     if (variant == 6)
       variant = (h->cfg.n_cars <= rollout_split_max_cars() && h->Kloc <= rollout_split_capacity(h->cfg.n_cars, h->num_sms) &&
                  !h->rollout_stage) ? 5 : 3;
-    if (!(variant >= 4 && launch_rollout_car_split(h->car, a, variant == 5, h->stop(), h->st)))
+    const int ctas = (h->Kloc + 63) / 64;
+    const int spin = h->rollout_spin < 0 ? ctas <= h->num_sms : h->rollout_spin;  // default: only at <= 1 CTA per SM
+    if (!(variant >= 4 && launch_rollout_car_split(h->car, a, variant == 5, spin, h->stop(), h->st)))
       launch_rollout_car(h->car, a, variant >= 4 ? 3 : variant, h->rollout_block,
                          h->rollout_stage, h->stop(), h->st);
   } else
@@ -1121,6 +1124,8 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     h->rollout_block = b;
   } else if (!strcmp(key, "moments_small")) {
     h->moments_small = value != 0.0;
+  } else if (!strcmp(key, "rollout_spin")) {
+    h->rollout_spin = value < 0 ? -1 : (value != 0.0);
   } else if (!strcmp(key, "fuse_cov")) {
     h->fuse_cov = value != 0.0;
   } else if (!strcmp(key, "apply_l")) {

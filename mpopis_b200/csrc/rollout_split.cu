@@ -51,6 +51,7 @@ struct SplitSmem {
   double ext[VW][2][NCARS][3][32];      // per control step (parity-buffered): Ψ̇, δ, pedal at its end (trajectory log)
   double fin[VW][32];                   // control cost (POL:272) of the finished rollout
   uint64_t full[VW][NGROUP], empty[VW][NGROUP];
+  unsigned nfull[VW][NGROUP], nempty[VW][NGROUP];  // SPIN hand-over: completed fills / drains of each group
 };
 
 __device__ __forceinline__ void bar_wait(uint64_t *bar, unsigned parity, long long *waited = nullptr) {
@@ -62,6 +63,19 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, unsigned parity, long lo
 }
 __device__ __forceinline__ void bar_arrive(uint64_t *bar) {
   (void)ptx::mbarrier_arrive(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar);
+}
+// SPIN hand-over (latency regime: at most one CTA per SM, so a polling warp takes issue slots from nobody): a counter
+// per group in shared memory, bumped by one lane after the warp's stores are fenced, polled by every lane of the peer.
+// mbarrier.try_wait parks the warp and costs ≈ 1000 cycles per control step at K = 150 (profiles/r2_split_ablation.txt).
+__device__ __forceinline__ void spin_wait(const unsigned *cnt, unsigned want) {
+  while (*reinterpret_cast<const volatile unsigned *>(cnt) < want) {
+  }
+  __threadfence_block();  // acquire: the ring slots are read after the counter
+}
+__device__ __forceinline__ void spin_post(unsigned *cnt, unsigned value, int lane) {
+  __threadfence_block();  // release: this lane's ring stores before the counter
+  __syncwarp();
+  if (lane == 0) *reinterpret_cast<volatile unsigned *>(cnt) = value;
 }
 
 // GROUP Euler sub-steps of the velocity recurrence on the general path (car_step_fast's loop body, CAR:301-328, without
@@ -156,7 +170,7 @@ __device__ __forceinline__ StepK make_step(const CarParams &P, const CarDerived 
   return k;
 }
 
-template <int NCARS>
+template <int NCARS, bool SPIN>
 __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm,
                                               const double *Us, int vw, int k, int lane, long long *waited) {
   constexpr int AS = 2 * NCARS;
@@ -210,7 +224,10 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
 #pragma unroll
     for (int q = 0; q < GPS; ++q, ++gi) {
       const int grp = gi % NGROUP;
-      if (gi >= NGROUP) bar_wait(&sm.empty[vw][grp], (unsigned)((gi / NGROUP - 1) & 1), waited);
+      if (gi >= NGROUP) {
+        if (SPIN) spin_wait(&sm.nempty[vw][grp], (unsigned)(gi / NGROUP));
+        else bar_wait(&sm.empty[vw][grp], (unsigned)((gi / NGROUP - 1) & 1), waited);
+      }
       if (q == 0 && t + 1 < T) {  // constants of step t + 1, overlapped with this group's recurrence
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
@@ -324,8 +341,11 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
         }
         if (t + 1 == T) sm.fin[vw][lane] = cc;
       }
-      __syncwarp();  // every lane's slots of the group are written: hand it over
-      if (lane == 0) bar_arrive(&sm.full[vw][grp]);
+      if (SPIN) spin_post(&sm.nfull[vw][grp], (unsigned)(gi / NGROUP + 1), lane);
+      else {
+        __syncwarp();  // every lane's slots of the group are written: hand it over
+        if (lane == 0) bar_arrive(&sm.full[vw][grp]);
+      }
     }
 #pragma unroll
     for (int c = 0; c < NCARS; ++c) cur[c] = nxt[c];
@@ -333,7 +353,7 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
 }
 
 // NV rollouts per lane: the pose warp serves the velocity warps v0 .. v0 + NV − 1
-template <int NCARS, int NV>
+template <int NCARS, int NV, bool SPIN>
 __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm,
                                           const TrackView &tr, int kbase, int v0, int nvw, int lane, long long *waited) {
   constexpr int SS = 8 * NCARS;
@@ -373,7 +393,10 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
       const int grp = gi % NGROUP;
 #pragma unroll
       for (int v = 0; v < NV; ++v)
-        if (v0 + v < nvw) bar_wait(&sm.full[v0 + v][grp], (unsigned)((gi / NGROUP) & 1), waited);
+        if (v0 + v < nvw) {
+          if (SPIN) spin_wait(&sm.nfull[v0 + v][grp], (unsigned)(gi / NGROUP + 1));
+          else bar_wait(&sm.full[v0 + v][grp], (unsigned)((gi / NGROUP) & 1), waited);
+        }
       // GROUP sub-steps of NV x NCARS independent poses in one straight-line block: the short sin/cos polynomials of
       // all increments overlap, only the heading rotation (two operations per sub-step) is sequential
 #pragma unroll
@@ -409,11 +432,17 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
           }
           vx_end[v][c] = Vx[GROUP - 1], vy_end[v][c] = Vy[GROUP - 1];
         }
-      __syncwarp();  // every lane has read the group: give it back
-      if (lane == 0 && !(q + 1 == GPS && t + 1 == T)) {
+      if (SPIN) {
 #pragma unroll
         for (int v = 0; v < NV; ++v)
-          if (v0 + v < nvw) bar_arrive(&sm.empty[v0 + v][grp]);
+          if (v0 + v < nvw) spin_post(&sm.nempty[v0 + v][grp], (unsigned)(gi / NGROUP + 1), lane);
+      } else {
+        __syncwarp();  // every lane has read the group: give it back
+        if (lane == 0 && !(q + 1 == GPS && t + 1 == T)) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            if (v0 + v < nvw) bar_arrive(&sm.empty[v0 + v][grp]);
+        }
       }
     }
     // ---- end of the control step: heading wrap (CAR:330), reward (CAR:201-213 / MCR:145-158), log ----
@@ -465,7 +494,7 @@ __device__ __forceinline__ void pose_warp(const CarEnvArgs &env, const RolloutAr
 
 // NV: rollouts per pose lane (pose warps per CTA = VW / NV). REGS: register budget per thread — the velocity chain's
 // schedule and the pose warp's unrolled groups want ≈ 150; 96 keeps every rollout of K = 65 536 resident at once.
-template <int NCARS, int NV, int REGS>
+template <int NCARS, int NV, int REGS, bool SPIN>
 __global__ void __launch_bounds__(32 * (VW + VW / NV)) __maxnreg__(REGS)
     rollout_car_split_kernel(const __grid_constant__ CarEnvArgs env, const __grid_constant__ RolloutArgs a, const int *stop) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -480,7 +509,10 @@ __global__ void __launch_bounds__(32 * (VW + VW / NV)) __maxnreg__(REGS)
 #pragma unroll
     for (int v = 0; v < VW; ++v)
 #pragma unroll
-      for (int q = 0; q < NGROUP; ++q) ptx::mbarrier_init(&sm.full[v][q], 1), ptx::mbarrier_init(&sm.empty[v][q], 1);
+      for (int q = 0; q < NGROUP; ++q) {
+        ptx::mbarrier_init(&sm.full[v][q], 1), ptx::mbarrier_init(&sm.empty[v][q], 1);
+        sm.nfull[v][q] = 0, sm.nempty[v][q] = 0;
+      }
     ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
   }
   const long long t_begin = a.warp_cycles ? clock64() : 0;
@@ -496,10 +528,10 @@ __global__ void __launch_bounds__(32 * (VW + VW / NV)) __maxnreg__(REGS)
                      env.lut, env.lut_x0, env.lut_y0, env.lut_inv_c, env.lut_nx, env.lut_ny};
   long long waited = 0, *wp = a.warp_cycles ? &waited : nullptr;
   if (w < VW) {
-    if (w < nvw) velocity_warp<NCARS>(env, a, sm, Us, w, min(kbase + w * 32 + lane, a.K - 1), lane, wp);  // padding lanes copy the last rollout
+    if (w < nvw) velocity_warp<NCARS, SPIN>(env, a, sm, Us, w, min(kbase + w * 32 + lane, a.K - 1), lane, wp);  // padding lanes copy the last rollout
   } else {
     const int v0 = (w - VW) * NV;
-    if (v0 < nvw) pose_warp<NCARS, NV>(env, a, sm, tr, kbase, v0, nvw, lane, wp);
+    if (v0 < nvw) pose_warp<NCARS, NV, SPIN>(env, a, sm, tr, kbase, v0, nvw, lane, wp);
   }
   if (a.warp_cycles && lane == 0) {  // "rollout_profile": [total | waiting on the ring] cycles per warp
     constexpr int WPC = VW + VW / NV;
@@ -513,16 +545,16 @@ __global__ void __launch_bounds__(32 * (VW + VW / NV)) __maxnreg__(REGS)
 int rollout_split_max_cars() { return 3; }
 
 // returns 0 when the configuration is not covered (the caller falls back to the thread-per-rollout kernel)
-template <int N, int NV, int REGS>
+template <int N, int NV, int REGS, bool SPIN>
 static int launch_split(const CarEnvArgs &env, const RolloutArgs &a, const int *stop, cudaStream_t st) {
   const int grid = (a.K + 32 * VW - 1) / (32 * VW);
   const size_t smem = sizeof(SplitSmem<N>) + sizeof(double) * (3 * (size_t)env.n_trk + 3 * (size_t)2 * N * a.T);
   if (smem > 200 * 1024) return 0;
-  cudaFuncSetAttribute(rollout_car_split_kernel<N, NV, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(rollout_car_split_kernel<N, NV, REGS, SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   // all of the SM's L1/shared array as shared memory: 7 CTAs x 28 KB must be resident together at K = 65 536
-  cudaFuncSetAttribute(rollout_car_split_kernel<N, NV, REGS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  cudaFuncSetAttribute(rollout_car_split_kernel<N, NV, REGS, SPIN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                        cudaSharedmemCarveoutMaxShared);
-  rollout_car_split_kernel<N, NV, REGS><<<grid, 32 * (VW + VW / NV), smem, st>>>(env, a, stop);
+  rollout_car_split_kernel<N, NV, REGS, SPIN><<<grid, 32 * (VW + VW / NV), smem, st>>>(env, a, stop);
   return 1;
 }
 
@@ -531,12 +563,17 @@ static int launch_split(const CarEnvArgs &env, const RolloutArgs &a, const int *
 int rollout_split_capacity(int n_cars, int num_sms) { return n_cars == 1 ? num_sms * 3 * 32 * VW : num_sms * 2 * 32 * VW; }
 
 // wide: 0 = 2 velocity + 1 pose warp, 96 registers (7 CTAs per SM); 1 = 2 + 2 warps, 160 registers (3 CTAs per SM)
-int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, int wide, const int *stop, cudaStream_t st) {
+// spin: poll shared-memory counters instead of parking on mbarriers (only sensible while a polling warp shares its
+// scheduler with nobody: at most one CTA per SM)
+int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, int wide, int spin, const int *stop,
+                             cudaStream_t st) {
   if (env.nsub != GROUP * GPS) return 0;  // the ring hands over two groups of five sub-steps per control step
   switch (env.n_cars) {
-    case 1: return wide ? launch_split<1, 1, 160>(env, a, stop, st) : launch_split<1, 2, 96>(env, a, stop, st);
-    case 2: return launch_split<2, 1, 255>(env, a, stop, st);
-    case 3: return launch_split<3, 1, 255>(env, a, stop, st);
+    case 1:
+      if (!wide) return launch_split<1, 2, 96, false>(env, a, stop, st);
+      return spin ? launch_split<1, 1, 160, true>(env, a, stop, st) : launch_split<1, 1, 160, false>(env, a, stop, st);
+    case 2: return spin ? launch_split<2, 1, 255, true>(env, a, stop, st) : launch_split<2, 1, 255, false>(env, a, stop, st);
+    case 3: return spin ? launch_split<3, 1, 255, true>(env, a, stop, st) : launch_split<3, 1, 255, false>(env, a, stop, st);
   }
   return 0;
 }

@@ -515,10 +515,11 @@ def test_warp_specialised_rollouts_equal_the_thread_per_rollout_kernel(gpu_bound
     E = rng.standard_normal((g.cs, K)) * np.tile(np.array([0.25, 0.32] * n_cars), T)[:, None]
     U = rng.uniform(-0.3, 0.3, g.cs)
     out = {}
-    for variant in (3, 4, 5):
-        g.set_option("rollout_variant", variant)
+    for variant, spin in ((3, 0), (4, 0), (5, 0), (5.5, 1)):  # 5.5: variant 5 handing over through spin counters
+        g.set_option("rollout_variant", int(variant))
+        g.set_option("rollout_spin", spin)
         out[variant] = (g.rollout_costs(env.state, 0, U, U, E), g.fetch(costs=False, weights=False, traj=True)["traj"])
-    for variant in (4, 5):  # 5 = the same kernel compiled with 160 registers per thread
+    for variant in (4, 5, 5.5):  # 5 = two pose warps per CTA at 160 registers per thread
         r = rel(out[variant][0], out[3][0])
         assert (r > TIGHT).sum() <= max(1, K // 500), f"{(r > TIGHT).sum()} of {K} costs differ (max rel {r.max():.2e})"
         print(f"variant {variant} vs 3: median rel {np.median(r):.2e}, 99.9 % {np.quantile(r, 0.999):.2e}")

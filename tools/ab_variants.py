@@ -9,9 +9,10 @@ from mpopis_b200 import _lib
 
 bound = _lib.product()
 for K in [int(x) for x in (sys.argv[1:] or ["65536", "150", "4096", "262144"])]:
-    for variant in (3, 4, 5):
+    for variant, spin in ((3, 0), (5, 0), (5, 1)):
         env, eng = make_engine(bound, K, 0, 1, 0)
         eng.set_option("rollout_variant", variant)
+        eng.set_option("rollout_spin", spin)
         U, st = np.zeros(eng.cs), env.state.copy()
         tot, roll = [], []
         for i in range(8):
@@ -19,6 +20,6 @@ for K in [int(x) for x in (sys.argv[1:] or ["65536", "150", "4096", "262144"])]:
             tm = eng.last_timing()
             if i >= 3:
                 tot.append(tm["total_ms"]), roll.append(tm["rollout_ms"] / tm["rollout_launches"] * 1e3)
-        print(f"K={K} variant={variant}: step {np.median(tot):.3f} ms, rollout launch {np.median(roll):.1f} µs "
+        print(f"K={K} variant={variant} spin={spin}: step {np.median(tot):.3f} ms, rollout launch {np.median(roll):.1f} µs "
               f"(min {np.min(roll):.1f}), its={its}, control={ctrl}", flush=True)
         eng.close()
