@@ -263,6 +263,9 @@ int mpopis_b200_resident_reset(mpopis_t *h, const double *state, int64_t env_t, 
 int mpopis_b200_resident_plan(mpopis_t *h, int32_t advance_env);
 int mpopis_b200_resident_read(mpopis_t *h, double *state_out, double *U_out, double *control_out,
                               int32_t *its_run_out);
+/* Σ reward(env) over the env steps of the resident loop since resident_reset (`rew += reward(env)`, car_example.jl:209;
+ * mountaincar_example.jl:149) — lets many trials run as concurrent device-resident replicas without a per-step read. */
+int mpopis_b200_resident_reward_sum(mpopis_t *h, double *sum_out);
 
 /* AIS iterations executed since resident_reset() (summed over resident_plan() calls). */
 int mpopis_b200_resident_total_its(mpopis_t *h, int64_t *total_its_out);

@@ -15,11 +15,12 @@ from .policies import (CEMPPI_Policy, CMAMPPI_Policy, GMPPI_Policy, IMPPI_Policy
                        action_space_size, block_diagm, cma_constants, get_policy, seed_b, μAISMPPI_Policy,
                        μΣAISMPPI_Policy)
 from .tracks import Track
+from .trials import run_trial_replicas
 
 __all__ = [
     "ABI_VERSION", "MPPI_Policy", "GMPPI_Policy", "IMPPI_Policy", "CEMPPI_Policy", "CMAMPPI_Policy",
     "μAISMPPI_Policy", "μΣAISMPPI_Policy", "PMCMPPI_Policy", "Track", "CarRacingEnv", "CarRacingEnvParams",
     "MultiCarRacingEnv", "ExternalEnv", "MountainCarEnv", "MountainCarEnvParams", "within_track", "calculate_β", "exceed_β",
     "block_diagm", "action_space_size", "reward", "state", "get_policy", "seed_b", "cma_constants",
-    "simulate_car_racing", "simulate_mountaincar", "quantile_ci",
+    "simulate_car_racing", "simulate_mountaincar", "quantile_ci", "run_trial_replicas",
 ]

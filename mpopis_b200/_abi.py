@@ -94,6 +94,7 @@ PRODUCT_ONLY = {
     "resident_plan": (C.c_int, [_H, C.c_int32]),
     "resident_read": (C.c_int, [_H, _D, _D, _D, _I32]),
     "resident_total_its": (C.c_int, [_H, _I64]),
+    "resident_reward_sum": (C.c_int, [_H, _D]),
     "measure_fp64_peak": (C.c_int, [_H, _D]),
     "sortperm": (C.c_int, [_H, _D, C.c_int64, _I64]),
     "elite_select": (C.c_int, [_H, _D, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _I64, _I64, _I32, _D]),

@@ -108,6 +108,20 @@ MPOPIS_HD double sqrt_fast(double x) {
 #endif
 }
 
+// 1/sqrt(x) for x > 0 without libdevice's special-case branch (its slow-path CALL splits the basic block and keeps
+// ptxas from interleaving the per-step constants with the sub-step recurrence): reciprocal-square-root seed (2^-23) and
+// one third-order correction r(1 + e/2 + 3e²/8), e = 1 − x r²: relative error e³ = 2^-69 before the final rounding.
+MPOPIS_HD double rsqrt_pos(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-(x * r), r, 1.0);
+  return fma(r, e * fma(0.375, e, 0.5), r);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 struct TrackView {
   const double *x, *y, *w;
   int n;
@@ -239,7 +253,7 @@ MPOPIS_HD TireConsts tire_consts_der(const CarParams &P, const CarDerived &D, do
   const double fzr = (D.wr + P.h_cm * fx) * D.inv_L;
   const double vf = fmax((P.mu_f * fzf) * (P.mu_f * fzf) - c.fxf * c.fxf, 1e-8);
   const double vr = fmax((P.mu_r * fzr) * (P.mu_r * fzr) - c.fxr * c.fxr, 1e-8);
-  const double rf = rsqrt_f64(vf), rr = rsqrt_f64(vr);
+  const double rf = rsqrt_pos(vf), rr = rsqrt_pos(vr);  // vf, vr >= 1e-8: no special cases, no branch
   c.fymax_f = vf * rf;
   c.fymax_r = vr * rr;
   c.thr_f = c.fymax_f * D.thrC_f;

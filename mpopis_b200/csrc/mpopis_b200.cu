@@ -842,7 +842,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   TRY(dalloc(&h->d_q, 1));
   TRY(dalloc(&h->d_lambda, 1));
   TRY(dalloc(&h->d_ones, 512));  // scratch of the multi-CTA weights kernels
-  TRY(dalloc(&h->d_reward, 1));
+  TRY(dalloc(&h->d_reward, 2));  // [reward of the last env step | running sum of the resident loop]
   TRY(dalloc(&h->d_done, 1));
   const size_t nmax = K;  // moments may run over Kloc samples or up to K elites
   h->part_doubles = (size_t)(rowsum_nchunks((int)nmax) + 1) * (2 * cs + 1);
@@ -1529,16 +1529,23 @@ int mpopis_b200_resident_reset(mpopis_t *h, const double *state, int64_t env_t, 
   if (!h || !state || !U) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (int rc = set_device(h)) return rc;
   CU(cudaMemsetAsync(h->info(), 0, sizeof(int) * 2, h->st));  // info + accumulated iteration count
+  CU(cudaMemsetAsync(h->d_reward, 0, sizeof(double) * 2, h->st));
   if (int rc = upload_inputs(h, state, env_t, U)) return rc;
   CU(cudaStreamSynchronize(h->st));
   return 0;
 }
 
+__global__ void accumulate_reward_kernel(const double *reward, double *sum) { *sum += *reward; }
+
 int mpopis_b200_resident_plan(mpopis_t *h, int32_t advance_env) {
   if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (int rc = set_device(h)) return rc;
   if (int rc = plan_step(h)) return rc;
-  if (advance_env) env_step_device(h, h->d_control);  // env(act), car_example.jl:205-207
+  if (advance_env) {
+    env_step_device(h, h->d_control);  // env(act), car_example.jl:205-207
+    accumulate_reward_kernel<<<1, 1, 0, h->st>>>(h->d_reward, h->d_reward + 1);  // rew += reward(env), car_example.jl:209
+    h->launches += 1;
+  }
   CU(cudaMemcpyAsync(h->d_U_orig, h->d_U_next, sizeof(double) * h->cs, cudaMemcpyDeviceToDevice, h->st));
   return 0;
 }
@@ -1548,6 +1555,14 @@ int mpopis_b200_resident_read(mpopis_t *h, double *state_out, double *U_out, dou
   if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (int rc = set_device(h)) return rc;
   return download_outputs(h, U_out, control_out, its_run_out, state_out ? state_out : nullptr);
+}
+
+int mpopis_b200_resident_reward_sum(mpopis_t *h, double *sum_out) {
+  if (!h || !sum_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (int rc = set_device(h)) return rc;
+  CU(cudaMemcpyAsync(sum_out, h->d_reward + 1, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return 0;
 }
 
 int mpopis_b200_measure_fp64_peak(mpopis_t *h, double *dfma_per_s_out) {

@@ -70,6 +70,14 @@ __device__ __forceinline__ bool le96(unsigned long long ka, unsigned ia, unsigne
   return ka < kb || (ka == kb && ia <= ib);
 }
 
+// histogram increment aggregated over the warp: lanes with the same digit elect one lane that adds their count. The
+// most significant digits of real cost vectors are nearly constant (sign, exponent), so un-aggregated every lane of every
+// warp would serialise on ONE shared-memory word. All 32 lanes must call this (inactive ones with valid = false).
+__device__ __forceinline__ void hist_add(unsigned *hist, unsigned digit, bool valid) {
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? digit : 0xffffffffu);
+  if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+}
+
 struct Seg {  // summary of a run of buckets
   unsigned long long first, last;
   int flags;  // bit 0 any, bit 1 gap >= 10e-3
@@ -113,10 +121,11 @@ __global__ void __launch_bounds__(ST) ce_select_kernel(const double *__restrict_
     const unsigned mask = pass < 8 ? 0x7FFu : 0xFFu;
     for (int e = tid; e < NBIN; e += ST) sh[e] = 0;
     __syncthreads();
-    for (int i = ibeg + tid; i < iend; i += ST) {
-      const unsigned long long k = cost_key(costs[i]);
+    for (int i0 = ibeg; i0 < iend; i0 += ST) {
+      const int i = i0 + tid;
+      const unsigned long long k = i < iend ? cost_key(costs[i]) : KMAX;
       if (pass == 0) mn = k < mn ? k : mn;
-      if (match96(k, (unsigned)i, pk, pi, low)) atomicAdd(&sh[digit96(k, (unsigned)i, shift, mask)], 1u);
+      hist_add(sh, digit96(k, (unsigned)i, shift, mask), i < iend && match96(k, (unsigned)i, pk, pi, low));
     }
     __syncthreads();
     unsigned *gh = ws->hist[pass % 3];
@@ -388,10 +397,11 @@ __global__ void __launch_bounds__(CT) ce_select_cluster_kernel(const double *__r
     for (int e = tid; e < NBIN; e += CT) hl[e] = 0;
     __syncthreads();
     unsigned long long mn = KMAX;
-    for (int i = ibeg + tid; i < iend; i += CT) {
-      const unsigned long long k = cost_key(costs[i]);
+    for (int i0 = ibeg; i0 < iend; i0 += CT) {
+      const int i = i0 + tid;
+      const unsigned long long k = i < iend ? cost_key(costs[i]) : KMAX;
       if (pass == 0) mn = k < mn ? k : mn;
-      if (match96(k, (unsigned)i, pk, pi, low)) atomicAdd(&hl[digit96(k, (unsigned)i, shift, mask)], 1u);
+      hist_add(hl, digit96(k, (unsigned)i, shift, mask), i < iend && match96(k, (unsigned)i, pk, pi, low));
     }
     if (pass == 0) {
 #pragma unroll
@@ -452,14 +462,16 @@ __global__ void __launch_bounds__(CT) ce_select_cluster_kernel(const double *__r
     }
     cluster.sync();
     const unsigned n = min(s0->ncand, (unsigned)NCAND);
+    unsigned long long *ck = reinterpret_cast<unsigned long long *>(sm.hist[0]);  // local copy: 256 x 8 B + 256 x 4 B
+    unsigned *ci = sm.hist[1];
+    if (b != 0 && tid < (int)n) ck[tid] = s0->cand_k[tid], ci[tid] = s0->cand_i[tid];
+    if (b == 0 && tid < (int)n) ck[tid] = sm.cand_k[tid], ci[tid] = sm.cand_i[tid];
+    __syncthreads();
     if (tid < (int)n) {
-      const unsigned long long k = s0->cand_k[tid];
-      const unsigned i = s0->cand_i[tid];
+      const unsigned long long k = ck[tid];
+      const unsigned i = ci[tid];
       int below = 0;
-      for (unsigned j = 0; j < n; ++j) {
-        const unsigned long long kj = s0->cand_k[j];
-        below += (kj < k || (kj == k && s0->cand_i[j] < i)) ? 1 : 0;
-      }
+      for (unsigned j = 0; j < n; ++j) below += (ck[j] < k || (ck[j] == k && ci[j] < i)) ? 1 : 0;
       if (below == (int)need) sm.tk = k, sm.ti = i;
     }
     __syncthreads();

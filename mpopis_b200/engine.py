@@ -284,6 +284,11 @@ class Engine:
         self._chk(self.b.resident_total_its(self.h, C.byref(v)))
         return v.value
 
+    def resident_reward_sum(self) -> float:
+        v = C.c_double(0.0)
+        self._chk(self.b.resident_reward_sum(self.h, C.byref(v)))
+        return v.value
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0.0)
         self._chk(self.b.measure_fp64_peak(self.h, C.byref(v)))

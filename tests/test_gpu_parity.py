@@ -525,3 +525,22 @@ def test_warp_specialised_rollouts_equal_the_thread_per_rollout_kernel(gpu_bound
         print(f"variant {variant} vs 3: median rel {np.median(r):.2e}, 99.9 % {np.quantile(r, 0.999):.2e}")
         tr = np.abs(out[variant][1] - out[3][1]) / np.maximum(1.0, np.abs(out[3][1]))
         assert np.quantile(tr, 0.999) < 1e-9, "trajectory logs differ"
+
+
+def test_trial_replicas_equal_sequential_trials(gpu_bound):
+    """§8f-2: `num_trials` independent trials (car_example.jl:170) as concurrent device-resident replicas — each
+    trial its own handle / stream / Philox key — reproduce the same trials run one after the other, bit for bit."""
+    from mpopis_b200.trials import run_trial_replicas
+
+    def make(dev):
+        env = make_env("car")
+        e = configure(Engine(gpu_bound, **engine_kwargs("cemppi", env, 150, 50, 10, sigma_est="ss", device=dev)), env, "cemppi")
+        return env, e
+
+    seeds = [11, 12, 13, 14, 15, 16]
+    conc, _ = run_trial_replicas(make, 6, 8, seeds=seeds)
+    seq, _ = run_trial_replicas(make, 6, 8, seeds=seeds, concurrency=1)
+    for a, b in zip(conc, seq):
+        assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["U"], b["U"]) and a["its"] == b["its"]
+        assert a["reward_sum"] == b["reward_sum"] and np.isfinite(a["reward_sum"])
+    assert len({tuple(r["state"]) for r in conc}) == len(seeds), "different seeds give different trials"
