@@ -45,6 +45,8 @@ const POLICY = Dict(MPOPIS.MPPI_Policy => 0, MPOPIS.GMPPI_Policy => 1, MPOPIS.IM
                     MPOPIS.CEMPPI_Policy => 3, MPOPIS.CMAMPPI_Policy => 4, MPOPIS.μAISMPPI_Policy => 5,
                     MPOPIS.μΣAISMPPI_Policy => 6, MPOPIS.PMCMPPI_Policy => 7)
 policy_code(pol) = POLICY[Base.typename(typeof(pol)).wrapper]
+# policies the engine does not implement (NESMPPI_Policy: unreachable from get_policy) keep the stock Julia path
+supported(pol) = haskey(POLICY, Base.typename(typeof(pol)).wrapper)
 
 function sigma_est_code(pol)
     pol isa MPOPIS.CEMPPI_Policy || return Int32(0)
@@ -55,7 +57,21 @@ function sigma_est_code(pol)
 end
 
 # ---- handles, one per policy object ------------------------------------------------------------------------
-const HANDLES = IdDict{Any,Ptr{Cvoid}}()
+# Weak keys: the table must not keep a policy alive (the reference examples build a new policy per trial), otherwise
+# the finalizer below never runs and device memory / streams / events leak. `close!(pol)` frees a handle eagerly.
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+end
+const HANDLES = WeakKeyDict{Any,Handle}()
+function destroy!(hd::Handle)
+    if hd.ptr != C_NULL
+        ccall((:mpopis_b200_destroy, LIB[]), Cint, (Ptr{Cvoid},), hd.ptr)
+        hd.ptr = C_NULL
+    end
+    nothing
+end
+"Release the engine handle of `pol` now (otherwise it is released when `pol` is garbage-collected)."
+close!(pol) = haskey(HANDLES, pol) ? (destroy!(HANDLES[pol]); delete!(HANDLES, pol); nothing) : nothing
 
 env_code(::CarRacingEnv) = (Int32(0), Int32(1))
 env_code(e::MultiCarRacingEnv) = (Int32(0), Int32(e.N))
@@ -70,7 +86,14 @@ function set_env!(h, e::CarRacingEnv)
         h, 1, p, e.dt, e.δt, t.x′, t.y′, t.lane_width′, length(t.x′)))
 end
 function set_env!(h, e::MultiCarRacingEnv)
-    p = reduce(vcat, car_params.(e.envs)); t = e.envs[1].track      # sub-envs share the track file (multi-car_racing.jl:37-45)
+    # Every sub-env owns a Track built from the same file and sample factor (multi-car_racing.jl:37-45), and the engine
+    # takes ONE track per handle. Refuse anything else rather than silently using car 1's centre line for all cars.
+    t = e.envs[1].track
+    for sub in e.envs[2:end]
+        (sub.track.x′ == t.x′ && sub.track.y′ == t.y′ && sub.track.lane_width′ == t.lane_width′) ||
+            error("MPOPISB200: MultiCarRacingEnv sub-envs with different tracks are not supported by the engine")
+    end
+    p = reduce(vcat, car_params.(e.envs))
     check(ccall((:mpopis_b200_set_car_env, LIB[]), Cint,
         (Ptr{Cvoid}, Int32, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
         h, e.N, p, e.dt, e.δt, t.x′, t.y′, t.lane_width′, length(t.x′)))
@@ -81,19 +104,34 @@ function set_env!(h, e::MountainCarEnv)
     check(ccall((:mpopis_b200_set_mountaincar_env, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h, p, q.max_steps))
 end
 
+# Sharded policies (BASELINE config 5: K = 2^20 over the 8 GPUs of a box): one Julia process per GPU, e.g. under
+# MPI.jl / Distributed, each with `MPOPISB200.shard!(rank, world, device, nccl_id)` BEFORE the first control step;
+# `nccl_id = comm_id()` on rank 0, broadcast by the host program. Every rank then calls pol(env) with the same state
+# and gets the same control (the engine all-gathers the costs and all-reduces the moments over NCCL).
+const SHARD = Ref{Any}(nothing)     # (rank, world, device, id::Vector{UInt8}) or nothing
+function comm_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:mpopis_b200_comm_id, LIB[]), Cint, (Ptr{UInt8},), id))
+    return id
+end
+shard!(rank::Integer, world::Integer, device::Integer, id::Vector{UInt8}) = (SHARD[] = (Int32(rank), Int32(world), Int32(device), id); nothing)
+
 function handle(pol::AbstractPathIntegralPolicy, env; device=0)
-    get!(HANDLES, pol) do
+    hd = get!(HANDLES, pol) do
         ecode, ncars = env_code(env)
+        rank, world = SHARD[] === nothing ? (Int32(0), Int32(1)) : (SHARD[][1], SHARD[][2])
+        device = SHARD[] === nothing ? device : SHARD[][3]
         P = pol.params
         cfg = Cfg(ABI_VERSION, policy_code(pol), ecode, ncars, P.num_samples, P.horizon,
                   hasproperty(pol, :opt_its) ? pol.opt_its : 1, P.λ, P.α,
                   hasproperty(pol, :λ_ais) ? pol.λ_ais : 20.0,
                   hasproperty(pol, :ce_elite_threshold) ? pol.ce_elite_threshold : 0.8,
-                  sigma_est_code(pol), 1, P.log ? 1 : 0, device, 0, 1,
+                  sigma_est_code(pol), 1, P.log ? 1 : 0, device, rank, world,
                   ecode == 2 ? Int32(P.as) : Int32(0), (Int32(0), Int32(0), Int32(0)))
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:mpopis_b200_create, LIB[]), Cint, (Ref{Cfg}, Ref{Ptr{Cvoid}}), cfg, out))
         h = out[]
+        SHARD[] === nothing || check(ccall((:mpopis_b200_comm_init, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h, SHARD[][4]))
         set_env!(h, env)
         Σ = Matrix{Float64}(pol.Σ)                   # as x as for :mppi, cs x cs otherwise; column-major as is
         check(ccall((:mpopis_b200_set_sigma, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h, Σ, size(Σ, 1)))
@@ -105,9 +143,11 @@ function handle(pol::AbstractPathIntegralPolicy, env; device=0)
         # Random.seed!(pol, s) seeds pol.rng (MPOPIS.jl:54); draw the engine's Philox key from that stream so
         # that `seed!(pol, seed + k)` keeps controlling reproducibility.
         check(ccall((:mpopis_b200_seed, LIB[]), Cint, (Ptr{Cvoid}, UInt64), h, rand(pol.rng, UInt64)))
-        finalizer(_ -> ccall((:mpopis_b200_destroy, LIB[]), Cint, (Ptr{Cvoid},), h), pol)
-        h
+        hd = Handle(h)
+        finalizer(destroy!, hd)       # runs when the table's weak key (the policy) is collected and the Handle dies
+        hd
     end
+    return hd.ptr
 end
 
 env_t(e) = Int64(hasproperty(e, :t) ? e.t : 0)
@@ -201,12 +241,17 @@ on the GPU, engine RNG). `depth = :simulate_model` overrides only `simulate_mode
 function enable!(; depth::Symbol=:functor)
     for Env in (CarRacingEnv, MultiCarRacingEnv, MountainCarEnv)
         if depth == :functor
-            @eval (pol::AbstractGMPPI_Policy)(env::$Env) = plan!(pol, env)
+            # unsupported policy types (e.g. NESMPPI_Policy) fall through to the stock method of the abstract env type
+            @eval (pol::AbstractGMPPI_Policy)(env::$Env) =
+                supported(pol) ? plan!(pol, env) : invoke(pol, Tuple{MPOPIS.AbstractEnv}, env)
             @eval (pol::MPPI_Policy)(env::$Env) = plan!(pol, env)
         elseif depth == :simulate_model
             @eval MPOPIS.simulate_model(pol::AbstractGMPPI_Policy, env::$Env, E::Matrix{Float64},
                                         Σ_inv::Matrix{Float64}, U_orig::Vector{Float64}) =
-                simulate_model_b200(pol, env, E, Σ_inv, U_orig)
+                supported(pol) ? simulate_model_b200(pol, env, E, Σ_inv, U_orig) :
+                invoke(MPOPIS.simulate_model,
+                       Tuple{AbstractGMPPI_Policy,MPOPIS.AbstractEnv,Matrix{Float64},Matrix{Float64},Vector{Float64}},
+                       pol, env, E, Σ_inv, U_orig)
         else
             error("depth must be :functor or :simulate_model")
         end

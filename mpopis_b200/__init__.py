@@ -3,14 +3,13 @@ sisl/MPOPIS. The product is the C-ABI shared library `libmpopis_b200.so` (includ
 hand-written CUDA kernels under csrc/); this package is the Python mirror of the reference's host
 side — the same constructors, symbols and entry points a Julia user of MPOPIS.jl knows:
 
-    from mpopis_b200 import simulate_car_racing, CEMPPI_Policy, CarRacingEnv
+    from mpopis_b200 import CEMPPI_Policy, CarRacingEnv, get_policy, run_trial_replicas
 
 There is no CPU path: constructing/calling a policy without the built library and a B200 raises.
 """
 from ._abi import ABI_VERSION
 from .envs import (CarRacingEnv, CarRacingEnvParams, ExternalEnv, MountainCarEnv, MountainCarEnvParams, MultiCarRacingEnv,
                    calculate_β, exceed_β, reward, state, within_track)
-from .examples import quantile_ci, simulate_car_racing, simulate_mountaincar
 from .policies import (CEMPPI_Policy, CMAMPPI_Policy, GMPPI_Policy, IMPPI_Policy, MPPI_Policy, PMCMPPI_Policy,
                        action_space_size, block_diagm, cma_constants, get_policy, seed_b, μAISMPPI_Policy,
                        μΣAISMPPI_Policy)
@@ -22,5 +21,5 @@ __all__ = [
     "μAISMPPI_Policy", "μΣAISMPPI_Policy", "PMCMPPI_Policy", "Track", "CarRacingEnv", "CarRacingEnvParams",
     "MultiCarRacingEnv", "ExternalEnv", "MountainCarEnv", "MountainCarEnvParams", "within_track", "calculate_β", "exceed_β",
     "block_diagm", "action_space_size", "reward", "state", "get_policy", "seed_b", "cma_constants",
-    "simulate_car_racing", "simulate_mountaincar", "quantile_ci", "run_trial_replicas",
+    "run_trial_replicas",
 ]

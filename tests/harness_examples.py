@@ -1,5 +1,8 @@
-"""Entry points — mirror of src/examples/car_example.jl (EXC), mountaincar_example.jl (EXM) and
-example_utils.jl (EXU): `simulate_car_racing`, `simulate_mountaincar`, `quantile_ci`.
+"""TEST HARNESS (not product): the reference's own callers of the hot path, restated so that the policy API can be
+driven end to end without Julia — src/examples/car_example.jl (EXC), mountaincar_example.jl (EXM) and example_utils.jl
+(EXU): `simulate_car_racing`, `simulate_mountaincar`, `quantile_ci`. In a deployment these stay the reference's Julia
+functions, unchanged ("kept verbatim as the caller"); the product's own addition on this side of the path
+is `mpopis_b200.trials.run_trial_replicas` (many trials as concurrent device-resident replicas).
 
 Same keyword arguments, defaults, console tables and bookkeeping as the reference; `pol(env)`,
 `env(act)` and `reward(env)` run on the GPU. Plotting / GIF output (Plots.jl) is out of scope
@@ -16,8 +19,8 @@ from statistics import NormalDist
 
 import numpy as np
 
-from .envs import CarRacingEnv, MountainCarEnv, MultiCarRacingEnv, calculate_β, exceed_β, reward, within_track
-from .policies import block_diagm, get_policy
+from mpopis_b200.envs import CarRacingEnv, MountainCarEnv, MultiCarRacingEnv, calculate_β, exceed_β, reward, within_track
+from mpopis_b200.policies import block_diagm, get_policy
 
 
 def quantile_ci(x, p=0.05, q=0.5):

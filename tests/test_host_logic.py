@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 from conftest import make_env
 
+import harness_examples as H
 import mpopis_b200 as M
 from mpopis_b200 import policies as P
 from mpopis_b200.envs import CarRacingEnvParams
@@ -114,15 +115,15 @@ def test_simulate_mountaincar_with_oracle_backend(orc):
     _DeviceEnvMixin._backend = orc.bound()
     try:
         buf = io.StringIO()
-        res = M.simulate_mountaincar(num_trials=2, num_steps=60, policy_type="mppi", num_samples=20, horizon=15, λ=0.1,
+        res = H.simulate_mountaincar(num_trials=2, num_steps=60, policy_type="mppi", num_samples=20, horizon=15, λ=0.1,
                                      seed=11, x0=-0.5, out=buf, backend=orc.bound())
         txt = buf.getvalue()
         assert "MountainCar" in txt and "Trials AVE" in txt and "Trial    1" in txt
         assert np.all(res["trials"]["steps"] >= 1) and np.all(np.isfinite(res["trials"]["rews"]))
-        res2 = M.simulate_mountaincar(num_trials=2, num_steps=60, policy_type="mppi", num_samples=20, horizon=15, λ=0.1,
+        res2 = H.simulate_mountaincar(num_trials=2, num_steps=60, policy_type="mppi", num_samples=20, horizon=15, λ=0.1,
                                       seed=11, x0=-0.5, out=io.StringIO(), backend=orc.bound())
         assert np.array_equal(res["trials"]["rews"], res2["trials"]["rews"])  # same seed -> same run
-        res3 = M.simulate_mountaincar(num_trials=1, num_steps=200, policy_type="cemppi", seed=3, x0=-0.5,
+        res3 = H.simulate_mountaincar(num_trials=1, num_steps=200, policy_type="cemppi", seed=3, x0=-0.5,
                                       out=io.StringIO(), backend=orc.bound())
         assert res3["trials"]["rews"][0] > 50000  # the default CE-MPPI controller reaches the goal
     finally:
@@ -134,11 +135,11 @@ def test_simulate_car_racing_with_oracle_backend(orc):
     _DeviceEnvMixin._backend = orc.bound()
     try:
         buf = io.StringIO()
-        res = M.simulate_car_racing(num_trials=1, num_steps=12, num_samples=64, horizon=20, ais_its=3, seed=5, out=buf,
+        res = H.simulate_car_racing(num_trials=1, num_steps=12, num_samples=64, horizon=20, ais_its=3, seed=5, out=buf,
                                     backend=orc.bound())
         assert res["trials"]["steps"][0] == 12 and res["trials"]["T_viols"][0] == 0
         assert res["trials"]["mean_vs"][0] > 9.0 and "CE Σ Est Method:" in buf.getvalue()
-        res = M.simulate_car_racing(num_trials=1, num_steps=5, num_cars=2, policy_type="μaismppi", num_samples=32, horizon=10,
+        res = H.simulate_car_racing(num_trials=1, num_steps=5, num_cars=2, policy_type="μaismppi", num_samples=32, horizon=10,
                                     ais_its=2, seed=5, out=io.StringIO(), backend=orc.bound())
         assert res["trials"]["steps"][0] == 5
     finally:

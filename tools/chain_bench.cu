@@ -25,14 +25,15 @@ struct Consts {
 
 // VAR: 0 full; 1 no validity/integer bookkeeping; 2 selects replaced by the cubic; 3 reciprocal seeds replaced by a
 // (numerically wrong, latency-free) linear guess; 4 = 2 + 3; 5 = level-ordered source exactly as rollout_split.cu
-template <int VAR>
+// UNROLL: how many copies of the sub-step the loop body holds (code size ≈ UNROLL x 1.4 KB): the instruction-cache probe
+template <int VAR, int UNROLL = 5>
 __global__ void substep_kernel(const Consts c, int iters, double *out, long long *cycles) {
   double Vx = 10.0 + 0.01 * threadIdx.x, Vy = 0.1, psid = 0.05, sd = 0.02, cd = 0.9998;
   const double cI1fxf = c.cI1 * c.fxf, cmfxf = c.cm * c.fxf, cmfxr = c.cm * c.fxr, nddt = -c.ddt;
   int bad = 0;
   const int hvx0 = hi32(Vx), brake_mask = 0;
   const long long t0 = clock64();
-#pragma unroll 5
+#pragma unroll UNROLL
   for (int i = 0; i < iters; ++i) {
     const double ns = fma(sd, c.cdl, cd * c.sdl);
     const double nc = fma(cd, c.cdl, -(sd * c.sdl));
@@ -122,6 +123,17 @@ int main() {
   RUN_SUB(2, "tyre-force selects replaced by the cubic")
   RUN_SUB(3, "reciprocal seeds (MUFU.RCP64H) replaced by a linear guess")
   RUN_SUB(4, "no selects and no MUFU")
+#define RUN_UNR(U, name)                                                                   \
+  substep_kernel<0, U><<<1, 32>>>(c, iters, out, cyc);                                     \
+  substep_kernel<0, U><<<1, 32>>>(c, iters, out, cyc);                                     \
+  cudaMemcpy(&h, cyc, sizeof h, cudaMemcpyDeviceToHost);                                   \
+  printf("sub-step %-58s %8.1f cycles per sub-step (one warp alone)\n", name, (double)h / iters);
+  RUN_UNR(1, "full, loop body = 1 sub-step  (~1.4 KB of code)")
+  RUN_UNR(2, "full, loop body = 2 sub-steps")
+  RUN_UNR(10, "full, loop body = 10 sub-steps (~14 KB)")
+  RUN_UNR(20, "full, loop body = 20 sub-steps (~28 KB)")
+  RUN_UNR(40, "full, loop body = 40 sub-steps (~56 KB)")
+  RUN_UNR(100, "full, loop body = 100 sub-steps (~140 KB)")
 #define RUN_LAT(O, name)                                                                   \
   latency_kernel<O><<<1, 32>>>(iters, 1.25, out, cyc);                                     \
   latency_kernel<O><<<1, 32>>>(iters, 1.25, out, cyc);                                     \
