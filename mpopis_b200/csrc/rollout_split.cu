@@ -44,12 +44,14 @@ namespace ptx = cuda::ptx;
 constexpr int GROUP = 5, NGROUP = 3, RING = GROUP * NGROUP;  // sub-step slots per velocity warp, handed over in groups
 constexpr int GPS = 2;                                        // groups per control step: the kernel requires nsub == 10
 constexpr int VW = 2;                                         // velocity warps per CTA
+constexpr int NSTAGE = 4;                                     // control steps of noise in flight per velocity warp
 
 template <int NCARS>
 struct SplitSmem {
   double ring[VW][RING][NCARS][3][32];  // (Vx, Vy, Ψ̇δt) after each sub-step
   double ext[VW][2][NCARS][3][32];      // per control step (parity-buffered): Ψ̇, δ, pedal at its end (trajectory log)
   double fin[VW][32];                   // control cost (POL:272) of the finished rollout
+  double noise[VW][NSTAGE][2 * NCARS][32];  // E[:, k] of the next control steps, brought in by cp.async (no register staging)
   uint64_t full[VW][NGROUP], empty[VW][NGROUP];
   unsigned nfull[VW][NGROUP], nempty[VW][NGROUP];  // SPIN hand-over: completed fills / drains of each group
 };
@@ -76,6 +78,21 @@ __device__ __forceinline__ void spin_post(unsigned *cnt, unsigned value, int lan
   __threadfence_block();  // release: this lane's ring stores before the counter
   __syncwarp();
   if (lane == 0) *reinterpret_cast<volatile unsigned *>(cnt) = value;
+}
+
+// The noise of a rollout — AS doubles per control step, coalesced 256-byte rows across the warp — is copied global ->
+// shared memory asynchronously (cp.async, 8 bytes per lane and row, three control steps ahead). A register prefetch
+// does not survive here: under register pressure ptxas spills the loaded value right behind the load, and on an in-order
+// warp that store waits for the whole global-memory latency (ncu, K = 4096: 10 % of all stall samples sat on that one
+// STL pair). cp.async involves no register, so nothing waits until the values are read two steps later.
+__device__ __forceinline__ void noise_issue(double *dst_smem, const double *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void noise_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void noise_wait() {  // all but the N most recent groups of this thread have landed
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // GROUP Euler sub-steps of the velocity recurrence on the general path (car_step_fast's loop body, CAR:301-328, without
@@ -185,28 +202,27 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
     car[c].sd = 0.0, car[c].cd = 1.0, car[c].trig_valid = false;
   }
   const double *Ek = a.E + k;
-  double cc = 0.0, e1[AS], e2[AS];  // noise of the next step (its constants are built one step ahead) and the one after
+  double cc = 0.0;
+  auto fetch = [&](int t) {  // start the copy of control step t's noise (an empty group past the horizon keeps the count)
+    if (t < T) {
 #pragma unroll
-  for (int r = 0; r < AS; ++r) {
-    e1[r] = Ek[(size_t)r * a.ldk];
-    e2[r] = T > 1 ? Ek[(size_t)(AS + r) * a.ldk] : 0.0;
-  }
+      for (int r = 0; r < AS; ++r) noise_issue(&sm.noise[vw][t % NSTAGE][r][lane], Ek + (size_t)(t * AS + r) * a.ldk);
+    }
+    noise_commit();
+  };
+  fetch(0), fetch(1), fetch(2);
+  noise_wait<2>();  // step 0 has landed
   StepK cur[NCARS], nxt[NCARS];
 #pragma unroll
   for (int c = 0; c < NCARS; ++c) {
-    const double v0 = Uc[2 * c] + e1[2 * c], v1 = Uc[2 * c + 1] + e1[2 * c + 1];  // Vₖ = pol.U + E[:,k], POL:271
+    const double v0 = Uc[2 * c] + sm.noise[vw][0][2 * c][lane], v1 = Uc[2 * c + 1] + sm.noise[vw][0][2 * c + 1][lane];  // Vₖ = pol.U + E[:,k], POL:271
     if (a.bvec) cc += Bv[2 * c] * (v0 - Uo[2 * c]) + Bv[2 * c + 1] * (v1 - Uo[2 * c + 1]);  // POL:272
     cur[c] = make_step(env.car[c], env.der[c], env.dt, ddt, v0, v1, car[c].delta, jl_sign(car[c].Vx));
     nxt[c] = cur[c];
   }
   int gi = 0;  // global group counter of this rollout
   for (int t = 0; t < T; ++t) {
-#pragma unroll
-    for (int r = 0; r < AS; ++r) e1[r] = e2[r];  // E(t+1)
-    if (t + 2 < T) {
-#pragma unroll
-      for (int r = 0; r < AS; ++r) e2[r] = Ek[(size_t)((t + 2) * AS + r) * a.ldk];
-    }
+    fetch(t + 3);  // its slot held step t − 1, consumed during step t − 2
     // ---- what DOES depend on the velocities at the step's start ----
     double dpsi[NCARS], sg[NCARS];
     int hvx0[NCARS], brake_mask[NCARS];
@@ -229,10 +245,12 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
         else bar_wait(&sm.empty[vw][grp], (unsigned)((gi / NGROUP - 1) & 1), waited);
       }
       if (q == 0 && t + 1 < T) {  // constants of step t + 1, overlapped with this group's recurrence
+        noise_wait<2>();            // steps t + 2 and t + 3 may still be in flight, step t + 1 has landed
 #pragma unroll
         for (int c = 0; c < NCARS; ++c) {
           const int row = (t + 1) * AS + 2 * c;
-          const double v0 = Uc[row] + e1[2 * c], v1 = Uc[row + 1] + e1[2 * c + 1];
+          const double *en = &sm.noise[vw][(t + 1) % NSTAGE][2 * c][lane];
+          const double v0 = Uc[row] + en[0], v1 = Uc[row + 1] + en[32];
           if (a.bvec) cc += Bv[row] * (v0 - Uo[row]) + Bv[row + 1] * (v1 - Uo[row + 1]);
           nxt[c] = make_step(env.car[c], env.der[c], env.dt, ddt, v0, v1, fma((double)env.nsub, cur[c].dlt, car[c].delta),
                              sg[c]);

@@ -690,9 +690,10 @@ void launch_select_init(void *ws, unsigned long long *bmin, unsigned long long *
 
 int launch_ce_select(const double *costs, int Ktot, int m, long long k0, int Kloc, int early_stop, void *ws,
                      unsigned long long *bmin, unsigned long long *bmax, long long nb_cap, int *eidx, int *m_loc,
-                     double *tau_out, int *stop_flag, const int *stop, int max_ctas, cudaStream_t s) {
-  static const bool no_cluster = getenv("MPOPIS_SELECT_CLUSTER") && atoi(getenv("MPOPIS_SELECT_CLUSTER")) == 0;
-  if (Ktot <= (1 << 21) && !no_cluster) {  // one cluster of 8 CTAs: barriers in hardware, histograms in distributed shared memory
+                     double *tau_out, int *stop_flag, const int *stop, int max_ctas, int use_cluster, cudaStream_t s) {
+  // Opt-in ("select_cluster" option): measured SLOWER than the cooperative kernel at K = 65 536 (ncu: 60 vs 36 µs —
+  // 8 SMs pull the keys and walk the buckets where 64 do; the barriers were never the cost), kept as a tested variant.
+  if (Ktot <= (1 << 21) && use_cluster) {  // one cluster of 8 CTAs: barriers in hardware, histograms in distributed shared memory
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL), cfg.blockDim = dim3(CT), cfg.dynamicSmemBytes = 0, cfg.stream = s;
     cudaLaunchAttribute attr[1];
