@@ -162,30 +162,31 @@ struct PoseCar {  // pose-side state of one car
 // the straight-line block of its first sub-step group, where ptxas interleaves them with the recurrence) instead of
 // in front of it — ≈ 850 of ≈ 3100 cycles per control step of a lone velocity warp were this prologue (ablations:
 // tools/ablate.py, profiles/r2_split_ablation.txt).
-struct StepK {
+struct StepK {  // kept small: two of these (this step's and the next one's) are live in registers at once
   TireConsts tc;
-  double dlt, sdl, cdl, accel, bk, split, sgp, sd0, cd0, pedal, delta0;
+  double dlt, sdl, cdl, pedal;
+  int sgp;  // sign(Vx) the tyre constants were built for: -1, 0, 1
   bool pre_ok;
 };
 
 __device__ __forceinline__ StepK make_step(const CarParams &P, const CarDerived &D, double dt, double ddt, double v0,
-                                           double v1, double delta0, double sg_guess) {
+                                           double v1, double delta0, int sg_guess) {
   StepK k;
   const double a0 = clamp1(v0), a1 = clamp1(v1);                                  // UTL:55-67
   const double tgt = a0 * P.d_max - delta0;
   const double rate = fmin(fast_div(fabs(tgt), dt), P.dd_max) * jl_sign(tgt);     // CAR:295-296
-  k.accel = P.Fx_max * fmax(a1, 0.0);                                             // CAR:310
-  k.bk = P.Fx_min * fmin(a1, 0.0);                                                // CAR:311 without sign(Vx)
-  k.split = a1 <= 0.0 ? P.l_brake : P.l_drive;
+  const double accel = P.Fx_max * fmax(a1, 0.0);                                  // CAR:310
+  const double bk = P.Fx_min * fmin(a1, 0.0);                                     // CAR:311 without sign(Vx)
+  const double split = a1 <= 0.0 ? P.l_brake : P.l_drive;
   k.sgp = sg_guess;
-  k.tc = tire_consts_der(P, D, k.accel, k.bk, k.split, sg_guess);
+  k.tc = tire_consts_der(P, D, accel, bk, split, (double)sg_guess);
   k.dlt = rate * ddt;
   k.pre_ok = (fmax(fabs(delta0), fabs(a0 * P.d_max)) <= 0.78) & (fabs(k.dlt) <= 0.03);
   sincos_tiny(k.dlt, &k.sdl, &k.cdl);       // |rate·δt| <= δ̇_max·δt = 0.0157 for the default car
-  sincos_kernel(delta0, &k.sd0, &k.cd0);    // used when the δ recurrence is re-synchronised (every 5th step / after a repair)
-  k.pedal = a1, k.delta0 = delta0;
+  k.pedal = a1;
   return k;
 }
+__device__ __forceinline__ int sign_int(double x) { return x > 0.0 ? 1 : (x < 0.0 ? -1 : 0); }
 
 template <int NCARS, bool SPIN>
 __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const RolloutArgs &a, SplitSmem<NCARS> &sm,
@@ -217,7 +218,7 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
   for (int c = 0; c < NCARS; ++c) {
     const double v0 = Uc[2 * c] + sm.noise[vw][0][2 * c][lane], v1 = Uc[2 * c + 1] + sm.noise[vw][0][2 * c + 1][lane];  // Vₖ = pol.U + E[:,k], POL:271
     if (a.bvec) cc += Bv[2 * c] * (v0 - Uo[2 * c]) + Bv[2 * c + 1] * (v1 - Uo[2 * c + 1]);  // POL:272
-    cur[c] = make_step(env.car[c], env.der[c], env.dt, ddt, v0, v1, car[c].delta, jl_sign(car[c].Vx));
+    cur[c] = make_step(env.car[c], env.der[c], env.dt, ddt, v0, v1, car[c].delta, sign_int(car[c].Vx));
     nxt[c] = cur[c];
   }
   int gi = 0;  // global group counter of this rollout
@@ -229,12 +230,14 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
     bool gen[NCARS];  // this lane integrates the rest of the control step on the general path
 #pragma unroll
     for (int c = 0; c < NCARS; ++c) {
+      const CarParams &P = env.car[c];
+      const double a1 = cur[c].pedal, bk = P.Fx_min * fmin(a1, 0.0);
       sg[c] = jl_sign(car[c].Vx);
-      if (cur[c].bk != 0.0 && sg[c] != cur[c].sgp)  // rare: the car changed direction while the constants were in flight
-        cur[c].tc = tire_consts_der(env.car[c], env.der[c], cur[c].accel, cur[c].bk, cur[c].split, sg[c]);
-      hvx0[c] = hi32(car[c].Vx), brake_mask[c] = cur[c].bk != 0.0 ? (int)0x80000000 : 0;
+      if (bk != 0.0 && sign_int(car[c].Vx) != cur[c].sgp)  // rare: the car changed direction while the constants were in flight
+        cur[c].tc = tire_consts_der(P, env.der[c], P.Fx_max * fmax(a1, 0.0), bk, a1 <= 0.0 ? P.l_brake : P.l_drive, sg[c]);
+      hvx0[c] = hi32(car[c].Vx), brake_mask[c] = bk != 0.0 ? (int)0x80000000 : 0;
       gen[c] = !(cur[c].pre_ok & (car[c].Vx != 0.0));
-      if (!car[c].trig_valid || (t % 5) == 0) car[c].sd = cur[c].sd0, car[c].cd = cur[c].cd0;
+      if (!car[c].trig_valid || (t % 5) == 0) sincos_kernel(car[c].delta, &car[c].sd, &car[c].cd);  // re-synchronise the δ recurrence
       dpsi[c] = car[c].psid * ddt;
     }
 #pragma unroll
@@ -253,7 +256,7 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
           const double v0 = Uc[row] + en[0], v1 = Uc[row + 1] + en[32];
           if (a.bvec) cc += Bv[row] * (v0 - Uo[row]) + Bv[row + 1] * (v1 - Uo[row + 1]);
           nxt[c] = make_step(env.car[c], env.der[c], env.dt, ddt, v0, v1, fma((double)env.nsub, cur[c].dlt, car[c].delta),
-                             sg[c]);
+                             sign_int(car[c].Vx));
         }
       }
 #pragma unroll
@@ -338,7 +341,9 @@ __device__ __forceinline__ void velocity_warp(const CarEnvArgs &env, const Rollo
         }
         gen[c] = gen[c] | (bad < 0);
         if (gen[c]) {  // rare: redo THIS group on the general path from its un-advanced state, stay there for the step
-          const VelState o = vel_group_general(P, ddt, cur[c].accel, cur[c].bk, cur[c].split, car[c].delta, cur[c].dlt,
+          const double a1 = cur[c].pedal;
+          const VelState o = vel_group_general(P, ddt, P.Fx_max * fmax(a1, 0.0), P.Fx_min * fmin(a1, 0.0),
+                                               a1 <= 0.0 ? P.l_brake : P.l_drive, car[c].delta, cur[c].dlt,
                                                q * GROUP, VelState{car[c].Vx, car[c].Vy, car[c].psid, sg[c]},
                                                &sm.ring[vw][grp * GROUP][c][0][lane], NCARS * 3 * 32);
           Vx = o.Vx, Vy = o.Vy, psid = o.psid, sg[c] = o.sg;
@@ -591,7 +596,8 @@ int launch_rollout_car_split(const CarEnvArgs &env, const RolloutArgs &a, int wi
   switch (env.n_cars) {
     case 1:
       if (!wide) return launch_split<1, 2, 96, false>(env, a, stop, st);
-      return spin ? launch_split<1, 1, 160, true>(env, a, stop, st) : launch_split<1, 1, 160, false>(env, a, stop, st);
+      // at most one CTA per SM (spin): the register file is not a constraint either — no spills at 255
+      return spin ? launch_split<1, 1, 255, true>(env, a, stop, st) : launch_split<1, 1, 160, false>(env, a, stop, st);
     case 2: return spin ? launch_split<2, 1, 255, true>(env, a, stop, st) : launch_split<2, 1, 255, false>(env, a, stop, st);
     case 3: return spin ? launch_split<3, 1, 255, true>(env, a, stop, st) : launch_split<3, 1, 255, false>(env, a, stop, st);
   }
