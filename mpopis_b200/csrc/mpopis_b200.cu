@@ -367,7 +367,8 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
       variant = (h->cfg.n_cars <= rollout_split_max_cars() && h->Kloc <= rollout_split_capacity(h->cfg.n_cars, h->num_sms) &&
                  !h->rollout_stage) ? 5 : 3;
     const int ctas = (h->Kloc + 63) / 64;
-    const int spin = h->rollout_spin < 0 ? ctas <= h->num_sms : h->rollout_spin;  // default: only at <= 1 CTA per SM
+    // default: the lone-CTA flavour (255 registers, spin hand-over) while at most two CTAs share an SM
+    const int spin = h->rollout_spin < 0 ? ctas <= 2 * h->num_sms : h->rollout_spin;
     if (!(variant >= 4 && launch_rollout_car_split(h->car, a, variant == 5, spin, h->stop(), h->st)))
       launch_rollout_car(h->car, a, variant >= 4 ? 3 : variant, h->rollout_block,
                          h->rollout_stage, h->stop(), h->st);

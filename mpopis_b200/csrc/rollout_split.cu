@@ -585,7 +585,7 @@ static int launch_split(const CarEnvArgs &env, const RolloutArgs &a, const int *
 // — the latency regime, where a launch lasts as long as one rollout's chain. Measured cross-over against the
 // thread-per-rollout kernel (MODE 3: every rollout of K = 65 536 resident at 128 registers) between K = 8 192 and 16 384
 // (profiles/r2_ab_variants.txt).
-int rollout_split_capacity(int n_cars, int num_sms) { return n_cars == 1 ? num_sms * 80 : num_sms * 64; }
+int rollout_split_capacity(int n_cars, int num_sms) { return n_cars == 1 ? num_sms * 128 : num_sms * 64; }
 
 // wide: 0 = 2 velocity + 1 pose warp, 96 registers (7 CTAs per SM); 1 = 2 + 2 warps, 160 registers (3 CTAs per SM)
 // spin: poll shared-memory counters instead of parking on mbarriers (only sensible while a polling warp shares its
