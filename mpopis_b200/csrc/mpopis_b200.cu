@@ -65,7 +65,7 @@ struct mpopis_handle {
   long long k0 = 0, ldk = 0, ldm = 0;
   int dev = 0, world = 1, rank = 0;
   cudaStream_t st = nullptr, st2 = nullptr;  // main stream; side stream for the next iteration's normals
-  cudaEvent_t ev_z_free = nullptr, ev_z_ready = nullptr;
+  cudaEvent_t ev_z_free = nullptr, ev_z_ready = nullptr, ev_q_fork = nullptr, ev_q_join = nullptr;
   Comm comm{};
   bool env_set = false, cma_set = false;
   CarEnvArgs car{};
@@ -278,16 +278,20 @@ int ce_adapt(mpopis_t *h) {
     h->launches += 2;
   }
   mark(h, "mean");
+  double *qdst = h->d_Sraw + (size_t)cs * cs;  // travels with the scatter matrix
+  if (shrink) {  // the shrinkage statistic needs only X, μ and 1/σ: it runs beside the scatter matrix on the side stream
+    CU(cudaEventRecord(h->ev_q_fork, st));
+    CU(cudaStreamWaitEvent(h->st2, h->ev_q_fork, 0));
+    launch_shrink_q_partial(h->d_X, h->ldm, cs, mmax, nullptr, h->d_mu, h->d_Sraw, h->d_sums + cs, ss, h->d_qpart, stop,
+                            h->st2, h->d_mloc, h->d_bvec2);
+    launch_reduce_partials(h->d_qpart, shrink_q_nblocks(mmax), 1, qdst, stop, h->st2);
+    CU(cudaEventRecord(h->ev_q_join, h->st2));
+    h->launches += 2;
+  }
   launch_syrk_partial(h->d_X, h->ldm, cs, mmax, nullptr, h->d_mu, h->d_P, stop, st, h->d_mloc);
   launch_scatter_reduce(h->d_P, syrk_nchunks(mmax), cs, h->d_Sraw, stop, st);
   h->launches += 2;
-  double *qdst = h->d_Sraw + (size_t)cs * cs;  // travels with the scatter matrix
-  if (shrink) {
-    launch_shrink_q_partial(h->d_X, h->ldm, cs, mmax, nullptr, h->d_mu, h->d_Sraw, h->d_sums + cs, ss, h->d_qpart, stop,
-                            st, h->d_mloc, h->d_bvec2);
-    launch_reduce_partials(h->d_qpart, shrink_q_nblocks(mmax), 1, qdst, stop, st);
-    h->launches += 2;
-  }
+  if (shrink) CU(cudaStreamWaitEvent(st, h->ev_q_join, 0));
   mark(h, "scatter.local");
   if (int rc = allreduce_sum(h, h->d_Sraw, (size_t)cs * cs + (shrink ? 1 : 0))) return rc;
   mark(h, "scatter.coll");
@@ -807,7 +811,9 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
   if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_z_free, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_z_ready, cudaEventDisableTiming) != cudaSuccess)
+      cudaEventCreateWithFlags(&h->ev_z_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_q_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_q_join, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(MPOPIS_ERR_CUDA, "cudaStreamCreate failed"));
   const size_t cs = h->cs, K = h->K, Kloc = h->Kloc, ld = h->ldk;
   TRY(dalloc(&h->d_state, h->ss));
@@ -952,6 +958,8 @@ int mpopis_b200_destroy(mpopis_t *h) {
   for (auto &e : h->mark_pool) cudaEventDestroy(e);
   if (h->ev_z_free) cudaEventDestroy(h->ev_z_free);
   if (h->ev_z_ready) cudaEventDestroy(h->ev_z_ready);
+  if (h->ev_q_fork) cudaEventDestroy(h->ev_q_fork);
+  if (h->ev_q_join) cudaEventDestroy(h->ev_q_join);
   if (h->st2) cudaStreamSynchronize(h->st2), cudaStreamDestroy(h->st2);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;

@@ -645,30 +645,38 @@ __global__ void __launch_bounds__(256) elite_gather_sums_kernel(const double *__
   }
 }
 
-// sums = [Σx (cs) | n | Σx² (cs)] from the chunk partials in chunk order; with `finalize` (single GPU, or after the
-// all-reduce in the sharded case with nchunks = 0) also μ = Σx/n, pol.U += μ (POL:465) and 1/σ_i for the :ss
-// standardisation (σ_i² = Σx_i²/n − μ_i²: the elites' noise mean is a fraction of their spread, so the cancellation
-// costs a few ulps at most, and it only feeds the shrinkage intensity λ̂).
-__global__ void ce_sums_kernel(const double *__restrict__ partial, int nchunks, int cs, const int *m_loc,
-                               double *__restrict__ sums, int finalize, int standardise, double *__restrict__ mu,
-                               double *__restrict__ U, double *__restrict__ dinv, const int *stop) {
+// sums = [Σx (cs) | n | Σx² (cs)] from the chunk partials; with `finalize` (single GPU, or after the all-reduce in the
+// sharded case with nchunks = 0) also μ = Σx/n, pol.U += μ (POL:465) and 1/σ_i for the :ss standardisation
+// (σ_i² = Σx_i²/n − μ_i²: the elites' noise mean is a fraction of their spread, so the cancellation costs a few ulps at
+// most, and it only feeds the shrinkage intensity λ̂). One warp per row: the lanes fetch the chunk partials in parallel
+// (a per-thread loop over the chunks was a chain of dependent L2 round trips, 12 µs for 13 chunks) and combine them in
+// a fixed shuffle tree, so the sums are deterministic.
+__global__ void __launch_bounds__(256) ce_sums_kernel(const double *__restrict__ partial, int nchunks, int cs,
+                                                       const int *m_loc, double *__restrict__ sums, int finalize,
+                                                       int standardise, double *__restrict__ mu, double *__restrict__ U,
+                                                       double *__restrict__ dinv, const int *stop) {
   if (stop && *stop) return;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > cs) return;
+  const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r > cs) return;  // warp-uniform
+  double s1 = 0.0, s2 = 0.0;
+  if (nchunks > 0 && r < cs) {
+    for (int c = lane; c < nchunks; c += 32) s1 += partial[((size_t)c * 2) * cs + r], s2 += partial[((size_t)c * 2 + 1) * cs + r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane != 0) return;
   if (nchunks > 0) {
     if (r == cs) sums[cs] = (double)*m_loc;
-    else {
-      double a = 0.0, b2 = 0.0;
-      for (int c = 0; c < nchunks; ++c) a += partial[((size_t)c * 2) * cs + r], b2 += partial[((size_t)c * 2 + 1) * cs + r];
-      sums[r] = a, sums[cs + 1 + r] = b2;
-    }
+    else sums[r] = s1, sums[cs + 1 + r] = s2;
+  } else if (r < cs) {
+    s1 = sums[r], s2 = sums[cs + 1 + r];
   }
   if (!finalize || r == cs) return;
   const double n = nchunks > 0 ? (double)*m_loc : sums[cs];
-  const double m1 = sums[r] / n;
+  const double m1 = s1 / n;
   mu[r] = m1;
   U[r] = U[r] + m1;
-  dinv[r] = standardise ? 1.0 / sqrt(sums[cs + 1 + r] / n - m1 * m1) : 1.0;
+  dinv[r] = standardise ? 1.0 / sqrt(s2 / n - m1 * m1) : 1.0;
 }
 
 }  // namespace
@@ -723,8 +731,8 @@ void launch_elite_gather_sums(const double *E, long long ldk, int cs, const int 
 
 void launch_ce_sums(const double *partial, int nchunks, int cs, const int *m_loc, double *sums, int finalize,
                     int standardise, double *mu, double *U, double *dinv, const int *stop, cudaStream_t s) {
-  ce_sums_kernel<<<(cs + 1 + 127) / 128, 128, 0, s>>>(partial, nchunks, cs, m_loc, sums, finalize, standardise, mu, U,
-                                                     dinv, stop);
+  ce_sums_kernel<<<(cs + 1 + 7) / 8, 256, 0, s>>>(partial, nchunks, cs, m_loc, sums, finalize, standardise, mu, U, dinv,
+                                                 stop);
 }
 
 }  // namespace mpopis
