@@ -581,11 +581,12 @@ static int launch_split(const CarEnvArgs &env, const RolloutArgs &a, const int *
   return 1;
 }
 
-// Largest shard for which the split kernel is the default: about one CTA (64 rollouts, 4 warps x 160 registers) per SM
-// — the latency regime, where a launch lasts as long as one rollout's chain. Measured cross-over against the
-// thread-per-rollout kernel (MODE 3: every rollout of K = 65 536 resident at 128 registers) between K = 8 192 and 16 384
-// (profiles/r2_ab_variants.txt).
-int rollout_split_capacity(int n_cars, int num_sms) { return n_cars == 1 ? num_sms * 128 : num_sms * 64; }
+// Largest shard for which the split kernel is the default — the latency regime, where a launch lasts as long as one
+// rollout's chain: up to two CTAs (64 rollouts, 4 warps) per SM the 255-register / spin flavour, up to ≈ 2.6 per SM the
+// 160-register one. Measured against the thread-per-rollout kernel (MODE 3: every rollout of K = 65 536 resident at 128
+// registers), µs per launch: K = 150: 87 vs 150, 8 192: 95 vs 146, 18 944: 111 vs 146, 24 576: 147 vs 170; at K = 65 536
+// the split kernel needs several waves (372-495 vs 271) — profiles/r2_ab_variants.txt.
+int rollout_split_capacity(int n_cars, int num_sms) { return n_cars == 1 ? num_sms * 168 : num_sms * 64; }
 
 // wide: 0 = 2 velocity + 1 pose warp, 96 registers (7 CTAs per SM); 1 = 2 + 2 warps, 160 registers (3 CTAs per SM)
 // spin: poll shared-memory counters instead of parking on mbarriers (only sensible while a polling warp shares its
