@@ -51,6 +51,7 @@ struct Ws {  // device workspace; zero/clean between launches (the kernel restor
   unsigned long long part_first[MAXCTA];   // bucket scan partials: key of the first non-empty bucket's min
   unsigned long long part_last[MAXCTA];    //                      key of the last non-empty bucket's max
   int part_flags[MAXCTA];                  // bit 0: any non-empty bucket, bit 1: a gap >= 10e-3 seen
+  unsigned long long cta_min1[MAXCTA], cta_min2[MAXCTA];  // the two smallest keys of each CTA's slice (pass 0)
 };
 static_assert(sizeof(Ws) <= SELECT_WS_BYTES, "SELECT_WS_BYTES too small");
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(ST) ce_select_kernel(const double *__restrict_
   if (stop && *stop) return;  // grid-uniform: nobody writes the flag before the last grid barrier
   cg::grid_group grid = cg::this_grid();
   __shared__ unsigned sh[NBIN];
-  __shared__ unsigned long long s64[ST / 32 * 2 + 4];
+  __shared__ unsigned long long s64[ST / 32 * 2 + 4];  // per-warp pairs; [0] doubles as the τ hand-over
   __shared__ int s32[ST / 32 + 8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nc = gridDim.x, b = blockIdx.x;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(ST) ce_select_kernel(const double *__restrict_
   unsigned pi = 0, ti = 0;
   long long need = m - 1;
   int low = 96;  // bits >= low of the prefix are fixed
-  unsigned long long mn = KMAX;
+  unsigned long long mn = KMAX, mn2 = KMAX;  // the two smallest keys this thread has seen (mn <= mn2, duplicates kept)
   bool have_tau = false;
   for (int pass = 0; pass < 9; ++pass) {
     const int shift = pass < 8 ? 85 - 11 * pass : 0;
@@ -124,7 +125,10 @@ __global__ void __launch_bounds__(ST) ce_select_kernel(const double *__restrict_
     for (int i0 = ibeg; i0 < iend; i0 += ST) {
       const int i = i0 + tid;
       const unsigned long long k = i < iend ? cost_key(costs[i]) : KMAX;
-      if (pass == 0) mn = k < mn ? k : mn;
+      if (pass == 0) {
+        mn2 = k < mn ? mn : (k < mn2 ? k : mn2);
+        mn = k < mn ? k : mn;
+      }
       hist_add(sh, digit96(k, (unsigned)i, shift, mask), i < iend && match96(k, (unsigned)i, pk, pi, low));
     }
     __syncthreads();
@@ -135,13 +139,26 @@ __global__ void __launch_bounds__(ST) ce_select_kernel(const double *__restrict_
       unsigned *nh = ws->hist[(pass + 1) % 3];
       for (int e = tid; e < NBIN; e += ST) nh[e] = 0;
     }
-    if (pass == 0) {  // global minimum key (the smallest elite cost)
+    if (pass == 0) {  // the two smallest keys: the global minimum (smallest elite cost) and its successor
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long v = __shfl_xor_sync(0xffffffffu, mn, o);
-        mn = v < mn ? v : mn;
+        const unsigned long long a1 = __shfl_xor_sync(0xffffffffu, mn, o), a2 = __shfl_xor_sync(0xffffffffu, mn2, o);
+        const unsigned long long lo = a1 < mn ? a1 : mn, hi = a1 < mn ? mn : a1;  // merge the pairs (mn, mn2), (a1, a2)
+        const unsigned long long c2 = a2 < mn2 ? a2 : mn2;
+        mn = lo, mn2 = hi < c2 ? hi : c2;
       }
-      if (lane == 0 && mn != KMAX) atomicMin(&ws->min_key, mn);
+      if (lane == 0) s64[2 * wid] = mn, s64[2 * wid + 1] = mn2;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long m1 = KMAX, m2 = KMAX;
+        for (int w = 0; w < ST / 32; ++w) {
+          const unsigned long long a1 = s64[2 * w], a2 = s64[2 * w + 1];
+          const unsigned long long lo = a1 < m1 ? a1 : m1, hi = a1 < m1 ? m1 : a1, c2 = a2 < m2 ? a2 : m2;
+          m1 = lo, m2 = hi < c2 ? hi : c2;
+        }
+        ws->cta_min1[b] = m1, ws->cta_min2[b] = m2;
+        if (m1 != KMAX) atomicMin(&ws->min_key, m1);
+      }
     }
     grid.sync();
     // every CTA finds the bin of rank `need` in the global histogram (redundantly: no broadcast needed)
@@ -218,8 +235,32 @@ __global__ void __launch_bounds__(ST) ce_select_kernel(const double *__restrict_
   // ---- 2. mark: bucket min/max of all elites, count of the elites this shard owns ------------------------------
   const unsigned long long mnk = __ldcg(&ws->min_key);
   const double c1 = key_cost(mnk), cm = key_cost(tk);
+  // The two smallest costs are the first two elites (m >= 2). The best samples of a cost vector are sparse, so their gap
+  // alone usually exceeds 10e-3 and decides "no stop" — then no bucket is touched. Every CTA merges the per-CTA pairs.
+  unsigned long long g1 = KMAX, g2 = KMAX;
+  for (int q = tid; q < nc; q += ST) {
+    const unsigned long long a1 = __ldcg(&ws->cta_min1[q]), a2 = __ldcg(&ws->cta_min2[q]);
+    const unsigned long long lo = a1 < g1 ? a1 : g1, hi = a1 < g1 ? g1 : a1, c2 = a2 < g2 ? a2 : g2;
+    g1 = lo, g2 = hi < c2 ? hi : c2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long a1 = __shfl_xor_sync(0xffffffffu, g1, o), a2 = __shfl_xor_sync(0xffffffffu, g2, o);
+    const unsigned long long lo = a1 < g1 ? a1 : g1, hi = a1 < g1 ? g1 : a1, c2 = a2 < g2 ? a2 : g2;
+    g1 = lo, g2 = hi < c2 ? hi : c2;
+  }
+  __syncthreads();
+  if (lane == 0) s64[2 * wid] = g1, s64[2 * wid + 1] = g2;
+  __syncthreads();
+  g1 = KMAX, g2 = KMAX;
+  for (int w = 0; w < ST / 32; ++w) {
+    const unsigned long long a1 = s64[2 * w], a2 = s64[2 * w + 1];
+    const unsigned long long lo = a1 < g1 ? a1 : g1, hi = a1 < g1 ? g1 : a1, c2 = a2 < g2 ? a2 : g2;
+    g1 = lo, g2 = hi < c2 ? hi : c2;
+  }
+  const bool first_gap_decides = m > 1 && g2 != KMAX && !(fabs(key_cost(g2) - key_cost(g1)) < 10e-3);  // POL:459 on c₂ − c₁
   long long nb = 0;  // 0: the stop test is decided without buckets (no stop)
-  if (early_stop && m > 1 && tk < COST_KEY_NAN && isfinite(c1) && isfinite(cm)) {
+  if (early_stop && m > 1 && !first_gap_decides && tk < COST_KEY_NAN && isfinite(c1) && isfinite(cm)) {
     const double span = (cm - c1) * 200.0;
     if (span < (double)(2LL * m + 2) && span + 1.0 <= (double)nb_cap) nb = (long long)span + 1;
   }

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 from conftest import configure, engine_kwargs, julia_sortperm, make_env, synthetic_states
 
+from mpopis_b200 import _abi
 from oracle import np_mirror as npm
 
 
@@ -249,3 +250,36 @@ def test_shift_identity_and_its(orc):
         np.testing.assert_allclose(ctrl, np.clip(wc[:2], -1, 1), rtol=1e-10)
         np.testing.assert_allclose(U2[:-2], wc[2:], rtol=1e-10, atol=1e-14)
         assert abs(out["weights"].sum() - 1) < 1e-12
+
+
+def test_oas_and_rblw_against_their_defining_iterations(orc):
+    """Independent pin for two of the shrinkage estimators the reference takes from CovarianceEstimation.jl (POL:421-423):
+    Chen, Wiesel, Eldar & Hero (2010) DEFINE the OAS intensity as the limit of the iteration
+        ρ_{j+1} = [(1 − 2/p) tr(Σ_j S) + tr²(Σ_j)] / [(n + 1 − 2/p) tr(Σ_j S) + (1 − n/p) tr²(Σ_j)],  Σ_j = (1 − ρ_j) S + ρ_j F
+    (its closed form is what the oracle and the engine implement) and the RBLW intensity by their eq. (17). Running the
+    iteration here checks the closed form without sharing its code. sklearn's OAS is NOT usable as a cross-check: it
+    documents a deliberately different formula (0.3085 vs 0.3060 on this matrix). :lw / :ss (Ledoit–Wolf and
+    Schäfer–Strimmer towards diag(S)) have no independent implementation in this image and stay unpinned until
+    tests/golden/julia_v1.json exists (julia/make_fixtures.jl)."""
+    rng = np.random.default_rng(0)
+    for p, n in ((20, 60), (100, 30), (100, 819)):
+        A = rng.normal(size=(p, p))
+        X = A @ rng.normal(size=(p, n))
+        e = orc.engine(policy="cemppi", env=_abi.ENV_MOUNTAIN_CAR, num_samples=max(n, 2), horizon=p, opt_its=2, lam=1.0)
+        Xc = X - X.mean(axis=1, keepdims=True)
+        S = Xc @ Xc.T / n
+        F = np.trace(S) / p * np.eye(p)
+        Sig = S.copy()
+        for _ in range(500):
+            num = (1 - 2 / p) * np.trace(Sig @ S) + np.trace(Sig) ** 2
+            den = (n + 1 - 2 / p) * np.trace(Sig @ S) + (1 - n / p) * np.trace(Sig) ** 2
+            rho = min(num / den, 1.0)
+            Sig = (1 - rho) * S + rho * F
+        _, S_oas = e.cov_estimate(X, "oas")
+        assert abs(e.last_shrinkage() - rho) < 1e-10
+        np.testing.assert_allclose(S_oas, Sig, rtol=1e-9, atol=1e-12)
+        tr, tr2 = np.trace(S), np.sum(S * S)
+        rho_rblw = min(((n - 2) / n * tr2 + tr * tr) / ((n + 2) * (tr2 - tr * tr / p)), 1.0)  # eq. (17)
+        _, S_rblw = e.cov_estimate(X, "rblw")
+        assert abs(e.last_shrinkage() - rho_rblw) < 1e-12
+        np.testing.assert_allclose(S_rblw, (1 - rho_rblw) * S + rho_rblw * F, rtol=1e-10, atol=1e-13)
