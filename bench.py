@@ -233,17 +233,16 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mpopis_b200 import _lib
+    from mpopis_b200 import _lib, sharding
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     bound = _lib.product()  # raises if the CUDA library is missing: no fallback
+    transport = []  # of the per-iteration exchanges: "peer" (csrc/comm.cu kernels over NVLink) or "nccl"
     def sharded_engine(Kx, **extra):
         envx, engx = make_engine(bound, Kx, rank, world, local_rank, **extra)
         if world > 1:
-            ids = [_lib.comm_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            engx.comm_init(ids[0])
+            transport.append(sharding.connect(engx, dist, rank, world))
         if args.rollout_variant is not None:
             engx.set_option("rollout_variant", args.rollout_variant)
         return envx, engx
@@ -442,7 +441,7 @@ def main():
     line = dict(base, value=value, ms_per_step=dev_ms / args.steps,
                 config={"workload": workload, "l2": "flushed between steps (256 MiB memset outside the timed intervals)",
                         "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU",
-                        "rollout_variant": variant},
+                        "collectives": (transport[-1] if transport else "none"), "rollout_variant": variant},
                 e2e={"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "ms_per_step": e2e_s / args.steps * 1e3},
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_fp64=roofline_fp64,

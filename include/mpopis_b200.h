@@ -138,6 +138,17 @@ int mpopis_b200_loopback_create(int32_t world, void **group_out);
 int mpopis_b200_loopback_destroy(void *group);
 int mpopis_b200_comm_init_loopback(mpopis_t *h, void *group);
 
+/* Peer-memory collectives (one node, NVLink / NVSwitch): after comm_init, every rank exports 128 bytes (two CUDA IPC
+ * handles: its control region and its cost vector), the host all-gathers the blobs in rank order (any transport) and
+ * every rank attaches them. From then on the per-iteration exchanges (all-gather of 8 B x K_loc costs, all-reduce of
+ * the 2cs+1 / cs²+1 moment sums) are single kernels that store into the peers' memory and spin on arrival flags
+ * (csrc/comm.cu) instead of NCCL calls; NCCL keeps serving the oversize all-reduce of :cmamppi. The reference has no
+ * counterpart (its only parallel loop is Threads.@threads over the samples, POL:269). comm_peer_loopback does the
+ * same between the virtual ranks of a loop-back group (collective: call it from every rank's thread). */
+int mpopis_b200_comm_peer_export(mpopis_t *h, void *handle_out128);
+int mpopis_b200_comm_peer_attach(mpopis_t *h, const void *handles, int64_t n_bytes);
+int mpopis_b200_comm_peer_loopback(mpopis_t *h);
+
 /* env.params (CAR:2-21, 18 doubles per car in declaration order), env.dt, env.δt (CAR:33-34),
  * env.track.x′, y′, lane_width′ (TRK:6-8). n_cars > 1 is MultiCarRacingEnv (MCR:2-12). */
 int mpopis_b200_set_car_env(mpopis_t *h, int32_t n_cars, const double *params18_per_car, double dt,

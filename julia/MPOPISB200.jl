@@ -150,6 +150,17 @@ function handle(pol::AbstractPathIntegralPolicy, env; device=0)
     return hd.ptr
 end
 
+# Peer-memory collectives on one NVLink node (include/mpopis_b200.h, csrc/comm.cu): every rank exports 128 bytes, the
+# host program all-gathers them in rank order (e.g. MPI.Allgather) and every rank attaches the world x 128 bytes; the
+# per-iteration exchanges then run as single kernels over NVLink instead of NCCL calls.
+function peer_export(pol::AbstractPathIntegralPolicy, env)
+    blob = Vector{UInt8}(undef, 128)
+    check(ccall((:mpopis_b200_comm_peer_export, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}), handle(pol, env), blob))
+    return blob
+end
+peer_attach!(pol::AbstractPathIntegralPolicy, env, blobs::Vector{UInt8}) =
+    check(ccall((:mpopis_b200_comm_peer_attach, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), handle(pol, env), blobs, length(blobs)))
+
 env_t(e) = Int64(hasproperty(e, :t) ? e.t : 0)
 
 # ---- depth (iii): the whole functor, mppi_mpopi_policies.jl:121-146 and 221-238 ------------------------------

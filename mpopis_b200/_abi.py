@@ -88,6 +88,9 @@ PRODUCT_ONLY = {
     "loopback_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "loopback_destroy": (C.c_int, [C.c_void_p]),
     "comm_init_loopback": (C.c_int, [_H, C.c_void_p]),
+    "comm_peer_export": (C.c_int, [_H, C.c_void_p]),
+    "comm_peer_attach": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "comm_peer_loopback": (C.c_int, [_H]),
     "set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "get_option": (C.c_int, [_H, C.c_char_p, _D]),
     "resident_reset": (C.c_int, [_H, _D, C.c_int64, _D]),

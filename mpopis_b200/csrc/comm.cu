@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -89,6 +90,8 @@ struct LoopGroup {
   unsigned long long gen = 0;
   bool broken = false;
   const double *pub[COMM_MAX_WORLD] = {};
+  char *peer_region[COMM_MAX_WORLD] = {};
+  double *peer_gather[COMM_MAX_WORLD] = {};
   // generation barrier between the host threads of the virtual ranks; a rank that never arrives (it returned an
   // error before the collective) breaks the group instead of hanging the others forever
   int barrier() {
@@ -150,12 +153,196 @@ int comm_init_loopback(Comm &c, LoopGroup *g, int device, size_t max_doubles) {
 
 void comm_destroy(Comm &c) {
   if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
+  for (void *&p : c.peer_opened)
+    if (p) cudaIpcCloseMemHandle(p), p = nullptr;
+  if (c.peer_region) cudaFree(c.peer_region);
+  c.peer_region = nullptr, c.peer = false;
   if (c.loop_tmp) cudaFree(c.loop_tmp);
   c.nccl = nullptr, c.loop = nullptr, c.loop_tmp = nullptr;
 }
 
+// =====================================================================================================================
+// Peer-memory collectives: one kernel per exchange, stores into the peers' HBM over NVLink / NVSwitch
+// =====================================================================================================================
+// Every rank owns a `region` = PeerCtrl + 2 (parity) x world all-reduce slots, and its full-length cost vector; every
+// rank holds pointers to all of them (PeerTable). Per control step the engine runs ~3 tiny exchanges per AIS iteration
+// (8 B x K_loc costs, 2cs+1 and cs²+1 moment sums): their cost is latency, not bytes, and NCCL's launch + protocol
+// latency (≈35 µs each on 8 GPUs, profiles/r2_multi_gpu.md) was most of the weak-scaling loss. Here:
+//   all-reduce  push my vector into slot[parity][my rank] of EVERY rank -> fence -> release-store the epoch into every
+//               rank's flag[parity][my rank] -> acquire-spin on my own world flags -> sum the world slots in rank order
+//               (bit-identical on all ranks, no atomics on data) -> last CTA bumps the device-resident epoch.
+//               Two parities suffice: a rank can only reach epoch e+2 after it received everyone's e+1 contribution,
+//               which each rank sends only after it finished reading epoch e.
+//   all-gather  store my K_loc costs straight into segment [my rank] of every rank's cost vector, flag, wait. One
+//               buffer suffices because an all-reduce always separates two gathers (the step ends in one) and the
+//               consumers of the gathered costs are stream-ordered before this rank's contribution to it.
+// Epochs live in device memory and are advanced by the kernels, so a captured CUDA graph replays them unchanged.
+// A spin that sees no peer for ~10 s sets *peer_err (sticky, surfaces as MPOPIS_ERR_NCCL) instead of hanging the GPU.
+namespace {
+
+constexpr size_t PEER_CTRL_BYTES = 1024;
+struct PeerCtrl {
+  unsigned epoch_ar, epoch_ag, cnt_push, cnt_exit, pad[4];
+  unsigned flags_ar[2][COMM_PEER_MAX];
+  unsigned flags_ag[COMM_PEER_MAX];
+};
+static_assert(sizeof(PeerCtrl) <= PEER_CTRL_BYTES, "control block fits its reservation");
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double *peer_slot(char *region, int par, int world, int src, size_t slot_n) {
+  return (double *)(region + PEER_CTRL_BYTES) + ((size_t)par * world + src) * slot_n;
+}
+// spin until *flag reaches `want` (epochs only grow); false on timeout
+__device__ bool wait_flag(const unsigned *flag, unsigned want) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(flag) - want) < 0) {
+    __nanosleep(40);
+    if (clock64() - t0 > 20000000000LL) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(512) peer_allreduce_kernel(double *__restrict__ buf, int n, const PeerTable tab, int world,
+                                                              int rank, size_t slot_n, int *err) {
+  PeerCtrl *me = (PeerCtrl *)tab.region[rank];
+  __shared__ unsigned s_epoch;
+  if (threadIdx.x == 0) s_epoch = *(volatile unsigned *)&me->epoch_ar;
+  __syncthreads();
+  const unsigned e = s_epoch;
+  const int par = e & 1;
+  const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = i0; i < n; i += stride) {
+    const double v = buf[i];
+    for (int p = 0; p < world; ++p) peer_slot(tab.region[p], par, world, rank, slot_n)[i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&me->cnt_push, 1u) == gridDim.x - 1) {
+    __threadfence_system();  // the other CTAs' stores (fenced before their atomicAdd) precede the flags
+    for (int p = 0; p < world; ++p) st_release_sys(&((PeerCtrl *)tab.region[p])->flags_ar[par][rank], e + 1);
+  }
+  if (threadIdx.x < world && !wait_flag(&me->flags_ar[par][threadIdx.x], e + 1) && err) atomicCAS(err, 0, COMM_PEER_TIMEOUT);
+  __syncthreads();
+  for (int i = i0; i < n; i += stride) {
+    double s = __ldcg(peer_slot(tab.region[rank], par, world, 0, slot_n) + i);
+    for (int q = 1; q < world; ++q) s += __ldcg(peer_slot(tab.region[rank], par, world, q, slot_n) + i);
+    buf[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&me->cnt_exit, 1u) == gridDim.x - 1) {
+    me->cnt_push = 0, me->cnt_exit = 0;
+    __threadfence();
+    *(volatile unsigned *)&me->epoch_ar = e + 1;
+  }
+}
+
+__global__ void __launch_bounds__(512) peer_allgather_kernel(const double *__restrict__ base, size_t n_per, const PeerTable tab,
+                                                              int world, int rank, int *err) {
+  PeerCtrl *me = (PeerCtrl *)tab.region[rank];
+  __shared__ unsigned s_epoch;
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_epoch = *(volatile unsigned *)&me->epoch_ag;
+  __syncthreads();
+  const unsigned e = s_epoch;
+  const size_t off = (size_t)rank * n_per, n2 = n_per / 2;  // n_per is even (a multiple of 32): 16-byte stores
+  const double2 *src = (const double2 *)(base + off);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const double2 v = src[i];
+    for (int p = 0; p < world; ++p)
+      if (p != rank) ((double2 *)(tab.gather[p] + off))[i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&me->cnt_push, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  // the last CTA to finish its stores publishes the segment and waits for everyone else's
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < world; ++p) st_release_sys(&((PeerCtrl *)tab.region[p])->flags_ag[rank], e + 1);
+  }
+  if (threadIdx.x < world && threadIdx.x != rank && !wait_flag(&me->flags_ag[threadIdx.x], e + 1) && err)
+    atomicCAS(err, 0, COMM_PEER_TIMEOUT);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    me->cnt_push = 0;
+    __threadfence();
+    *(volatile unsigned *)&me->epoch_ag = e + 1;
+  }
+}
+
+}  // namespace
+
+int comm_peer_alloc(Comm &c, size_t slot_doubles) {
+  if (c.world == 1 || c.peer_region) return 0;
+  if (c.world > COMM_PEER_MAX) return cfail("peer-memory collectives support at most 16 ranks");
+  const size_t bytes = PEER_CTRL_BYTES + sizeof(double) * 2 * (size_t)c.world * slot_doubles;
+  CUC(cudaMalloc((void **)&c.peer_region, bytes));
+  CUC(cudaMemset(c.peer_region, 0, bytes));
+  CUC(cudaDeviceSynchronize());  // zeroed before any peer can learn the address
+  c.peer_slot_n = slot_doubles;
+  return 0;
+}
+
+int comm_peer_export(Comm &c, double *gather_base, void *out128) {
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) == COMM_PEER_HANDLE, "two IPC handles per rank");
+  if (!c.peer_region) return cfail("comm_peer_alloc first");
+  cudaIpcMemHandle_t hd[2];
+  CUC(cudaIpcGetMemHandle(&hd[0], c.peer_region));
+  CUC(cudaIpcGetMemHandle(&hd[1], gather_base));
+  memcpy(out128, hd, sizeof hd);
+  return 0;
+}
+
+int comm_peer_attach(Comm &c, double *gather_base, const void *all_handles) {
+  if (!c.peer_region) return cfail("comm_peer_alloc first");
+  if (c.peer) return cfail("peer-memory collectives already attached");
+  for (int r = 0; r < c.world; ++r) {
+    if (r == c.rank) {
+      c.peer_tab.region[r] = c.peer_region, c.peer_tab.gather[r] = gather_base;
+      continue;
+    }
+    cudaIpcMemHandle_t hd[2];
+    memcpy(hd, (const char *)all_handles + (size_t)r * COMM_PEER_HANDLE, sizeof hd);
+    void *a = nullptr, *b = nullptr;
+    CUC(cudaIpcOpenMemHandle(&a, hd[0], cudaIpcMemLazyEnablePeerAccess));
+    c.peer_opened[2 * r] = a;
+    CUC(cudaIpcOpenMemHandle(&b, hd[1], cudaIpcMemLazyEnablePeerAccess));
+    c.peer_opened[2 * r + 1] = b;
+    c.peer_tab.region[r] = (char *)a, c.peer_tab.gather[r] = (double *)b;
+  }
+  c.peer = true;
+  return 0;
+}
+
+int comm_peer_attach_loopback(Comm &c, double *gather_base) {
+  if (!c.loop) return cfail("not a loop-back communicator");
+  if (!c.peer_region) return cfail("comm_peer_alloc first");
+  LoopGroup *g = c.loop;
+  g->peer_region[c.rank] = c.peer_region, g->peer_gather[c.rank] = gather_base;
+  if (g->barrier()) return cfail("loop-back group broken (a virtual rank left the collective sequence)");
+  for (int r = 0; r < c.world; ++r) c.peer_tab.region[r] = g->peer_region[r], c.peer_tab.gather[r] = g->peer_gather[r];
+  if (g->barrier()) return cfail("loop-back group broken (a virtual rank left the collective sequence)");
+  c.peer = true;
+  return 0;
+}
+
 int comm_allreduce_sum(Comm &c, double *buf, size_t n, cudaStream_t st) {
   if (c.world == 1) return 0;
+  if (c.peer && n <= c.peer_slot_n) {
+    const unsigned grid = (unsigned)std::min<size_t>(8, (n + 1023) / 1024);
+    peer_allreduce_kernel<<<grid, 512, 0, st>>>(buf, (int)n, c.peer_tab, c.world, c.rank, c.peer_slot_n, c.peer_err);
+    CUC(cudaGetLastError());
+    return 0;
+  }
   if (c.nccl) {
     NC(g_nccl.AllReduce(buf, buf, n, ncclFloat64, ncclSum, (ncclComm_t)c.nccl, st));
     return 0;
@@ -177,6 +364,12 @@ int comm_allreduce_sum(Comm &c, double *buf, size_t n, cudaStream_t st) {
 
 int comm_allgather_f64(Comm &c, double *base, size_t n_per_rank, cudaStream_t st) {
   if (c.world == 1) return 0;
+  if (c.peer && base == c.peer_tab.gather[c.rank] && n_per_rank % 2 == 0) {
+    const unsigned grid = (unsigned)std::min<size_t>(32, (n_per_rank / 2 + 2047) / 2048);
+    peer_allgather_kernel<<<grid, 512, 0, st>>>(base, n_per_rank, c.peer_tab, c.world, c.rank, c.peer_err);
+    CUC(cudaGetLastError());
+    return 0;
+  }
   if (c.nccl) {
     NC(g_nccl.AllGather(base + (size_t)c.rank * n_per_rank, base, n_per_rank, ncclFloat64, (ncclComm_t)c.nccl, st));
     return 0;

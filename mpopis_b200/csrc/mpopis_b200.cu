@@ -579,7 +579,8 @@ void drop_graph(mpopis_t *h) {
 // Any capture/instantiate failure falls back to eager launches for the lifetime of the handle.
 int plan_step(mpopis_t *h) {
   factor_sigma0(h);
-  const bool can = h->graph_enabled && !h->trace && !h->comm.host_synchronous() && h->cfg.env != MPOPIS_ENV_EXTERNAL;
+  const bool can = h->graph_enabled && !h->trace && !h->comm.host_synchronous() &&
+                   !(h->comm.loop && h->cfg.policy == MPOPIS_POLICY_CMAMPPI) && h->cfg.env != MPOPIS_ENV_EXTERNAL;
   if (!can) return plan_core(h, nullptr, nullptr);
   if (!h->gexec) {
     const long long l0 = h->launches, step0 = h->step;
@@ -613,6 +614,9 @@ int plan_step(mpopis_t *h) {
 }
 
 int check_info(mpopis_t *h, int info) {
+  if (info == COMM_PEER_TIMEOUT)
+    return fail(MPOPIS_ERR_NCCL, "a peer-memory collective waited 10 s for a rank that never arrived (rank %d of %d)",
+                h->rank, h->world);
   if (info != 0)
     return fail(MPOPIS_ERR_NOT_PD, "PosDefException: matrix is not positive definite; Cholesky factorization failed (%s)",
                 info >= 1000 ? "initial Σ" : (std::string("AIS iteration ") + std::to_string(info)).c_str());
@@ -1001,6 +1005,40 @@ int mpopis_b200_comm_init_loopback(mpopis_t *h, void *group) {
   if (int rc = set_device(h)) return rc;
   const size_t cap = std::max((size_t)h->cs * h->cs + 64, (size_t)h->K) + 2 * (size_t)h->cs + 128;
   if (comm_init_loopback(h->comm, (LoopGroup *)group, h->dev, cap)) return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
+  return 0;
+}
+
+// Peer-memory collectives (comm.cu): export -> the host exchanges the 128-byte blobs of all ranks -> attach.
+int mpopis_b200_comm_peer_export(mpopis_t *h, void *out128) {
+  if (!h || !out128) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->world == 1) return fail(MPOPIS_ERR_BAD_ARG, "not a sharded handle");
+  if (int rc = set_device(h)) return rc;
+  if (comm_peer_alloc(h->comm, (size_t)h->cs * h->cs + 2 * (size_t)h->cs + 64) ||
+      comm_peer_export(h->comm, h->d_costs, out128))
+    return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
+  return 0;
+}
+
+int mpopis_b200_comm_peer_attach(mpopis_t *h, const void *handles, int64_t n_bytes) {
+  if (!h || !handles) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (n_bytes != (int64_t)h->world * COMM_PEER_HANDLE)
+    return fail(MPOPIS_ERR_BAD_ARG, "expected world_size x %d bytes of peer handles", COMM_PEER_HANDLE);
+  if (int rc = set_device(h)) return rc;
+  drop_graph(h);
+  h->comm.peer_err = h->info();
+  if (comm_peer_attach(h->comm, h->d_costs, handles)) return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
+  return 0;
+}
+
+int mpopis_b200_comm_peer_loopback(mpopis_t *h) {
+  if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
+  if (h->world == 1) return 0;
+  if (int rc = set_device(h)) return rc;
+  drop_graph(h);
+  h->comm.peer_err = h->info();
+  if (comm_peer_alloc(h->comm, (size_t)h->cs * h->cs + 2 * (size_t)h->cs + 64) ||
+      comm_peer_attach_loopback(h->comm, h->d_costs))
+    return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
   return 0;
 }
 

@@ -65,7 +65,7 @@ class Engine:
             self.as_ = 2 * n_cars if env == _abi.ENV_CAR_RACING else 1
             self.ss = 8 * n_cars if env == _abi.ENV_CAR_RACING else 2
         self.cs = self.as_ * horizon
-        self.world_size, self.rank = world_size, rank
+        self.world_size, self.rank, self.device = world_size, rank, device
         self.Kloc = num_samples // max(world_size, 1)
         self.h = C.c_void_p()
         self._chk(bound.create(C.byref(self.cfg), C.byref(self.h)))
@@ -322,6 +322,21 @@ class Engine:
     def comm_init_loopback(self, group):
         """Attach this handle (virtual rank) to a loop-back group (`_lib.LoopbackGroup`)."""
         self._chk(self.b.comm_init_loopback(self.h, group.ptr))
+
+    def comm_peer_export(self) -> bytes:
+        """128-byte blob (CUDA IPC handles of this rank's control region and cost vector) for comm_peer_attach."""
+        buf = C.create_string_buffer(128)
+        self._chk(self.b.comm_peer_export(self.h, buf))
+        return buf.raw
+
+    def comm_peer_attach(self, blobs):
+        """Switch the per-iteration exchanges to peer-memory kernels; `blobs`: every rank's export, in rank order."""
+        raw = b"".join(blobs)
+        self._chk(self.b.comm_peer_attach(self.h, C.create_string_buffer(raw, len(raw)), len(raw)))
+
+    def comm_peer_loopback(self):
+        """The same between the virtual ranks of a loop-back group (collective: every rank's thread calls it)."""
+        self._chk(self.b.comm_peer_loopback(self.h))
 
     def warp_cycles(self) -> np.ndarray:
         """Per-warp clock64() cycles of the most recent rollout launch (needs set_option("rollout_profile", 1))."""

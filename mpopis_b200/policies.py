@@ -178,6 +178,15 @@ class AbstractPathIntegralPolicy:
                 self._eng.seed(self._seed)
         return self._eng
 
+    def connect(self, dist) -> str:
+        """Join the shards of this policy (constructed with rank / world_size on every process) over an initialised
+        torch.distributed group: NCCL communicator plus, on one NVLink node, the peer-memory collectives
+        (sharding.connect). Returns the transport of the per-iteration exchanges: "peer" or "nccl"."""
+        from . import sharding
+        if self._nccl_id is not None:
+            raise ValueError("this policy was given an nccl_id: its communicator is already set up")
+        return sharding.connect(self.engine(), dist, self._engine_args["rank"], self._engine_args["world_size"])
+
     def seed(self, seed: int):
         """Random.seed!(pol, seed) (MPOPIS.jl:54) — keys the engine's Philox stream."""
         self._seed = int(seed)

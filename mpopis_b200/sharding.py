@@ -31,6 +31,34 @@ def broadcast_comm_id(dist, rank: int, src: int = 0) -> bytes:
     return box[0]
 
 
+def connect(engine, dist, rank: int, world: int, peer: bool | None = None) -> str:
+    """Join `engine` (created with rank / world_size) to its peers over an initialised torch.distributed group:
+    NCCL communicator first, then — when every rank sits on one node with peer access (an NVLink / NVSwitch box) —
+    the peer-memory collectives of csrc/comm.cu. `peer`: None = decide (MPOPIS_COMM_PEER=0 disables), True = require,
+    False = NCCL only. Returns "peer" or "nccl": the transport of the per-iteration exchanges."""
+    import os
+    import socket
+    if world == 1:
+        return "none"
+    engine.comm_init(broadcast_comm_id(dist, rank))
+    if peer is None:
+        peer = os.environ.get("MPOPIS_COMM_PEER", "1") != "0"
+    if not peer or world > 16:
+        return "nccl"
+    import torch
+    dev = engine.device
+    ok = all(d == dev or torch.cuda.can_device_access_peer(dev, d) for d in range(torch.cuda.device_count()))
+    info = [None] * world
+    dist.all_gather_object(info, (socket.gethostname(), bool(ok)))
+    if len({h for h, _ in info}) != 1 or not all(o for _, o in info):  # the same verdict on every rank
+        return "nccl"
+    blobs = [None] * world
+    dist.all_gather_object(blobs, engine.comm_peer_export())
+    engine.comm_peer_attach(blobs)
+    dist.barrier()  # nobody stores into a region before everyone has mapped it
+    return "peer"
+
+
 def run_virtual_ranks(fns):
     """Run one callable per virtual rank of a loop-back group, each on its own host thread (the collectives of a
     loop-back group block until every rank has entered them). Returns the results in rank order; the first

@@ -1,5 +1,10 @@
+import os
 import sys
 from pathlib import Path
+
+# loop-back groups run up to 8 virtual ranks x 2 streams on one device and their peer-memory collectives spin on
+# flags: with the default 8 hardware queues a spinning kernel could sit in front of the very kernel it waits for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 import pytest

@@ -14,13 +14,17 @@ pytestmark = pytest.mark.gpu
 CONTROL_RTOL = 1e-5
 
 
-def sharded_engines(gpu_bound, policy, env, K, T, N, G, **kw):
+def sharded_engines(gpu_bound, policy, env, K, T, N, G, peer=False, **kw):
+    """peer=False: host-barrier collectives (the reference transport of the loop-back group); peer=True: the
+    peer-memory kernels of csrc/comm.cu — the production single-node transport — between the virtual ranks."""
     grp = _lib.LoopbackGroup(G)
     engs = []
     for r in range(G):
         e = configure(Engine(gpu_bound, **engine_kwargs(policy, env, K, T, N, rank=r, world_size=G, **kw)), env, policy)
         e.comm_init_loopback(grp)
         engs.append(e)
+    if peer:
+        sharding.run_virtual_ranks([e.comm_peer_loopback for e in engs])
     return grp, engs
 
 
@@ -28,13 +32,14 @@ def plan_all(engs, state, step, U, Z=None, u=None):
     return sharding.run_virtual_ranks([(lambda e=e: e.plan(state, step, U, Z=Z, resample_u=u)) for e in engs])
 
 
+@pytest.mark.parametrize("peer", [False, True], ids=["hostbarrier", "peer"])
 @pytest.mark.parametrize("G", [2, 3, 8])
 @pytest.mark.parametrize("sigma_est", ["ss", "mle"])
-def test_sharded_cemppi_equals_unsharded_and_oracle(gpu_bound, orc, G, sigma_est):
+def test_sharded_cemppi_equals_unsharded_and_oracle(gpu_bound, orc, G, sigma_est, peer):
     env = make_env("car")
     K, T, N = 4104, 30, 6  # 4104 = 2^3 · 3^3 · 19: divisible by 2, 3 and 8; > 2048 so one GPU also takes select.cu
     kw = dict(sigma_est=sigma_est)
-    grp, engs = sharded_engines(gpu_bound, "cemppi", env, K, T, N, G, **kw)
+    grp, engs = sharded_engines(gpu_bound, "cemppi", env, K, T, N, G, peer=peer, **kw)
     one = configure(Engine(gpu_bound, **engine_kwargs("cemppi", env, K, T, N, **kw)), env, "cemppi")
     cpu = configure(orc.engine(nthreads=8, **engine_kwargs("cemppi", env, K, T, N, **kw)), env, "cemppi")
     rng = np.random.Generator(np.random.Philox(key=100 + G))
@@ -81,11 +86,12 @@ def test_sharded_cemppi_equals_unsharded_and_oracle(gpu_bound, orc, G, sigma_est
     grp.close()
 
 
+@pytest.mark.parametrize("peer", [False, True], ids=["hostbarrier", "peer"])
 @pytest.mark.parametrize("policy", ["μΣaismppi", "pmcmppi", "cmamppi", "imppi"])
-def test_other_policies_sharded(gpu_bound, orc, policy):
+def test_other_policies_sharded(gpu_bound, orc, policy, peer):
     env = make_env("car")
     K, T, N, G = 1536, 20, 4, 3
-    grp, engs = sharded_engines(gpu_bound, policy, env, K, T, N, G)
+    grp, engs = sharded_engines(gpu_bound, policy, env, K, T, N, G, peer=peer)
     cpu = configure(orc.engine(nthreads=8, **engine_kwargs(policy, env, K, T, N)), env, policy)
     rng = np.random.Generator(np.random.Philox(key=5))
     Z, u = rng.standard_normal((cpu.cs, K, cpu.N)), rng.uniform(size=(K, max(cpu.N - 1, 1)))
@@ -121,17 +127,20 @@ def test_sharded_early_stop(gpu_bound, orc):
     grp.close()
 
 
-def test_device_rng_is_independent_of_the_sharding(gpu_bound):
-    """The Philox counter is the GLOBAL sample id: a sharded policy draws the same noise as the unsharded one."""
+@pytest.mark.parametrize("peer", [False, True], ids=["hostbarrier", "peer"])
+def test_device_rng_is_independent_of_the_sharding(gpu_bound, peer):
+    """The Philox counter is the GLOBAL sample id: a sharded policy draws the same noise as the unsharded one. With
+    peer=True the step runs as a captured CUDA graph containing the peer-memory collectives (epochs live on the
+    device), replayed for the second control step."""
     env = make_env("car")
     K, T, N, G = 4096, 30, 5, 4
-    grp, engs = sharded_engines(gpu_bound, "cemppi", env, K, T, N, G, sigma_est="ss")
+    grp, engs = sharded_engines(gpu_bound, "cemppi", env, K, T, N, G, peer=peer, sigma_est="ss")
     one = configure(Engine(gpu_bound, **engine_kwargs("cemppi", env, K, T, N, sigma_est="ss")), env, "cemppi")
     for e in engs + [one]:
         e.seed(77)
     U = np.zeros(one.cs)
     st = env.state
-    for step in range(2):
+    for step in range(3):
         res = plan_all(engs, st, step, U)
         c1, u1, i1 = one.plan(st, step, U)
         for cr, ur, ir in res:

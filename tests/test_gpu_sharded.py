@@ -1,5 +1,6 @@
 """BASELINE config 5 (sample-sharded :cemppi) on real GPUs: a policy sharded over 2 GPUs (one process per
-GPU, the engine's own NCCL communicator) must reproduce the single-GPU result. Skipped on a 1-GPU box."""
+GPU; exchanges over the engine's own NCCL communicator, and over the peer-memory kernels of csrc/comm.cu through CUDA
+IPC) must reproduce the single-GPU result. Skipped on a 1-GPU box."""
 import os
 import socket
 import sys
@@ -28,7 +29,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, policy, K, out_dir):
+def _worker(rank, world, port, policy, K, out_dir, peer):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
     import torch
@@ -42,7 +43,7 @@ def _worker(rank, world, port, policy, K, out_dir):
     env = make_env("car")
     g = configure(Engine(_lib.product(), **engine_kwargs(policy, env, K, 30, 5, sigma_est="ss", device=rank, rank=rank,
                                                         world_size=world)), env, policy)
-    g.comm_init(sharding.broadcast_comm_id(dist, rank))
+    assert sharding.connect(g, dist, rank, world, peer=peer) == ("peer" if peer else "nccl")
     g.seed(77)
     U = np.zeros(g.cs)
     st = env.state
@@ -57,13 +58,14 @@ def _worker(rank, world, port, policy, K, out_dir):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer"])
 @pytest.mark.parametrize("policy", ["cemppi", "μΣaismppi", "pmcmppi", "cmamppi"])
-def test_two_gpu_shards_match_single_gpu(tmp_path, gpu_bound, policy):
+def test_two_gpu_shards_match_single_gpu(tmp_path, gpu_bound, policy, peer):
     import torch.multiprocessing as mp
     from conftest import configure, engine_kwargs, make_env
     from mpopis_b200.engine import Engine
     K = 4096
-    mp.spawn(_worker, args=(2, _free_port(), policy, K, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), policy, K, str(tmp_path), peer), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
     env = make_env("car")
     g = configure(Engine(gpu_bound, **engine_kwargs(policy, env, K, 30, 5, sigma_est="ss")), env, policy)

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from bench import make_engine
-from mpopis_b200 import _lib
+from mpopis_b200 import _lib, sharding
 
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
@@ -17,9 +17,7 @@ if world > 1:
 K = int(sys.argv[1]) * world
 env, eng = make_engine(_lib.product(), K, rank, world, lr)
 if world > 1:
-    ids = [_lib.comm_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    eng.comm_init(ids[0])
+    print("transport", sharding.connect(eng, dist, rank, world), file=sys.stderr)
 U, st = np.zeros(eng.cs), env.state.copy()
 for i in range(4):
     ctrl, U, its = eng.plan(st, i, U)
