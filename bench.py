@@ -343,8 +343,9 @@ def main():
 
     # ---------------- rooflines ----------------
     hbm_peak, peak_src = peaks()
-    variant = int(eng.get_option("rollout_variant"))
+    variant = int(eng.get_option("rollout_variant_used"))  # what the automatic choice (6) resolved to at this K
     kname = {4: "rollout_car_split_kernel<1> (v5: velocity warps + pose/reward warps)",
+             5: "rollout_car_split_kernel<1> wide (v5: 1 velocity warp + 2 pose/reward warps per 32 rollouts)",
              3: "rollout_car_kernel<1,3,0> (v4: one thread per rollout)"}.get(variant, f"rollout variant {variant}")
     roll_ms_per_launch = tm["rollout_ms"] / max(tm["rollout_launches"], 1)
     alg_bytes = ALG_BYTES_PER_ROLLOUT_STEP * eng.Kloc * T

@@ -251,14 +251,18 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
 
 /* λ̂ of the last shrinkage covariance estimate (:lw/:ss/:rblw/:oas), for parity tests. */
 int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out);
-/* Tuning knobs, not part of the reference API: "rollout_variant" (3 = default, speculative straight-line
- * step with repair; 0 = branchy fast formulation; 2 = first fast cut; 1 = literal libm call sequence of
- * CAR:299-333), "rollout_block" (threads per CTA of the rollout kernel: 32, 64, 96 or 128), "rollout_queue" (n > 0: persistent work-queue rollout kernel with n warps per SM handing out
- * (32 rollouts x 10 control steps) units dynamically; 0 = one thread per rollout, one launch-time placement),
- * "rollout_profile" (1 = record per-warp cycles of the rollout kernel, see warp_cycles), "rollout_stage" (how the rollout
- * kernel reads the noise tensor: 0 = register prefetch, 1 = TMA bulk copies into a per-warp shared-memory ring), "apply_l" (E = L·Z kernel,
- * process-wide: 0 = DFMA register tile, 1 = DMMA 32-row blocks, 2 = DMMA column tiles with cp.async),
- * "moments_small" (1 = single-CTA moment chain for <= 512 columns, the default; 0 = the multi-kernel chain). */
+/* Tuning knobs, not part of the reference API (the full table with defaults is in INTEGRATION.md):
+ * "rollout_variant" (6 = automatic, the default: the warp-specialised kernel 5 while every rollout of the shard stays
+ * resident, the thread-per-rollout kernel 3 beyond; 4 = warp-specialised at 96 registers; 0 = branchy fast formulation,
+ * also the repair path; 1 = literal libm call sequence of CAR:299-333, the parity anchor), "rollout_spin" (hand-over of
+ * the warp-specialised kernel: -1 automatic, 0 mbarrier, 1 spin counters), "rollout_block" (threads per CTA of the
+ * thread-per-rollout kernel: 32, 64, 96 or 128), "rollout_profile" (1 = record per-warp cycles, see warp_cycles),
+ * "rollout_stage" (noise tensor of kernel 3: 0 = register prefetch, 1 = TMA bulk copies into a shared-memory ring),
+ * "graph" (1 = replay the control step as a CUDA graph, the default), "fuse_cov" (1 = shrinkage + ridge folded into
+ * the Cholesky launch), "select_cluster" (1 = elite selection as one 8-CTA cluster instead of the cooperative grid),
+ * "moments_small" (1 = single-CTA moment chain for <= 512 columns, the default; 0 = the multi-kernel chain).
+ * get_option additionally reads "rollout_variant_used" (what 6 resolved to at the latest launch), "graph_active",
+ * "ce_select" and "comm_peer". */
 int mpopis_b200_set_option(mpopis_t *h, const char *key, double value);
 int mpopis_b200_get_option(mpopis_t *h, const char *key, double *value_out);
 

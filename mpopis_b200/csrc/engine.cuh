@@ -124,7 +124,6 @@ void launch_philox_uniforms(double *u, int K, uint64_t seed, uint32_t step, cons
                             const int *stop, cudaStream_t s);
 void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E, long long ldk, int K,
                     const int *stop, cudaStream_t s);
-void set_apply_L_path(int path);  // 0 DFMA tile, 1 DMMA row blocks, 2 DMMA column tiles (process-wide)
 void launch_transpose_in(const double *colmajor, double *dev, int cs, int K, long long ldk, cudaStream_t s);
 void launch_transpose_out(const double *dev, double *colmajor, int cs, int K, long long ldk, const double *shift_a,
                           const double *shift_b, cudaStream_t s);

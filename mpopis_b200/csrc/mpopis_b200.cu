@@ -75,7 +75,7 @@ struct mpopis_handle {
   long long step = 0;
   int select_cluster = 0;  // "select_cluster" option: the single-cluster flavour of the elite selection (select.cu)
   int rollout_spin = -1;  // split kernel hand-over: -1 auto, 0 mbarrier, 1 spin on shared-memory counters
-  int rollout_variant = 6, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1, sel_max = 1;
+  int rollout_variant = 6, rollout_variant_used = -1, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1, sel_max = 1;
   bool moments_small = true;  // single-CTA moment chain for small n ("moments_small" option, A/B)
   int sigma_bs = 0;  // block size of the initial Σ (as => block diagonal, cs => dense)
   bool L0_valid = false;
@@ -373,8 +373,9 @@ int launch_rollouts(mpopis_t *h, const double *U_cur, const double *U_orig, cons
     const int ctas = (h->Kloc + 63) / 64;
     // default: the lone-CTA flavour (255 registers, spin hand-over) while at most two CTAs share an SM
     const int spin = h->rollout_spin < 0 ? ctas <= 2 * h->num_sms : h->rollout_spin;
+    h->rollout_variant_used = variant;
     if (!(variant >= 4 && launch_rollout_car_split(h->car, a, variant == 5, spin, h->stop(), h->st)))
-      launch_rollout_car(h->car, a, variant >= 4 ? 3 : variant, h->rollout_block,
+      h->rollout_variant_used = variant >= 4 ? 3 : variant, launch_rollout_car(h->car, a, variant >= 4 ? 3 : variant, h->rollout_block,
                          h->rollout_stage, h->stop(), h->st);
   } else
     launch_rollout_mc(h->mc, a, h->rollout_block, h->stop(), h->st);
@@ -1178,10 +1179,6 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     h->rollout_spin = value < 0 ? -1 : (value != 0.0);
   } else if (!strcmp(key, "fuse_cov")) {
     h->fuse_cov = value != 0.0;
-  } else if (!strcmp(key, "apply_l")) {
-    if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
-      return fail(MPOPIS_ERR_BAD_ARG, "apply_l must be 0, 1, 2 or 3");
-    set_apply_L_path((int)value);  // process-wide
   } else
     return fail(MPOPIS_ERR_BAD_ARG, "unknown option %s", key);
   return 0;
@@ -1190,6 +1187,8 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
 int mpopis_b200_get_option(mpopis_t *h, const char *key, double *value_out) {
   if (!h || !key || !value_out) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (!strcmp(key, "rollout_variant")) *value_out = h->rollout_variant;
+  else if (!strcmp(key, "rollout_variant_used")) *value_out = h->rollout_variant_used;  // of the latest launch (6 resolved)
+  else if (!strcmp(key, "comm_peer")) *value_out = h->comm.peer;
   else if (!strcmp(key, "rollout_block")) *value_out = h->rollout_block;
   else if (!strcmp(key, "rollout_stage")) *value_out = h->rollout_stage;
   else if (!strcmp(key, "moments_small")) *value_out = h->moments_small;

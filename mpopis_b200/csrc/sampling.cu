@@ -93,154 +93,18 @@ __global__ void __launch_bounds__(256) apply_L_block_kernel(const double *Lt, in
   E[(size_t)r * ldk + k] = acc;
 }
 
-// Dense lower-triangular E = L Z as a register-tiled FP64 GEMM: CTA tile = 32 rows x 128 samples,
-// 256 threads as 8 (row groups) x 32 (sample groups), 4 x 4 outputs per thread; j is walked in slabs of
-// 16 staged in shared memory (L slab transposed so a thread's 4 rows are one 32-byte read, broadcast
-// across the 32 lanes of a warp; Z slab read as 32-byte vectors). Row tile b only needs j < 32(b+1)
-// (Lt carries explicit zeros above the diagonal), so the triangle costs ~half a square GEMM.
-// FP64 has no tcgen05 kind and DMMA (mma.sync m8n8k4) has the same peak as the DFMA pipe on B200, so
-// this stays on the FMA pipe.
-// Round-1 ncu (profiles/): with the 4 x 4 register tile the kernel is bound by shared-memory wavefronts
-// (67 % of peak, FP64 36 %) because every warp re-reads the Z slab. A 4 x 8 tile (AL_BN = 256) halves the Z
-// wavefronts per FMA but measured SLOWER (153 vs 112 µs: register pressure cuts the resident warps), so the
-// 4 x 4 tile stays.
-constexpr int AL_BM = 32, AL_BN = 128, AL_BJ = 16, AL_NB = AL_BN / 64;  // AL_NB pairs of samples per thread
-__global__ void __launch_bounds__(256) apply_L_dense_kernel(const double *__restrict__ Lt, int cs,
-                                                             const double *__restrict__ Z,
-                                                             double *__restrict__ E, long long ldk, int K,
-                                                             const int *stop) {
-  if (stop && *stop) return;
-  __shared__ __align__(16) double Ls[AL_BJ][AL_BM];  // Ls[j][i]
-  __shared__ __align__(16) double Zs[AL_BJ][AL_BN];  // Zs[j][k]
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty: 0..7
-  const int kbase = blockIdx.x * AL_BN, i0 = blockIdx.y * AL_BM;
-  double acc[4][2 * AL_NB];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 2 * AL_NB; ++b) acc[a][b] = 0.0;
-  const int jend = min(i0 + AL_BM, cs);
-  for (int jc = 0; jc < jend; jc += AL_BJ) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < AL_BJ * AL_BM; e += 256) {  // L slab: coalesced along j, stored transposed
-      const int ii = e / AL_BJ, jj = e % AL_BJ;
-      const int i = i0 + ii, j = jc + jj;
-      Ls[jj][ii] = (i < cs && j < cs) ? __ldg(Lt + (size_t)i * cs + j) : 0.0;
-    }
-    for (int e = threadIdx.x; e < AL_BJ * AL_BN; e += 256) {
-      const int jj = e / AL_BN, kk = e % AL_BN;
-      const int j = jc + jj, kg = kbase + kk;
-      Zs[jj][kk] = (j < cs && kg < K) ? Z[(size_t)j * ldk + kg] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int jj = 0; jj < AL_BJ; ++jj) {
-      const double2 l01 = *reinterpret_cast<const double2 *>(&Ls[jj][ty * 4]);
-      const double2 l23 = *reinterpret_cast<const double2 *>(&Ls[jj][ty * 4 + 2]);
-      // samples {64q + 2tx, 64q + 2tx + 1}: consecutive lanes read consecutive 16-byte words
-      const double l[4] = {l01.x, l01.y, l23.x, l23.y};
-      double z[2 * AL_NB];
-#pragma unroll
-      for (int q = 0; q < AL_NB; ++q) {
-        const double2 zz = *reinterpret_cast<const double2 *>(&Zs[jj][64 * q + tx * 2]);
-        z[2 * q] = zz.x, z[2 * q + 1] = zz.y;
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 2 * AL_NB; ++b) acc[a][b] = fma(l[a], z[b], acc[a][b]);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int i = i0 + ty * 4 + a;
-    if (i >= cs) continue;
-#pragma unroll
-    for (int q = 0; q < AL_NB; ++q) {
-      const int k = kbase + 64 * q + tx * 2;
-      double *dst = E + (size_t)i * ldk + k;
-      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[a][2 * q], acc[a][2 * q + 1]);
-      else if (k < K) dst[0] = acc[a][2 * q];
-    }
-  }
-}
-
-// The same contraction on the FP64 tensor cores: mma.sync.m8n8k4.f64 (SASS: DMMA). FP64 has no tcgen05
-// kind, so this warp-level MMA is the tensor path that exists for doubles; on B200 its peak is ~1.3x the
-// DFMA pipe, and — what matters here — one instruction performs 256 FMAs from 2+2 register operands per
-// lane, i.e. 8x less shared-memory traffic per FMA than the 4x4 register tile above (which ncu showed bound
-// by shared-memory wavefronts). CTA = 4 warps, tile = 32 rows x 128 samples (32 samples per warp, 4 x 4
-// accumulator fragments); row fragments beyond cs are skipped, so the triangle is followed at 8-row
-// granularity. Fragment layouts (PTX ISA, m8n8k4 .f64): A[g][t], B[t][g], C[g][2t..2t+1] with g = lane/4,
-// t = lane%4. Shared pitches 20 and 136 doubles make every fragment load 2 wavefronts (the minimum).
-constexpr int DM_BM = 32, DM_BN = 128, DM_BJ = 16, DM_LP = 20, DM_ZP = 136;
-__global__ void __launch_bounds__(128) apply_L_dmma_kernel(const double *__restrict__ Lt, int cs,
-                                                            const double *__restrict__ Z, double *__restrict__ E,
-                                                            long long ldk, int K, const int *stop) {
-  if (stop && *stop) return;
-  __shared__ double Ls[DM_BM][DM_LP];
-  __shared__ double Zs[DM_BJ][DM_ZP];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int kbase = blockIdx.x * DM_BN, i0 = blockIdx.y * DM_BM;
-  const int nrf = min(4, (cs - i0 + 7) / 8);  // row fragments that contain rows < cs
-  double acc[4][4][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  const int jend = min(i0 + DM_BM, cs);
-  for (int jc = 0; jc < jend; jc += DM_BJ) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < DM_BM * DM_BJ; e += 128) {
-      const int ii = e / DM_BJ, jj = e % DM_BJ;
-      const int i = i0 + ii, j = jc + jj;
-      Ls[ii][jj] = (i < cs && j < cs) ? __ldg(Lt + (size_t)i * cs + j) : 0.0;
-    }
-    for (int e = threadIdx.x; e < DM_BJ * DM_BN; e += 128) {
-      const int jj = e / DM_BN, kk = e % DM_BN;
-      const int j = jc + jj, kg = kbase + kk;
-      Zs[jj][kk] = (j < cs && kg < K) ? Z[(size_t)j * ldk + kg] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j4 = 0; j4 < DM_BJ; j4 += 4) {
-      double bf[4];
-#pragma unroll
-      for (int cf = 0; cf < 4; ++cf) bf[cf] = Zs[j4 + t][w * 32 + cf * 8 + g];
-#pragma unroll
-      for (int rf = 0; rf < 4; ++rf) {
-        if (rf >= nrf) break;
-        const double af = Ls[rf * 8 + g][j4 + t];
-#pragma unroll
-        for (int cf = 0; cf < 4; ++cf)
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(acc[rf][cf][0]), "+d"(acc[rf][cf][1])
-                       : "d"(af), "d"(bf[cf]));
-      }
-    }
-  }
-#pragma unroll
-  for (int rf = 0; rf < 4; ++rf) {
-    const int i = i0 + rf * 8 + g;
-    if (rf >= nrf || i >= cs) continue;
-#pragma unroll
-    for (int cf = 0; cf < 4; ++cf) {
-      const int k = kbase + w * 32 + cf * 8 + 2 * t;
-      double *dst = E + (size_t)i * ldk + k;
-      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[rf][cf][0], acc[rf][cf][1]);
-      else if (k < K) dst[0] = acc[rf][cf][0];
-    }
-  }
-}
-
-// Second DMMA formulation (the default; MPOPIS_APPLY_L=1 / "apply_l" = 1 selects the kernel above): the kernel above re-reads Z once per 32-row block (2.9x for
-// cs = 100), stages L and Z single-buffered between two barriers and leaves the triangle's load imbalance to
-// the block scheduler. Here ONE CTA owns a 64-sample column tile and ALL rows of a 104-row block (13 row
-// fragments of 8), so Z streams through shared memory exactly once per block, double-buffered with cp.async
+// Dense lower-triangular E = L Z on the FP64 tensor path: mma.sync.m8n8k4.f64 (SASS: DMMA). FP64 has no tcgen05 kind,
+// so this warp-level MMA is the tensor path that exists for doubles; one instruction performs 256 FMAs from 2+2
+// register operands per lane, i.e. 8x less shared-memory traffic per FMA than a 4x4 DFMA register tile (round 1
+// measured that tile bound by shared-memory wavefronts, and two other DMMA tilings slower than the one below:
+// profiles/README.md items 5, 15; they were removed in round 2). Fragment layouts (PTX ISA, m8n8k4 .f64): A[g][t],
+// B[t][g], C[g][2t..2t+1] with g = lane/4, t = lane%4.
+//
+// ONE CTA owns a 64-sample column tile and ALL rows of a 104-row block (13 row fragments of 8), so Z streams through shared memory exactly once per block, double-buffered with cp.async
 // (16-byte vectors, zero-filled past cs / ldk); L (80 KB for cs = 100, shared by every CTA) is read through
 // the read-only L1 path straight into A fragments. Seven warps: warp w owns row fragments {w, 12 − w}
 // (w = 6: fragment 6 alone) — fragment f needs j < 8f + 8, so each pair costs 14 units and the triangle is
-// balanced inside the CTA. Fragment layouts as above; Z pitch 68 doubles (≡ 4 mod 16) keeps the B-fragment
+// balanced inside the CTA. Z pitch 68 doubles (≡ 4 mod 16) keeps the B-fragment
 // loads conflict-free. ncu on the first cut (2 buffers, 2 barriers per chunk, L read at the point of use): 27 % of
 // the stall samples on the barrier, 23 % on the L loads (long scoreboard), DMMA pipe 44 % busy — hence the 3-stage
 // ring (one barrier per chunk) and A fragments fetched one chunk ahead. Measured DMMA cost on B200: ≈24.5 pipe
@@ -353,131 +217,14 @@ __global__ void __launch_bounds__(D2_NT, 2) apply_L_dmma2_kernel(const double *_
   }
 }
 
-// Third DMMA formulation ("apply_l" = 3, opt-in until measured): the kernel above balances the triangle over its
-// seven warps only on average — per 16-row chunk the warps hold 2, 1 or 0 active row fragments and the barrier
-// makes everyone wait for the busiest (≈70 % lock-step efficiency, 22 % of the stall samples on the barrier). Here
-// the COLUMNS are split instead: a CTA is 8 warps x 8 samples, every warp carries all 13 row fragments of the
-// 104-row block (26 accumulator doubles), so each warp does the whole triangle for its 8 columns and the warps
-// are perfectly balanced. L chunks (104 x 16) travel through the same 3-stage cp.async ring as Z.
-constexpr int D3_NW = 8, D3_NT = 32 * D3_NW, D3_BN = 8 * D3_NW, D3_LP = 20;
-struct D3Smem {
-  double Zs[3][D2_BJ][D2_ZP];
-  double Ls[3][D2_RB][D3_LP];
-};
-
-__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gsrc, bool pred) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int sz = pred ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
-}
-
-__global__ void __launch_bounds__(D3_NT, 2) apply_L_dmma3_kernel(const double *__restrict__ Lt, int cs,
-                                                                  const double *__restrict__ Z,
-                                                                  double *__restrict__ E, long long ldk, int K,
-                                                                  const int *stop) {
-  if (stop && *stop) return;
-  extern __shared__ __align__(16) unsigned char d3raw[];
-  D3Smem &sm = *reinterpret_cast<D3Smem *>(d3raw);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int kbase = blockIdx.x * D3_BN, i0 = blockIdx.y * D2_RB;
-  const int jend = min(i0 + D2_RB, cs);
-  const int nchunks = (jend + D2_BJ - 1) / D2_BJ;
-  const int nfr = min(D2_NF, (cs - i0 + 7) / 8);  // row fragments of this block that contain rows < cs
-  double acc[D2_NF][2];
-#pragma unroll
-  for (int f = 0; f < D2_NF; ++f) acc[f][0] = acc[f][1] = 0.0;
-
-  auto stage = [&](int chunk) {
-    if (chunk < nchunks) {
-      const int jc = chunk * D2_BJ, buf = chunk % 3;
-      for (int e = threadIdx.x; e < D2_BJ * (D3_BN / 2); e += D3_NT) {  // Z: 16 rows x 64 samples, 16-byte vectors
-        const int jj = e / (D3_BN / 2), v = e % (D3_BN / 2);
-        const int j = jc + jj;
-        const long long kg = (long long)kbase + 2 * v;
-        const bool pred = j < cs && kg + 1 < ldk;
-        cp_async16_zfill(&sm.Zs[buf][jj][2 * v], pred ? (const void *)(Z + (size_t)j * ldk + kg) : (const void *)Z, pred);
-      }
-      for (int e = threadIdx.x; e < 8 * nfr * D2_BJ; e += D3_NT) {  // L: rows i0.. x 16 columns jc.., 8-byte copies
-        const int ii = e / D2_BJ, jj = e % D2_BJ;
-        const int i = i0 + ii, j = jc + jj;
-        const bool pred = i < cs && j < cs;
-        cp_async8_zfill(&sm.Ls[buf][ii][jj], pred ? (const void *)(Lt + (size_t)i * cs + j) : (const void *)Lt, pred);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  stage(0);
-  stage(1);
-  for (int c = 0; c < nchunks; ++c) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();
-    stage(c + 2);
-    const int buf = c % 3, jc = c * D2_BJ;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j4 = 4 * q, jg = jc + j4;
-      if (jg >= jend) break;
-      const double bf = sm.Zs[buf][j4 + t][w * 8 + g];
-      const int fmin = (jg - i0) >> 3;  // fragment f needs j < i0 + 8f + 8  <=>  f > (j − i0)/8 − 1
-#pragma unroll
-      for (int f = 0; f < D2_NF; ++f) {
-        if (f >= fmin && f < nfr) {  // warp-uniform
-          const double af = sm.Ls[buf][f * 8 + g][j4 + t];
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(acc[f][0]), "+d"(acc[f][1])
-                       : "d"(af), "d"(bf));
-        }
-      }
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  const int k = kbase + w * 8 + 2 * t;
-#pragma unroll
-  for (int f = 0; f < D2_NF; ++f) {
-    const int i = i0 + f * 8 + g;
-    if (f < nfr && i < cs) {
-      double *dst = E + (size_t)i * ldk + k;
-      if (k + 1 < K) *reinterpret_cast<double2 *>(dst) = make_double2(acc[f][0], acc[f][1]);
-      else if (k < K) dst[0] = acc[f][0];
-    }
-  }
-}
-
-// 0 = DFMA register tile, 1 = DMMA (32-row blocks), 2 = DMMA column-tile kernel; MPOPIS_APPLY_L / the
-// "apply_l" option select it process-wide (A/B evidence, profiles/).
-static int g_apply_L_path = -1;
-static int apply_L_path() {
-  if (g_apply_L_path < 0) {
-    const char *e = getenv("MPOPIS_APPLY_L");
-    g_apply_L_path = (e && e[0] == 'f') ? 0 : (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;  // default: 2
-  }
-  return g_apply_L_path;
-}
-void set_apply_L_path(int path) { g_apply_L_path = path; }
-
 void launch_apply_L(const double *Lt, int cs, int bs, const double *Z, double *E, long long ldk, int K,
                     const int *stop, cudaStream_t s) {
   if (bs < cs) {
     dim3 grid((K + 255) / 256, cs);
     apply_L_block_kernel<<<grid, 256, 0, s>>>(Lt, cs, bs, Z, E, ldk, K, stop);
-  } else if (apply_L_path() == 3) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(apply_L_dmma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(D3Smem));
-      attr_set = true;
-    }
-    dim3 grid((K + D3_BN - 1) / D3_BN, (cs + D2_RB - 1) / D2_RB);
-    apply_L_dmma3_kernel<<<grid, D3_NT, sizeof(D3Smem), s>>>(Lt, cs, Z, E, ldk, K, stop);
-  } else if (apply_L_path() == 2) {
+  } else {
     dim3 grid((K + D2_BN - 1) / D2_BN, (cs + D2_RB - 1) / D2_RB);
     apply_L_dmma2_kernel<<<grid, D2_NT, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);
-  } else if (apply_L_path() == 1) {
-    dim3 grid((K + DM_BN - 1) / DM_BN, (cs + DM_BM - 1) / DM_BM);
-    apply_L_dmma_kernel<<<grid, 128, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);
-  } else {
-    dim3 grid((K + AL_BN - 1) / AL_BN, (cs + AL_BM - 1) / AL_BM);
-    apply_L_dense_kernel<<<grid, 256, 0, s>>>(Lt, cs, Z, E, ldk, K, stop);
   }
 }
 
