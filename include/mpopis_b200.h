@@ -144,7 +144,8 @@ int mpopis_b200_comm_init_loopback(mpopis_t *h, void *group);
  * the 2cs+1 / cs²+1 moment sums) are single kernels that store into the peers' memory and spin on arrival flags
  * (csrc/comm.cu) instead of NCCL calls; NCCL keeps serving the oversize all-reduce of :cmamppi. The reference has no
  * counterpart (its only parallel loop is Threads.@threads over the samples, POL:269). comm_peer_loopback does the
- * same between the virtual ranks of a loop-back group (collective: call it from every rank's thread). */
+ * same between the virtual ranks of a loop-back group (collective: call it from every rank's thread; the process must
+ * run with CUDA_MODULE_LOADING=EAGER because the virtual ranks share one CUDA context — see csrc/comm.cu). */
 int mpopis_b200_comm_peer_export(mpopis_t *h, void *handle_out128);
 int mpopis_b200_comm_peer_attach(mpopis_t *h, const void *handles, int64_t n_bytes);
 int mpopis_b200_comm_peer_loopback(mpopis_t *h);

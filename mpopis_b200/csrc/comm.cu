@@ -199,12 +199,14 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
 __device__ __forceinline__ double *peer_slot(char *region, int par, int world, int src, size_t slot_n) {
   return (double *)(region + PEER_CTRL_BYTES) + ((size_t)par * world + src) * slot_n;
 }
-// spin until *flag reaches `want` (epochs only grow); false on timeout
-__device__ bool wait_flag(const unsigned *flag, unsigned want) {
+// spin until *flag reaches `want` (epochs only grow); false on timeout. Once a collective of this handle has timed out
+// (*err set, sticky until the host reads it) later ones give up after ~1 ms instead of 10 s each.
+__device__ bool wait_flag(const unsigned *flag, unsigned want, const int *err) {
   const long long t0 = clock64();
+  const long long limit = (err && *(const volatile int *)err == COMM_PEER_TIMEOUT) ? 2000000LL : 20000000000LL;
   while ((int)(ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(40);
-    if (clock64() - t0 > 20000000000LL) return false;
+    if (clock64() - t0 > limit) return false;
   }
   return true;
 }
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(double *__restrict_
     __threadfence_system();  // the other CTAs' stores (fenced before their atomicAdd) precede the flags
     for (int p = 0; p < world; ++p) st_release_sys(&((PeerCtrl *)tab.region[p])->flags_ar[par][rank], e + 1);
   }
-  if (threadIdx.x < world && !wait_flag(&me->flags_ar[par][threadIdx.x], e + 1) && err) atomicCAS(err, 0, COMM_PEER_TIMEOUT);
+  if (threadIdx.x < world && !wait_flag(&me->flags_ar[par][threadIdx.x], e + 1, err) && err) atomicCAS(err, 0, COMM_PEER_TIMEOUT);
   __syncthreads();
   for (int i = i0; i < n; i += stride) {
     double s = __ldcg(peer_slot(tab.region[rank], par, world, 0, slot_n) + i);
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(const double *__res
     __threadfence_system();
     for (int p = 0; p < world; ++p) st_release_sys(&((PeerCtrl *)tab.region[p])->flags_ag[rank], e + 1);
   }
-  if (threadIdx.x < world && threadIdx.x != rank && !wait_flag(&me->flags_ag[threadIdx.x], e + 1) && err)
+  if (threadIdx.x < world && threadIdx.x != rank && !wait_flag(&me->flags_ag[threadIdx.x], e + 1, err) && err)
     atomicCAS(err, 0, COMM_PEER_TIMEOUT);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -288,6 +290,9 @@ int comm_peer_alloc(Comm &c, size_t slot_doubles) {
   CUC(cudaMalloc((void **)&c.peer_region, bytes));
   CUC(cudaMemset(c.peer_region, 0, bytes));
   CUC(cudaDeviceSynchronize());  // zeroed before any peer can learn the address
+  cudaFuncAttributes fa;         // load both kernels now, not under a spinning peer
+  CUC(cudaFuncGetAttributes(&fa, peer_allreduce_kernel));
+  CUC(cudaFuncGetAttributes(&fa, peer_allgather_kernel));
   c.peer_slot_n = slot_doubles;
   return 0;
 }
@@ -323,9 +328,26 @@ int comm_peer_attach(Comm &c, double *gather_base, const void *all_handles) {
   return 0;
 }
 
+// CUDA's lazy module loading may synchronise the context when a kernel is first used. Between PROCESSES that is harmless
+// (a rank's spinning kernel only needs the peer's kernel of the same collective, launched before any later load), but
+// the virtual ranks of a loop-back group share one context: rank A's kernel spinning on rank B's flag would block the
+// very load rank B's launch is waiting for. Loop-back peer mode therefore requires CUDA_MODULE_LOADING=EAGER.
+static int module_loading_is_eager() {
+  void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return -1;
+  typedef int (*fn_t)(int *);
+  fn_t fn = (fn_t)dlsym(lib, "cuModuleGetLoadingMode");
+  int mode = 0;
+  if (!fn || fn(&mode) != 0) return -1;
+  return mode == 1;  // CU_MODULE_EAGER_LOADING = 0x1, CU_MODULE_LAZY_LOADING = 0x2
+}
+
 int comm_peer_attach_loopback(Comm &c, double *gather_base) {
   if (!c.loop) return cfail("not a loop-back communicator");
   if (!c.peer_region) return cfail("comm_peer_alloc first");
+  if (module_loading_is_eager() != 1)
+    return cfail("peer-memory collectives between loop-back ranks need CUDA_MODULE_LOADING=EAGER in the environment "
+                 "(virtual ranks share one CUDA context: a lazy kernel load would wait for the spinning peer)");
   LoopGroup *g = c.loop;
   g->peer_region[c.rank] = c.peer_region, g->peer_gather[c.rank] = gather_base;
   if (g->barrier()) return cfail("loop-back group broken (a virtual rank left the collective sequence)");

@@ -335,7 +335,8 @@ class Engine:
         self._chk(self.b.comm_peer_attach(self.h, C.create_string_buffer(raw, len(raw)), len(raw)))
 
     def comm_peer_loopback(self):
-        """The same between the virtual ranks of a loop-back group (collective: every rank's thread calls it)."""
+        """The same between the virtual ranks of a loop-back group (collective: every rank's thread calls it; needs
+        CUDA_MODULE_LOADING=EAGER in the environment before CUDA initialises)."""
         self._chk(self.b.comm_peer_loopback(self.h))
 
     def warp_cycles(self) -> np.ndarray:
