@@ -253,13 +253,20 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(const double *__res
   if (threadIdx.x == 0) s_epoch = *(volatile unsigned *)&me->epoch_ag;
   __syncthreads();
   const unsigned e = s_epoch;
-  const size_t off = (size_t)rank * n_per, n2 = n_per / 2;  // n_per is even (a multiple of 32): 16-byte stores
-  const double2 *src = (const double2 *)(base + off);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-    const double2 v = src[i];
-    for (int p = 0; p < world; ++p)
-      if (p != rank) ((double2 *)(tab.gather[p] + off))[i] = v;
+  const size_t off = (size_t)rank * n_per, stride = (size_t)gridDim.x * blockDim.x;
+  if (n_per % 2 == 0) {  // the engine's shards are multiples of 32 samples: 16-byte stores
+    const double2 *src = (const double2 *)(base + off);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per / 2; i += stride) {
+      const double2 v = src[i];
+      for (int p = 0; p < world; ++p)
+        if (p != rank) ((double2 *)(tab.gather[p] + off))[i] = v;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per; i += stride) {
+      const double v = base[off + i];
+      for (int p = 0; p < world; ++p)
+        if (p != rank) tab.gather[p][off + i] = v;
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -357,6 +364,12 @@ int comm_peer_attach_loopback(Comm &c, double *gather_base) {
   return 0;
 }
 
+int comm_host_barrier(Comm &c) {
+  if (!c.loop) return 0;
+  if (c.loop->barrier()) return cfail("loop-back group broken (a virtual rank left the collective sequence)");
+  return 0;
+}
+
 int comm_allreduce_sum(Comm &c, double *buf, size_t n, cudaStream_t st) {
   if (c.world == 1) return 0;
   if (c.peer && n <= c.peer_slot_n) {
@@ -386,7 +399,7 @@ int comm_allreduce_sum(Comm &c, double *buf, size_t n, cudaStream_t st) {
 
 int comm_allgather_f64(Comm &c, double *base, size_t n_per_rank, cudaStream_t st) {
   if (c.world == 1) return 0;
-  if (c.peer && base == c.peer_tab.gather[c.rank] && n_per_rank % 2 == 0) {
+  if (c.peer && base == c.peer_tab.gather[c.rank]) {
     const unsigned grid = (unsigned)std::min<size_t>(32, (n_per_rank / 2 + 2047) / 2048);
     peer_allgather_kernel<<<grid, 512, 0, st>>>(base, n_per_rank, c.peer_tab, c.world, c.rank, c.peer_err);
     CUC(cudaGetLastError());

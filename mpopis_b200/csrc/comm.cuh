@@ -50,6 +50,7 @@ int comm_peer_alloc(Comm &c, size_t slot_doubles);
 int comm_peer_export(Comm &c, double *gather_base, void *out128);
 int comm_peer_attach(Comm &c, double *gather_base, const void *all_handles);
 int comm_peer_attach_loopback(Comm &c, double *gather_base);
+int comm_host_barrier(Comm &c);  // loop-back groups only (no-op otherwise): every virtual rank's thread has arrived
 int comm_allreduce_sum(Comm &c, double *buf, size_t n, cudaStream_t st);
 // in place: rank r's n_per_rank doubles live at base + r * n_per_rank
 int comm_allgather_f64(Comm &c, double *base, size_t n_per_rank, cudaStream_t st);

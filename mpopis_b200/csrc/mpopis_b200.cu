@@ -66,6 +66,11 @@ struct mpopis_handle {
   int dev = 0, world = 1, rank = 0;
   cudaStream_t st = nullptr, st2 = nullptr;  // main stream; side stream for the next iteration's normals
   cudaEvent_t ev_z_free = nullptr, ev_z_ready = nullptr, ev_q_fork = nullptr, ev_q_join = nullptr;
+  // injected noise / uniforms travel through a two-slot pinned ring (see stage_h2d)
+  double *h_pin[2] = {nullptr, nullptr};
+  size_t h_pin_bytes = 0;
+  cudaEvent_t ev_pin[2] = {nullptr, nullptr};
+  unsigned pin_next = 0;
   Comm comm{};
   bool env_set = false, cma_set = false;
   CarEnvArgs car{};
@@ -174,6 +179,32 @@ void dump_marks(mpopis_t *h) {
 
 int set_device(mpopis_t *h) {
   CU(cudaSetDevice(h->dev));
+  return 0;
+}
+
+// Host -> device copy of caller-owned (pageable) memory on h->st WITHOUT handing the driver a pageable pointer: a pageable
+// cudaMemcpyAsync blocks the calling thread inside the driver until the stream has drained, and with virtual ranks
+// sharing one context (loop-back group, peer-memory collectives) the thread it starves is the one that still has to
+// launch the kernel this rank's stream is spinning on. The bytes go through a two-slot pinned ring; a slot is reused
+// only after ITS previous copy has completed (an event wait on the copy alone, not on the stream).
+int ensure_pin(mpopis_t *h, size_t bytes) {
+  if (bytes <= h->h_pin_bytes) return 0;
+  CU(cudaStreamSynchronize(h->st));
+  for (int b = 0; b < 2; ++b) {
+    if (h->h_pin[b]) cudaFreeHost(h->h_pin[b]), h->h_pin[b] = nullptr;
+    CU(cudaMallocHost((void **)&h->h_pin[b], bytes));
+    if (!h->ev_pin[b]) CU(cudaEventCreateWithFlags(&h->ev_pin[b], cudaEventDisableTiming));
+  }
+  h->h_pin_bytes = bytes;
+  return 0;
+}
+int stage_h2d(mpopis_t *h, void *dst_dev, const void *src_host, size_t bytes) {
+  if (int rc = ensure_pin(h, bytes)) return rc;
+  const int b = (int)(h->pin_next++ & 1u);
+  CU(cudaEventSynchronize(h->ev_pin[b]));  // a never-recorded event is complete
+  memcpy(h->h_pin[b], src_host, bytes);
+  CU(cudaMemcpyAsync(dst_dev, h->h_pin[b], bytes, cudaMemcpyHostToDevice, h->st));
+  CU(cudaEventRecord(h->ev_pin[b], h->st));
   return 0;
 }
 
@@ -447,7 +478,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     // --- Z, E = L Z (POL:448) ---
     if (Z_host) {
       const double *src = Z_host + ((size_t)n * K + h->k0) * cs;
-      CU(cudaMemcpyAsync(h->d_stage, src, sizeof(double) * cs * Kloc, cudaMemcpyHostToDevice, st));
+      if (int rc = stage_h2d(h, h->d_stage, src, sizeof(double) * cs * Kloc)) return rc;
       launch_transpose_in(h->d_stage, h->d_Z, cs, Kloc, h->ldk, st);
     } else if (n == 0) {
       launch_philox_normals(h->d_Z, h->ldk, cs, Kloc, h->k0, h->seed, 0u, h->d_step, 0u, stop, st);
@@ -490,8 +521,9 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
       }
       case MPOPIS_POLICY_PMCMPPI: {  // POL:802-809
         h->launches += launch_weights(h->d_costs, K, h->cfg.lambda_ais, h->d_w, h->d_ones, stop, st) - 1;
-        if (u_host) CU(cudaMemcpyAsync(h->d_u, u_host + (size_t)n * K, sizeof(double) * K, cudaMemcpyHostToDevice, st));
-        else launch_philox_uniforms(h->d_u, K, h->seed, 0u, h->d_step, (uint32_t)n, stop, st);
+        if (u_host) {
+          if (int rc = stage_h2d(h, h->d_u, u_host + (size_t)n * K, sizeof(double) * K)) return rc;
+        } else launch_philox_uniforms(h->d_u, K, h->seed, 0u, h->d_step, (uint32_t)n, stop, st);
         launch_pmc_counts(h->d_w, K, h->d_u, h->d_cdf, h->d_counts, h->k0, Kloc, h->d_wcnt, stop, st);
         h->launches += 5;
         if (int rc = moments(h, h->d_E, h->ldk, Kloc, h->d_wcnt, true, 1, MPOPIS_SIGMA_MLE, 10e-9, true, nullptr,
@@ -580,8 +612,7 @@ void drop_graph(mpopis_t *h) {
 // Any capture/instantiate failure falls back to eager launches for the lifetime of the handle.
 int plan_step(mpopis_t *h) {
   factor_sigma0(h);
-  const bool can = h->graph_enabled && !h->trace && !h->comm.host_synchronous() &&
-                   !(h->comm.loop && h->cfg.policy == MPOPIS_POLICY_CMAMPPI) && h->cfg.env != MPOPIS_ENV_EXTERNAL;
+  const bool can = h->graph_enabled && !h->trace && !h->comm.host_synchronous() && h->cfg.env != MPOPIS_ENV_EXTERNAL;
   if (!can) return plan_core(h, nullptr, nullptr);
   if (!h->gexec) {
     const long long l0 = h->launches, step0 = h->step;
@@ -597,9 +628,15 @@ int plan_step(mpopis_t *h) {
     const cudaError_t e = cudaStreamEndCapture(h->st, &g);
     h->graph_launches = h->launches - l0;
     h->launches = l0, h->step = step0;  // nothing ran yet
-    if (rc || e != cudaSuccess || !g || cudaGraphInstantiate(&h->gexec, g, 0) != cudaSuccess) {
+    const bool bad = rc || e != cudaSuccess || !g || cudaGraphInstantiate(&h->gexec, g, 0) != cudaSuccess ||
+                     cudaGraphUpload(h->gexec, h->st) != cudaSuccess;
+    // virtual ranks share one context: instantiation / upload may synchronise the device, so nobody launches (and
+    // starts spinning on a peer) before every rank of the loop-back group is through it
+    if (comm_host_barrier(h->comm)) return fail(MPOPIS_ERR_NCCL, "%s", comm_error());
+    if (bad) {
       cudaGetLastError();
       if (g) cudaGraphDestroy(g);
+      if (h->gexec) cudaGraphExecDestroy(h->gexec);
       h->gexec = nullptr, h->graph_enabled = false;
       if (getenv("MPOPIS_GRAPH_VERBOSE")) fprintf(stderr, "[mpopis] graph capture failed (rc=%d, %s): eager launches\n", rc, cudaGetErrorString(e));
       return plan_core(h, nullptr, nullptr);
@@ -961,6 +998,10 @@ int mpopis_b200_destroy(mpopis_t *h) {
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto &e : h->mark_pool) cudaEventDestroy(e);
+  for (int b = 0; b < 2; ++b) {
+    if (h->h_pin[b]) cudaFreeHost(h->h_pin[b]);
+    if (h->ev_pin[b]) cudaEventDestroy(h->ev_pin[b]);
+  }
   if (h->ev_z_free) cudaEventDestroy(h->ev_z_free);
   if (h->ev_z_ready) cudaEventDestroy(h->ev_z_ready);
   if (h->ev_q_fork) cudaEventDestroy(h->ev_q_fork);
@@ -1034,9 +1075,18 @@ int mpopis_b200_comm_peer_attach(mpopis_t *h, const void *handles, int64_t n_byt
 int mpopis_b200_comm_peer_loopback(mpopis_t *h) {
   if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (h->world == 1) return 0;
+  // Virtual ranks share one device: a grid-cooperative launch of rank A does not start while rank B's collective
+  // kernel spins on A's flag (tools/coop_concurrency.cu), so the cooperative kernels are off the menu here — the
+  // elite selection runs as one thread-block cluster, and :cmamppi (cooperative Σ^-1/2 and merge sort) stays on the
+  // host-barrier transport.
+  if (h->cfg.policy == MPOPIS_POLICY_CMAMPPI)
+    return fail(MPOPIS_ERR_BAD_ARG, "peer-memory collectives between loop-back ranks do not support :cmamppi");
   if (int rc = set_device(h)) return rc;
   drop_graph(h);
   h->comm.peer_err = h->info();
+  h->select_cluster = 1;
+  // allocations may synchronise the device: make the ones the injected-noise path needs now, not under a spinning peer
+  if (int rc = ensure_pin(h, sizeof(double) * std::max((size_t)h->cs * h->Kloc, (size_t)h->K))) return rc;
   if (comm_peer_alloc(h->comm, (size_t)h->cs * h->cs + 2 * (size_t)h->cs + 64) ||
       comm_peer_attach_loopback(h->comm, h->d_costs))
     return fail(MPOPIS_ERR_NCCL, "%s", comm_error());

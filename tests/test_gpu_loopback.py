@@ -89,6 +89,8 @@ def test_sharded_cemppi_equals_unsharded_and_oracle(gpu_bound, orc, G, sigma_est
 @pytest.mark.parametrize("peer", [False, True], ids=["hostbarrier", "peer"])
 @pytest.mark.parametrize("policy", ["μΣaismppi", "pmcmppi", "cmamppi", "imppi"])
 def test_other_policies_sharded(gpu_bound, orc, policy, peer):
+    if peer and policy == "cmamppi":
+        pytest.skip("cooperative kernels (Σ^-1/2, merge sort) cannot run beside a spinning peer on the SAME device")
     env = make_env("car")
     K, T, N, G = 1536, 20, 4, 3
     grp, engs = sharded_engines(gpu_bound, policy, env, K, T, N, G, peer=peer)
