@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(const double *__res
   __syncthreads();
   const unsigned e = s_epoch;
   const size_t off = (size_t)rank * n_per, stride = (size_t)gridDim.x * blockDim.x;
-  if (n_per % 2 == 0) {  // the engine's shards are multiples of 32 samples: 16-byte stores
+  if (n_per % 2 == 0) {  // 16-byte stores
     const double2 *src = (const double2 *)(base + off);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per / 2; i += stride) {
       const double2 v = src[i];
