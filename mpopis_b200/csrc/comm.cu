@@ -168,11 +168,11 @@ void comm_destroy(Comm &c) {
 // rank holds pointers to all of them (PeerTable). Per control step the engine runs ~3 tiny exchanges per AIS iteration
 // (8 B x K_loc costs, 2cs+1 and cs²+1 moment sums): their cost is latency, not bytes, and NCCL's launch + protocol
 // latency (≈35 µs each on 8 GPUs, profiles/r2_multi_gpu.md) was most of the weak-scaling loss. Here:
-//   all-reduce  push my vector into slot[parity][my rank] of EVERY rank -> fence -> release-store the epoch into every
-//               rank's flag[parity][my rank] -> acquire-spin on my own world flags -> sum the world slots in rank order
-//               (bit-identical on all ranks, no atomics on data) -> last CTA bumps the device-resident epoch.
-//               Two parities suffice: a rank can only reach epoch e+2 after it received everyone's e+1 contribution,
-//               which each rank sends only after it finished reading epoch e.
+//   all-reduce  push my vector into slot[parity][my rank] of EVERY rank as self-validating 16-byte lines {lo, flag, hi,
+//               flag} (flag = epoch + 1: no fence, no separate flag, one NVLink trip) -> spin on the lines of my own
+//               slots and sum them in rank order (bit-identical on all ranks, no atomics on data) -> last CTA bumps the
+//               device-resident epoch. Two parities suffice: a rank can only reach epoch e+2 after it received
+//               everyone's e+1 contribution, which each rank sends only after it finished reading epoch e.
 //   all-gather  store my K_loc costs straight into segment [my rank] of every rank's cost vector, flag, wait. One
 //               buffer suffices because an all-reduce always separates two gathers (the step ends in one) and the
 //               consumers of the gathered costs are stream-ordered before this rank's contribution to it.
@@ -196,9 +196,6 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ double *peer_slot(char *region, int par, int world, int src, size_t slot_n) {
-  return (double *)(region + PEER_CTRL_BYTES) + ((size_t)par * world + src) * slot_n;
-}
 // spin until *flag reaches `want` (epochs only grow); false on timeout. Once a collective of this handle has timed out
 // (*err set, sticky until the host reads it) later ones give up after ~1 ms instead of 10 s each.
 __device__ bool wait_flag(const unsigned *flag, unsigned want, const int *err) {
@@ -211,35 +208,68 @@ __device__ bool wait_flag(const unsigned *flag, unsigned want, const int *err) {
   return true;
 }
 
+// All-reduce, "LL" wire format (the idea of NCCL's low-latency protocol): every double travels as ONE 16-byte store
+// {lo, flag, hi, flag} with flag = epoch + 1, so the data validates itself — no fence, no separate flag store, no second
+// NVLink round trip. Each 8-byte half is written atomically, hence a line whose two flags match is complete. The
+// receiver spins on the lines of its own slots and sums them in rank order.
+struct __align__(16) LLLine {
+  unsigned lo, f0, hi, f1;
+};
+__device__ __forceinline__ LLLine *peer_slot(char *region, int par, int world, int src, size_t slot_n) {
+  return (LLLine *)(region + PEER_CTRL_BYTES) + ((size_t)par * world + src) * slot_n;
+}
+__device__ __forceinline__ void ll_store(LLLine *dst, double v, unsigned flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"((unsigned)__double2loint(v)), "r"(flag),
+               "r"((unsigned)__double2hiint(v)), "r"(flag)
+               : "memory");
+}
+// false on timeout (≈10 s; ≈1 ms once a collective of this handle has already timed out)
+__device__ __forceinline__ bool ll_load(const LLLine *src, unsigned flag, double *v, const int *err) {
+  unsigned lo, f0, hi, f1;
+  long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+    if (f0 == flag && f1 == flag) break;
+    if ((spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      const long long limit = (err && *(const volatile int *)err == COMM_PEER_TIMEOUT) ? 2000000LL : 20000000000LL;
+      if (now - t0 > limit) return false;
+    }
+  }
+  *v = __hiloint2double((int)hi, (int)lo);
+  return true;
+}
+
 __global__ void __launch_bounds__(512) peer_allreduce_kernel(double *__restrict__ buf, int n, const PeerTable tab, int world,
                                                               int rank, size_t slot_n, int *err) {
   PeerCtrl *me = (PeerCtrl *)tab.region[rank];
   __shared__ unsigned s_epoch;
   if (threadIdx.x == 0) s_epoch = *(volatile unsigned *)&me->epoch_ar;
   __syncthreads();
-  const unsigned e = s_epoch;
+  const unsigned e = s_epoch, flag = e + 1;
   const int par = e & 1;
   const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int i = i0; i < n; i += stride) {
     const double v = buf[i];
-    for (int p = 0; p < world; ++p) peer_slot(tab.region[p], par, world, rank, slot_n)[i] = v;
+    for (int p = 0; p < world; ++p)
+      if (p != rank) ll_store(peer_slot(tab.region[p], par, world, rank, slot_n) + i, v, flag);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(&me->cnt_push, 1u) == gridDim.x - 1) {
-    __threadfence_system();  // the other CTAs' stores (fenced before their atomicAdd) precede the flags
-    for (int p = 0; p < world; ++p) st_release_sys(&((PeerCtrl *)tab.region[p])->flags_ar[par][rank], e + 1);
-  }
-  if (threadIdx.x < world && !wait_flag(&me->flags_ar[par][threadIdx.x], e + 1, err) && err) atomicCAS(err, 0, COMM_PEER_TIMEOUT);
-  __syncthreads();
+  bool ok = true;
   for (int i = i0; i < n; i += stride) {
-    double s = __ldcg(peer_slot(tab.region[rank], par, world, 0, slot_n) + i);
-    for (int q = 1; q < world; ++q) s += __ldcg(peer_slot(tab.region[rank], par, world, q, slot_n) + i);
+    const double own = buf[i];
+    double s = 0.0;
+    for (int q = 0; q < world; ++q) {  // rank order: bit-identical on every rank
+      double v = own;
+      if (q != rank) ok = ll_load(peer_slot(tab.region[rank], par, world, q, slot_n) + i, flag, &v, err) && ok;
+      s = q == 0 ? v : s + v;
+    }
     buf[i] = s;
   }
+  if (!ok && err) atomicCAS(err, 0, COMM_PEER_TIMEOUT);
   __syncthreads();
   if (threadIdx.x == 0 && atomicAdd(&me->cnt_exit, 1u) == gridDim.x - 1) {
-    me->cnt_push = 0, me->cnt_exit = 0;
+    me->cnt_exit = 0;
     __threadfence();
     *(volatile unsigned *)&me->epoch_ar = e + 1;
   }
@@ -268,9 +298,11 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(const double *__res
         if (p != rank) tab.gather[p][off + i] = v;
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&me->cnt_push, 1u) == gridDim.x - 1;
+  __syncthreads();  // the CTA's stores happen-before thread 0's system-scope fence (cumulative): one fence per CTA
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(&me->cnt_push, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   // the last CTA to finish its stores publishes the segment and waits for everyone else's
@@ -293,7 +325,7 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(const double *__res
 int comm_peer_alloc(Comm &c, size_t slot_doubles) {
   if (c.world == 1 || c.peer_region) return 0;
   if (c.world > COMM_PEER_MAX) return cfail("peer-memory collectives support at most 16 ranks");
-  const size_t bytes = PEER_CTRL_BYTES + sizeof(double) * 2 * (size_t)c.world * slot_doubles;
+  const size_t bytes = PEER_CTRL_BYTES + sizeof(LLLine) * 2 * (size_t)c.world * slot_doubles;
   CUC(cudaMalloc((void **)&c.peer_region, bytes));
   CUC(cudaMemset(c.peer_region, 0, bytes));
   CUC(cudaDeviceSynchronize());  // zeroed before any peer can learn the address

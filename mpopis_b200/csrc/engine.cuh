@@ -151,6 +151,12 @@ void launch_shrink_q_partial(const double *X, long long ld, int p, int n, const 
 void launch_cov_finalize(const double *Sraw, int p, const double *cnt_dev, int corrected, int method,
                          const double *qpart, int nq, double ridge, double *Sigma, double *lambda_out,
                          const int *stop, cudaStream_t s);
+// small_adapt.cu: sort + early stop + elite moments + shrinkage + Cholesky of one :cemppi iteration in ONE single-CTA launch
+// (K <= 512, m <= 128, cs <= 112: the reference's own sizes). Returns 0 when the sizes are not covered.
+int launch_ce_small_adapt(const double *costs, int K, int m, int early_stop, const double *E, long long ldk, int n,
+                          int method, double ridge, unsigned long long *keys_out, int *order_out, double *mu_out,
+                          double *U_cur, double *sums_out, double *Sigma, double *Lt, double *lambda_out, int *info, int tag,
+                          int *stop_flag, cudaStream_t s);
 // single-CTA fusion of the whole moment chain for n <= MOMENTS_SMALL_MAX columns (single GPU)
 constexpr int MOMENTS_SMALL_MAX = 512;
 void launch_moments_small(const double *X, long long ld, int p, int n, const double *w, const int *cols, int want_cov,

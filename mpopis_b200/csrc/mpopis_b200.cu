@@ -103,6 +103,7 @@ struct mpopis_handle {
   bool graph_enabled = true, capturing = false;
   long long graph_launches = 0;
   unsigned *d_step = nullptr;
+  bool Lt_ready = false, small_fused = true;  // small_adapt.cu formed the next iteration's factor already ("ce_small_fused")
   bool use_select = false, cov_pending = false, fuse_cov = true;  // fuse_cov: cov_finalize folded into the Cholesky kernel  // :cemppi: select.cu path (sharded, or K above the single-CTA sort)
   long long *d_env_t = nullptr, *d_warp_cycles = nullptr;  // d_warp_cycles: "rollout_profile" option
   unsigned long long *d_keys_a = nullptr, *d_keys_b = nullptr;
@@ -438,6 +439,7 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
   if (pol == MPOPIS_POLICY_PMCMPPI && N > 1 && Z_host && !u_host)
     return fail(MPOPIS_ERR_BAD_ARG, "pmcmppi with injected noise needs resample_u");
   CU(record(h, h->ev[0]));
+  h->Lt_ready = false;
   h->marks.clear();
   mark(h, "begin");
   CU(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 2, st));  // stop, its (info is sticky until read)
@@ -458,14 +460,18 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
     // --- proposal factor L of Σ′ (POL:447; CMA samples from σ²Σ, POL:550-554) ---
     const bool cma_scaled = pol == MPOPIS_POLICY_CMAMPPI && N > 1;
     if ((adapt && n > 0) || cma_scaled) {
-      // ce_adapt leaves Σ′ un-finalised when the shrinkage + ridge can be folded into the factorisation (one launch)
-      if (!(h->cov_pending &&
-            launch_chol_cov(h->d_Sraw, cs, h->d_sums + cs, 0, h->cfg.sigma_est, h->d_Sraw + (size_t)cs * cs, 10e-9,
-                            h->d_Sigma, h->d_Lt, h->d_lambda, h->info(), n + 1, stop, st)))
-        launch_chol(adapt && n > 0 ? h->d_Sigma : h->d_Sigma0, cs, cma_scaled ? h->d_sigma : nullptr, h->d_Lt,
-                    h->d_cholW, h->info(), n + 1, stop, st);
-      h->cov_pending = false;
-      h->launches += 1;
+      if (h->Lt_ready) {
+        // the fused small-size adaptation (small_adapt.cu) has factored Σ′ already
+      } else {
+        // ce_adapt leaves Σ′ un-finalised when the shrinkage + ridge can be folded into the factorisation (one launch)
+        if (!(h->cov_pending &&
+              launch_chol_cov(h->d_Sraw, cs, h->d_sums + cs, 0, h->cfg.sigma_est, h->d_Sraw + (size_t)cs * cs, 10e-9,
+                              h->d_Sigma, h->d_Lt, h->d_lambda, h->info(), n + 1, stop, st)))
+          launch_chol(adapt && n > 0 ? h->d_Sigma : h->d_Sigma0, cs, cma_scaled ? h->d_sigma : nullptr, h->d_Lt,
+                      h->d_cholW, h->info(), n + 1, stop, st);
+        h->launches += 1;
+      }
+      h->cov_pending = false, h->Lt_ready = false;
       Lt = h->d_Lt;
       if (n > 0) bs = cs;
     }
@@ -536,6 +542,15 @@ int plan_core(mpopis_t *h, const double *Z_host, const double *u_host) {
         const int m = h->m_elite;
         if (pol == MPOPIS_POLICY_CEMPPI && h->use_select) {  // selection instead of a sort (select.cu)
           if (int rc = ce_adapt(h)) return rc;
+          break;
+        }
+        if (pol == MPOPIS_POLICY_CEMPPI && h->world == 1 && h->small_fused && h->moments_small &&
+            launch_ce_small_adapt(h->d_costs, K, m, h->cfg.early_stop, h->d_E, h->ldk, cs, h->cfg.sigma_est, 10e-9,
+                                  h->d_keys_a, h->d_order, h->d_mu, h->d_U_cur, h->d_sums, h->d_Sigma, h->d_Lt, h->d_lambda,
+                                  h->info(), n + 2, stop, st)) {
+          h->Lt_ready = true;  // the factor of iteration n + 1 (failure tag n + 2, as launch_chol would report it)
+          h->launches += 1;
+          mark(h, "adapt.small");
           break;
         }
         {  // order = sortperm(costs) + the elite early-stop test (POL:455-461, 563-569)
@@ -1227,6 +1242,8 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     h->select_cluster = value != 0.0;
   } else if (!strcmp(key, "rollout_spin")) {
     h->rollout_spin = value < 0 ? -1 : (value != 0.0);
+  } else if (!strcmp(key, "ce_small_fused")) {
+    h->small_fused = value != 0.0;
   } else if (!strcmp(key, "fuse_cov")) {
     h->fuse_cov = value != 0.0;
   } else
@@ -1239,6 +1256,7 @@ int mpopis_b200_get_option(mpopis_t *h, const char *key, double *value_out) {
   if (!strcmp(key, "rollout_variant")) *value_out = h->rollout_variant;
   else if (!strcmp(key, "rollout_variant_used")) *value_out = h->rollout_variant_used;  // of the latest launch (6 resolved)
   else if (!strcmp(key, "comm_peer")) *value_out = h->comm.peer;
+  else if (!strcmp(key, "ce_small_fused")) *value_out = h->small_fused;
   else if (!strcmp(key, "rollout_block")) *value_out = h->rollout_block;
   else if (!strcmp(key, "rollout_stage")) *value_out = h->rollout_stage;
   else if (!strcmp(key, "moments_small")) *value_out = h->moments_small;
