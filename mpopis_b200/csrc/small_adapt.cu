@@ -98,18 +98,19 @@ __global__ void __launch_bounds__(256) ce_small_adapt_kernel(
     if (s_stop) return;
   }
 
-  // ---- 3. elite columns, mean, pol.U += μ′, centring: one warp per row, lanes over the elites ----
+  // ---- 3. elite columns (all n·m gathered loads in flight at once), then per row: mean, pol.U += μ′, centring ----
   const double cnt = (double)m, inv = 1.0 / cnt;
-  for (int r = wid; r < n; r += 8) {
+  for (int e = threadIdx.x; e < n * m; e += 256) {
+    const int r = e / m, s = e - r * m;
+    Xs[r * pitch + s] = E[(size_t)r * ldk + sv[s]];
+  }
+  __syncthreads();
+  for (int r = wid; r < n; r += 8) {  // one warp per row, lanes over the elites
     double a = 0.0;
-    for (int s = lane; s < m; s += 32) {
-      const double x = E[(size_t)r * ldk + sv[s]];
-      Xs[r * pitch + s] = x;
-      a = fma(1.0, x, a);
-    }
+    for (int s = lane; s < m; s += 32) a = fma(1.0, Xs[r * pitch + s], a);
     a = sa_warp_sum(a);
     const double mean = a / cnt;
-    for (int s = lane; s < m; s += 32) Xs[r * pitch + s] -= mean;  // each lane re-reads what it wrote itself
+    for (int s = lane; s < m; s += 32) Xs[r * pitch + s] -= mean;
     if (lane == 0) {
       if (mu_out) mu_out[r] = mean;
       sums_out[r] = a;

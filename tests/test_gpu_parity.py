@@ -457,6 +457,69 @@ def test_single_cta_moment_chain_equals_the_kernel_chain(gpu_bound, policy, sigm
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("envname,K,T", [("car", 150, 50), ("car", 500, 50), ("car", 64, 7), ("mc", 20, 15), ("mc", 300, 15)])
+@pytest.mark.parametrize("sigma_est", ["ss", "lw", "rblw", "oas", "mle"])
+def test_fused_small_adaptation_equals_the_kernel_chain_and_the_oracle(gpu_bound, orc, envname, K, T, sigma_est):
+    """The reference's own sizes (K = 150, cs = 100; MountainCar K = 20, cs = 15) run sort + early stop + elite moments +
+    shrinkage + Cholesky of one :cemppi iteration as ONE single-CTA launch (csrc/small_adapt.cu); "ce_small_fused" = 0
+    restores the kernel chain. Same iterations, proposal, λ̂ and control as the chain — and as the oracle."""
+    env = make_env(envname)
+    N = 5
+    rng = np.random.Generator(np.random.Philox(key=K + T))
+    cpu = configure(orc.engine(nthreads=4, **engine_kwargs("cemppi", env, K, T, N, sigma_est=sigma_est)), env, "cemppi")
+    Z = rng.standard_normal((cpu.cs, K, N))
+    U0 = rng.uniform(-0.1, 0.1, cpu.cs)
+    st = synthetic_states()[2] if envname == "car" else env.state
+    out = []
+    for flag in (1, 0):
+        g = configure(Engine(gpu_bound, **engine_kwargs("cemppi", env, K, T, N, sigma_est=sigma_est)), env, "cemppi")
+        g.set_option("ce_small_fused", flag)
+        assert int(g.get_option("ce_small_fused")) == flag
+        ctrl, U2, its = g.plan(st, 0, U0, Z=Z)
+        S, Ul = g.fetch_proposal()
+        out.append((ctrl, U2, its, S, Ul, g.last_shrinkage(), g.launch_count()))
+        g.close()
+    a, b = out
+    assert a[2] == b[2] and a[6] < b[6]  # same iterations, fewer launches
+    np.testing.assert_allclose(a[3], b[3], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(a[4], b[4], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(a[5], b[5], rtol=1e-9, atol=1e-12)
+    cc, uc, ic = cpu.plan(st, 0, U0, Z=Z)
+    Sc, Uc = cpu.fetch_proposal()
+    assert a[2] == ic
+    np.testing.assert_allclose(a[0], cc, rtol=1e-5, atol=1e-8)   # north-star tolerance
+    np.testing.assert_allclose(a[1], uc, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(a[3], Sc, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(a[5], cpu.last_shrinkage(), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_fused_small_adaptation_early_stop_and_failure(gpu_bound):
+    """Zero noise -> identical elite costs -> the fused kernel raises the stop flag and leaves pol.U / Σ′ untouched (POL:458-461);
+    a Σ′ that is not positive definite surfaces as the reference's PosDefException with the AIS iteration in the message."""
+    from mpopis_b200.engine import EngineError
+    env = make_env("car")
+    K, T, N = 150, 10, 5
+    res = []
+    for flag in (1, 0):
+        g = configure(Engine(gpu_bound, **engine_kwargs("cemppi", env, K, T, N, sigma_est="mle")), env, "cemppi")
+        g.set_option("ce_small_fused", flag)
+        res.append(g.plan(env.state, 0, np.full(g.cs, 0.05), Z=np.zeros((g.cs, K, N))))
+        g.close()
+    assert res[0][2] == res[1][2] == 1
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    # rank-deficient scatter matrix (every elite identical in all but one coordinate) with :mle and NaN noise -> NaN pivot
+    g = configure(Engine(gpu_bound, **engine_kwargs("cemppi", env, K, T, N, sigma_est="mle")), env, "cemppi")
+    Z = np.random.default_rng(3).standard_normal((g.cs, K, N))
+    Z[0, :, 0] = np.nan
+    with pytest.raises(EngineError, match="PosDefException.*AIS iteration 2"):
+        g.plan(env.state, 0, np.zeros(g.cs), Z=Z)
+    g.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n_cars,K", [(1, 2050), (1, 70), (2, 333), (3, 96), (4, 64)])
 def test_tma_staged_noise_equals_register_prefetch(gpu_bound, n_cars, K):
     """"rollout_stage" = 1 brings the noise tile of every warp into shared memory with TMA bulk copies (per-warp ring,
