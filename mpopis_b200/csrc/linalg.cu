@@ -6,6 +6,7 @@
 //             the reference only ever uses inside γ U_origᵀ Σ⁻¹ (V − U_orig), POL:272).
 // cs is 15..300 for the reference's configs, so these are single-CTA latency kernels; every rank of
 // a sharded policy runs them redundantly on bit-identical inputs.
+#include "chol_tile.cuh"
 #include "engine.cuh"
 
 namespace mpopis {
@@ -70,8 +71,7 @@ __global__ void __launch_bounds__(256) chol_reg_kernel(const double *__restrict_
                                                         double *__restrict__ Lt, int *info, int tag,
                                                         const int *stop) {
   if (stop && *stop) return;
-  __shared__ double col[2][16 * R];
-  __shared__ double dg[16 * R];
+  __shared__ CholTileSmem<R> sm;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const double sc = sigma_dev ? (*sigma_dev) * (*sigma_dev) : 1.0;
   double w[R][R];
@@ -82,66 +82,17 @@ __global__ void __launch_bounds__(256) chol_reg_kernel(const double *__restrict_
       const int i = ty + 16 * a, k = tx + 16 * b;
       w[a][b] = (i < n && k <= i) ? sc * A[(size_t)i * n + k] : 0.0;  // A symmetric: row-major == column-major
     }
-  bool failed = false;
-  // The pivot block index jb is a compile-time constant inside each phase, so the register blocks strictly
-  // below/right of the pivot block are updated with un-predicated FMAs; only the pivot block row/column
-  // and the diagonal blocks need lane predicates. Rows/columns >= n hold zeros and stay zero.
-#pragma unroll
-  for (int jb = 0; jb < R; ++jb) {
-    for (int jt = 0; jt < 16; ++jt) {
-      const int j = 16 * jb + jt, pb = jt & 1;
-      if (j >= n || failed) break;
-      if (tx == jt) {  // publish column j (final: every update of the steps < j has been applied)
-#pragma unroll
-        for (int a = jb; a < R; ++a) col[pb][ty + 16 * a] = w[a][jb];
-      }
-      __syncthreads();
-      const double d = col[pb][j];
-      if (!(d > 0.0)) {  // uniform across the CTA
-        failed = true;
-        break;
-      }
-      if (threadIdx.x == 0) dg[j] = d;
-      double inv_d;
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv_d) : "d"(d));
-      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
-      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
-      double ck[R];
-#pragma unroll
-      for (int b = jb; b < R; ++b) ck[b] = col[pb][tx + 16 * b];
-#pragma unroll
-      for (int a = jb; a < R; ++a) {
-        double ci = col[pb][ty + 16 * a] * inv_d;
-        if (a == jb && ty <= jt) ci = 0.0;  // rows at or above the pivot
-#pragma unroll
-        for (int b = jb; b <= a; ++b) {
-          bool on = true;
-          if (b == jb) on = tx > jt;             // columns right of the pivot only
-          if (b == a) on = on && (tx <= ty);      // lower triangle of a diagonal block
-          if (on) w[a][b] = fma(-ci, ck[b], w[a][b]);
-        }
-      }
-    }
-  }
-  if (failed) {
+  if (!chol_tile_factor<R>(w, n, sm, tx, ty)) {
     if (threadIdx.x == 0) atomicCAS(info, 0, tag);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
-  __syncthreads();
 #pragma unroll
   for (int a = 0; a < R; ++a)
 #pragma unroll
     for (int b = 0; b < R; ++b) {
       const int i = ty + 16 * a, k = tx + 16 * b;
-      if (i < n && k < n) {
-        double v = 0.0;
-        if (k <= i) {
-          const double r = sqrt(dg[k]);
-          v = k == i ? r : w[a][b] / r;
-        }
-        Lt[(size_t)i * n + k] = v;
-      }
+      if (i < n && k < n) Lt[(size_t)i * n + k] = k <= i ? chol_tile_entry<R>(w, sm, a, b, i, k) : 0.0;
     }
 }
 
@@ -169,10 +120,10 @@ __global__ void __launch_bounds__(256) chol_cov_kernel(const double *__restrict_
                                                         double *__restrict__ Lt, double *lambda_out, int *info, int tag,
                                                         const int *stop) {
   if (stop && *stop) return;
-  __shared__ double col[2][16 * R];
-  __shared__ double dg[16 * R];
+  __shared__ CholTileSmem<R> sm;
   __shared__ double dinv[16 * R];
   __shared__ double red[8];
+  double *dg = sm.dg;  // diag(S) until the factorisation takes the array over
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const double cnt = *cnt_dev, inv = 1.0 / (cnt - (corrected ? 1.0 : 0.0));
   double w[R][R];
@@ -242,63 +193,17 @@ __global__ void __launch_bounds__(256) chol_cov_kernel(const double *__restrict_
     }
   if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
   __syncthreads();
-  bool failed = false;
-#pragma unroll
-  for (int jb = 0; jb < R; ++jb) {  // identical to chol_reg_kernel from here on
-    for (int jt = 0; jt < 16; ++jt) {
-      const int j = 16 * jb + jt, pb = jt & 1;
-      if (j >= n || failed) break;
-      if (tx == jt) {
-#pragma unroll
-        for (int a = jb; a < R; ++a) col[pb][ty + 16 * a] = w[a][jb];
-      }
-      __syncthreads();
-      const double d = col[pb][j];
-      if (!(d > 0.0)) {
-        failed = true;
-        break;
-      }
-      if (threadIdx.x == 0) dg[j] = d;
-      double inv_d;
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv_d) : "d"(d));
-      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
-      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
-      double ck[R];
-#pragma unroll
-      for (int b = jb; b < R; ++b) ck[b] = col[pb][tx + 16 * b];
-#pragma unroll
-      for (int a = jb; a < R; ++a) {
-        double ci = col[pb][ty + 16 * a] * inv_d;
-        if (a == jb && ty <= jt) ci = 0.0;
-#pragma unroll
-        for (int b = jb; b <= a; ++b) {
-          bool on = true;
-          if (b == jb) on = tx > jt;
-          if (b == a) on = on && (tx <= ty);
-          if (on) w[a][b] = fma(-ci, ck[b], w[a][b]);
-        }
-      }
-    }
-  }
-  if (failed) {
+  if (!chol_tile_factor<R>(w, n, sm, tx, ty)) {
     if (threadIdx.x == 0) atomicCAS(info, 0, tag);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
-  __syncthreads();
 #pragma unroll
   for (int a = 0; a < R; ++a)
 #pragma unroll
     for (int b = 0; b < R; ++b) {
       const int i = ty + 16 * a, k = tx + 16 * b;
-      if (i < n && k < n) {
-        double v = 0.0;
-        if (k <= i) {
-          const double r = sqrt(dg[k]);
-          v = k == i ? r : w[a][b] / r;
-        }
-        Lt[(size_t)i * n + k] = v;
-      }
+      if (i < n && k < n) Lt[(size_t)i * n + k] = k <= i ? chol_tile_entry<R>(w, sm, a, b, i, k) : 0.0;
     }
 }
 

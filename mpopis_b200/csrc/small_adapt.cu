@@ -15,6 +15,7 @@
 //   5. right-looking register-tiled Cholesky of Σ′ (identical to chol_cov_kernel) -> Lt
 // Same formulas and summation structure as moments_small_kernel + chol_cov_kernel; tests/test_gpu_parity.py pins the
 // control step against the oracle at these sizes, with the fused kernel on (default) and off ("ce_small_fused" = 0).
+#include "chol_tile.cuh"
 #include "engine.cuh"
 
 namespace mpopis {
@@ -55,8 +56,10 @@ __global__ void __launch_bounds__(256) ce_small_adapt_kernel(
   extern __shared__ double Xs[];  // [n][pitch]: the centred elite columns
   __shared__ unsigned long long sk[SA_MAXK];
   __shared__ int sv[SA_MAXK];
-  __shared__ double col[2][16 * R], dg[16 * R], dinv[16 * R], red[8];
+  __shared__ CholTileSmem<R> sm;
+  __shared__ double dinv[16 * R], red[8];
   __shared__ int s_stop;
+  double *dg = sm.dg;  // diag(S) until the factorisation takes the array over
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
@@ -218,64 +221,18 @@ __global__ void __launch_bounds__(256) ce_small_adapt_kernel(
   if (threadIdx.x == 0 && lambda_out) *lambda_out = lam;
   __syncthreads();
 
-  // ---- 5. Cholesky of Σ′ in the register tile (chol_reg_kernel, linalg.cu) ----
-  bool failed = false;
-#pragma unroll
-  for (int jb = 0; jb < R; ++jb) {
-    for (int jt = 0; jt < 16; ++jt) {
-      const int j = 16 * jb + jt, pb = jt & 1;
-      if (j >= n || failed) break;
-      if (tx == jt) {
-#pragma unroll
-        for (int a = jb; a < R; ++a) col[pb][ty + 16 * a] = w[a][jb];
-      }
-      __syncthreads();
-      const double d = col[pb][j];
-      if (!(d > 0.0)) {
-        failed = true;
-        break;
-      }
-      if (threadIdx.x == 0) dg[j] = d;
-      double inv_d;
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv_d) : "d"(d));
-      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
-      inv_d = fma(fma(-d, inv_d, 1.0), inv_d, inv_d);
-      double ck[R];
-#pragma unroll
-      for (int b = jb; b < R; ++b) ck[b] = col[pb][tx + 16 * b];
-#pragma unroll
-      for (int a = jb; a < R; ++a) {
-        double ci = col[pb][ty + 16 * a] * inv_d;
-        if (a == jb && ty <= jt) ci = 0.0;
-#pragma unroll
-        for (int b = jb; b <= a; ++b) {
-          bool on = true;
-          if (b == jb) on = tx > jt;
-          if (b == a) on = on && (tx <= ty);
-          if (on) w[a][b] = fma(-ci, ck[b], w[a][b]);
-        }
-      }
-    }
-  }
-  if (failed) {
+  // ---- 5. Cholesky of Σ′ in the register tile (chol_tile.cuh) ----
+  if (!chol_tile_factor<R>(w, n, sm, tx, ty)) {
     if (threadIdx.x == 0) atomicCAS(info, 0, tag);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
-  __syncthreads();
 #pragma unroll
   for (int a = 0; a < R; ++a)
 #pragma unroll
     for (int b = 0; b < R; ++b) {
       const int i = ty + 16 * a, k = tx + 16 * b;
-      if (i < n && k < n) {
-        double v = 0.0;
-        if (k <= i) {
-          const double r = sqrt(dg[k]);
-          v = k == i ? r : w[a][b] / r;
-        }
-        Lt[(size_t)i * n + k] = v;
-      }
+      if (i < n && k < n) Lt[(size_t)i * n + k] = k <= i ? chol_tile_entry<R>(w, sm, a, b, i, k) : 0.0;
     }
 }
 

@@ -190,10 +190,33 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
   out[i] = s;
 }
 
+// Few columns, many chunks (the shrinkage statistic: ONE column, K_loc/64 partials — 1024 at 65 536 samples per rank):
+// the kernel above would walk them with one thread, a serial chain of L2 loads that outlasted the scatter matrix it
+// runs beside (profiles/r2_multi_gpu.md). One CTA per column: 256 strided partial sums in chunk order, then a fixed
+// shared-memory tree (deterministic; the same order on every rank).
+__global__ void __launch_bounds__(256) reduce_partials_tall_kernel(const double *__restrict__ partial, int nchunks, int stride,
+                                                                    double *__restrict__ out, const int *stop) {
+  if (stop && *stop) return;
+  __shared__ double red[256];
+  const int i = blockIdx.x;
+  double s = 0.0;
+  for (int c = threadIdx.x; c < nchunks; c += 256) s += partial[(size_t)c * stride + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[i] = red[0];
+}
+
 // stride = row pitch of `partial` (0: n)
 void launch_reduce_partials(const double *partial, int nchunks, int n, double *out, const int *stop,
                             cudaStream_t s, int stride) {
-  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, nchunks, n, stride ? stride : n, out, stop);
+  if (n <= 4 && nchunks > 64)
+    reduce_partials_tall_kernel<<<n, 256, 0, s>>>(partial, nchunks, stride ? stride : n, out, stop);
+  else
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, nchunks, n, stride ? stride : n, out, stop);
 }
 
 // μ = sums[0:rows] / sums[rows]; optionally U += scale * μ  (pol.U = pol.U + vec(μ′), POL:365,465,...)
