@@ -18,7 +18,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libmpopis_b200.so"
 OBJ = PKG / "csrc" / "_obj"
 SOURCES = ["mpopis_b200.cu", "rollout.cu", "rollout_split.cu", "rollout_aux.cu", "sampling.cu", "stats.cu", "linalg.cu", "small_adapt.cu", "sort.cu", "select.cu", "comm.cu", "cma.cu"]
-HEADERS = [CSRC / "engine.cuh", CSRC / "comm.cuh", CSRC / "car_model.cuh", CSRC / "rollout_kernels.cuh", PKG.parent / "include" / "mpopis_b200.h"]
+HEADERS = [CSRC / "engine.cuh", CSRC / "comm.cuh", CSRC / "chol_tile.cuh", CSRC / "car_model.cuh", CSRC / "rollout_kernels.cuh", PKG.parent / "include" / "mpopis_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

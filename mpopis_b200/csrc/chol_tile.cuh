@@ -6,10 +6,12 @@
 // d_j = l_jj²; L is formed at the end as W[i][j] / sqrt(d_j). One barrier per column, the pivot column travels through a
 // double-buffered shared-memory vector. Round 2 (profiles/r2 notes: the kernel was 620 cycles per column, 105
 // instructions per warp, on a chain barrier -> LDS d -> DSETP/BRA -> MUFU.RCP64H -> 4 DFMA -> DMUL -> DFMA -> FSEL -> STS):
-//   * look-ahead reciprocal: during step j every thread updates its element of the NEXT pivot's diagonal block first and
+//   * look-ahead reciprocal: during step j every thread updates its element of the pivot's diagonal block first and
 //     starts 1/x on it in the same straight-line block (the compiler interleaves it with the bulk update); the thread that
 //     actually owns W[j+1][j+1] publishes (d, 1/d). After the barrier of step j + 1 the reciprocal is a shared-memory
-//     read — the MUFU + Newton chain and the positivity branch are off the critical path;
+//     read — the MUFU + Newton chain and the positivity branch are off the critical path (except once per 16 columns,
+//     where the next pivot sits in the next diagonal block and its owner inverts it after the bulk update: peeling that
+//     step would double a code footprint that already stalls on instruction fetch);
 //   * masks on operands instead of results: rows at or above the pivot get c_i = 0, columns at or left of it c_k = 0
 //     (an FMA with a zero factor leaves its accumulator bit-exact), replacing a DFMA + 2 FSEL per masked element. The
 //     strictly-upper entries of diagonal blocks then accumulate finite junk that nothing ever reads;
@@ -64,27 +66,29 @@ __device__ __forceinline__ bool chol_tile_factor(double (&w)[R][R], int n, CholT
       }
       if (ty <= jt) ci[jb] = 0.0;  // rows at or above the pivot
       if (tx <= jt) ck[jb] = 0.0;  // columns at or left of the pivot
-      // look-ahead: the next pivot lives in this diagonal block (jt < 15) or the next one; update that element first
-      // and start its reciprocal. Only the owner's value is the pivot; the others' are discarded.
+      // look-ahead: while the next pivot lives in this diagonal block (jt < 15) every thread updates its element of the
+      // block first and starts 1/x on it; only the owner's value is the pivot, the others' are discarded.
       const bool own = (tx == ((jt + 1) & 15)) && (ty == ((jt + 1) & 15)) && j + 1 < n;
-      auto step = [&](int s) {  // s: diagonal block of the next pivot (a compile-time constant after unrolling)
-        if (s < R) {
-          w[s][s] = fma(-ci[s], ck[s], w[s][s]);
-          const double dn = w[s][s];
-          const double rn = chol_rcp(dn);
-          if (own) {
-            sm.dg[j + 1] = dn, sm.pinv[pb ^ 1] = rn;
-            if (!(dn > 0.0)) sm.failed = 1;
-          }
+      w[jb][jb] = fma(-ci[jb], ck[jb], w[jb][jb]);
+      {
+        const double dn = w[jb][jb];
+        const double rn = chol_rcp(dn);
+        if (own && jt < 15) {
+          sm.dg[j + 1] = dn, sm.pinv[pb ^ 1] = rn;
+          if (!(dn > 0.0)) sm.failed = 1;
         }
+      }
 #pragma unroll
-        for (int a = jb; a < R; ++a)
+      for (int a = jb; a < R; ++a)
 #pragma unroll
-          for (int b = jb; b <= a; ++b)
-            if (!(a == s && b == s)) w[a][b] = fma(-ci[a], ck[b], w[a][b]);
-      };
-      if (jt < 15) step(jb);
-      else step(jb + 1);
+        for (int b = jb; b <= a; ++b)
+          if (!(a == jb && b == jb)) w[a][b] = fma(-ci[a], ck[b], w[a][b]);
+      // block boundary (once per 16 columns): the next pivot is element (0, 0) of the next diagonal block, final now
+      if (jt == 15 && jb + 1 < R && own) {
+        const double dn = w[jb + 1 < R ? jb + 1 : jb][jb + 1 < R ? jb + 1 : jb];
+        sm.dg[j + 1] = dn, sm.pinv[pb ^ 1] = chol_rcp(dn);
+        if (!(dn > 0.0)) sm.failed = 1;
+      }
     }
   }
   __syncthreads();
