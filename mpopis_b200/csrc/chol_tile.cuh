@@ -95,12 +95,23 @@ __device__ __forceinline__ bool chol_tile_factor(double (&w)[R][R], int n, CholT
   return sm.failed == 0;
 }
 
-// L[i][k] of the factored tile for the entry (a, b) this thread owns (k <= i)
+// l_kk = sqrt(d_k) and 1/l_kk once per column (into the free column buffers), so that forming L costs one multiply per
+// entry: l_ik = W[i][k]·(1/l_kk), the scaling LAPACK's dpotf2 applies (DSCAL by 1/a_jj). An IEEE square root and a
+// division per ENTRY were 49 + 49 inline expansions per thread — half of the kernel's static code (the kernels stall
+// mostly on instruction fetch: ncu `no_instruction`) and a quarter of its executed instructions.
+template <int R>
+__device__ __forceinline__ void chol_tile_finish(CholTileSmem<R> &sm, int n) {
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const double r = sqrt(sm.dg[k]);
+    sm.col[0][k] = r, sm.col[1][k] = 1.0 / r;
+  }
+  __syncthreads();
+}
+// L[i][k] of the factored tile for the entry (a, b) this thread owns (k <= i); after chol_tile_finish
 template <int R>
 __device__ __forceinline__ double chol_tile_entry(const double (&w)[R][R], const CholTileSmem<R> &sm, int a, int b, int i,
                                                   int k) {
-  const double r = sqrt(sm.dg[k]);
-  return k == i ? r : w[a][b] / r;
+  return k == i ? sm.col[0][k] : w[a][b] * sm.col[1][k];
 }
 
 }  // namespace mpopis

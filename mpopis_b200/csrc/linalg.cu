@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256) chol_reg_kernel(const double *__restrict_
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
+  chol_tile_finish<R>(sm, n);
 #pragma unroll
   for (int a = 0; a < R; ++a)
 #pragma unroll
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(256) chol_cov_kernel(const double *__restrict_
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
+  chol_tile_finish<R>(sm, n);
 #pragma unroll
   for (int a = 0; a < R; ++a)
 #pragma unroll

@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(256) ce_small_adapt_kernel(
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
+  chol_tile_finish<R>(sm, n);
 #pragma unroll
   for (int a = 0; a < R; ++a)
 #pragma unroll
