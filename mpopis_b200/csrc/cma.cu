@@ -37,7 +37,7 @@ __device__ __forceinline__ double block_sum(double v, double *red /* >= 33 doubl
 }
 
 // one 32x32 tile of C = alpha * A * B + beta * I  (row-major n x n), 256 threads, 2x2 per thread
-__device__ __forceinline__ void gemm_tile(const double *__restrict__ A, const double *__restrict__ B, int n,
+__device__ __forceinline__ double gemm_tile(const double *__restrict__ A, const double *__restrict__ B, int n,
                                           int ti, int tj, double alpha, double beta, double *__restrict__ C,
                                           double (*As)[33], double (*Bs)[33]) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -59,16 +59,23 @@ __device__ __forceinline__ void gemm_tile(const double *__restrict__ A, const do
     }
   }
   const int i = i0 + 2 * ty, j = j0 + 2 * tx;
-  if (i < n && j < n) C[(size_t)i * n + j] = alpha * c00 + (i == j ? beta : 0.0);
-  if (i < n && j + 1 < n) C[(size_t)i * n + j + 1] = alpha * c01 + (i == j + 1 ? beta : 0.0);
-  if (i + 1 < n && j < n) C[(size_t)(i + 1) * n + j] = alpha * c10 + (i + 1 == j ? beta : 0.0);
-  if (i + 1 < n && j + 1 < n) C[(size_t)(i + 1) * n + j + 1] = alpha * c11 + (i == j ? beta : 0.0);
+  double res = 0.0;  // this thread's share of ‖C − I‖_F²
+  auto put = [&](int ii, int jj, double acc) {
+    if (ii < n && jj < n) {
+      const double v = alpha * acc + (ii == jj ? beta : 0.0);
+      C[(size_t)ii * n + jj] = v;
+      const double d = v - (ii == jj ? 1.0 : 0.0);
+      res = fma(d, d, res);
+    }
+  };
+  put(i, j, c00), put(i, j + 1, c01), put(i + 1, j, c10), put(i + 1, j + 1, c11);
+  return res;
 }
 }  // namespace
 
 constexpr int NS_MAX_IT = 100;
 
-// ws: 5 n² doubles (Y, Z, T, Y2, Z2). Launched cooperatively with <= (#tiles) CTAs of 256 threads.
+// ws: 5 n² doubles (Y, Z, T, Y2, Z2) + one per 32 x 32 tile. Launched cooperatively with <= (#tiles) CTAs of 256 threads.
 __global__ void __launch_bounds__(256) inv_sqrt_ns_kernel(const double *__restrict__ A, int n,
                                                            double *__restrict__ Cout, double *__restrict__ ws,
                                                            int *info, int tag, const int *stop) {
@@ -76,7 +83,7 @@ __global__ void __launch_bounds__(256) inv_sqrt_ns_kernel(const double *__restri
   cg::grid_group grid = cg::this_grid();
   __shared__ double As[32][33], Bs[32][33], red[33];
   const size_t nn = (size_t)n * n;
-  double *Y = ws, *Z = ws + nn, *T = ws + 2 * nn, *Y2 = ws + 3 * nn, *Z2 = ws + 4 * nn;
+  double *Y = ws, *Z = ws + nn, *T = ws + 2 * nn, *Y2 = ws + 3 * nn, *Z2 = ws + 4 * nn, *tile_res = ws + 5 * nn;
   const int nt = (n + 31) / 32, ntiles = nt * nt;
   // c = ‖A‖_F, computed redundantly (and identically) by every CTA
   double s = 0.0;
@@ -89,13 +96,15 @@ __global__ void __launch_bounds__(256) inv_sqrt_ns_kernel(const double *__restri
   grid.sync();
   bool ok = false;
   for (int it = 0; it < NS_MAX_IT; ++it) {
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) gemm_tile(Z, Y, n, t / nt, t % nt, -0.5, 1.5, T, As, Bs);
-    grid.sync();
-    double r = 0.0;  // ‖T − I‖_F², identical in every CTA
-    for (size_t e = threadIdx.x; e < nn; e += blockDim.x) {
-      const double d = T[e] - ((e / n == e % n) ? 1.0 : 0.0);
-      r = fma(d, d, r);
+    // ‖T − I‖_F² per tile while the tile is in registers (every CTA used to re-read all n² entries of T for it: ~10 µs of
+    // the ~75 µs an iteration took at n = 300), summed in tile order after the barrier: identical in every CTA
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const double part = block_sum(gemm_tile(Z, Y, n, t / nt, t % nt, -0.5, 1.5, T, As, Bs), red);
+      if (threadIdx.x == 0) tile_res[t] = part;
     }
+    grid.sync();
+    double r = 0.0;
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) r += __ldcg(tile_res + t);
     r = block_sum(r, red);
     if (!(r == r)) break;                           // NaN: diverged
     if (r < 1e-28 * (double)n) { ok = true; break; }  // ‖T − I‖_F < 1e-14 sqrt(n)

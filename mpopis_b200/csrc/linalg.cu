@@ -223,6 +223,126 @@ int launch_chol_cov(const double *Sraw, int n, const double *cnt_dev, int correc
   return 1;
 }
 
+// Blocked Cholesky for 160 < n <= 430 (MultiCarRacing: cs = 200 / 300), still ONE CTA — the matrix (720 KB at n = 300)
+// fits neither the register tile nor shared memory, and the unblocked kernel above walked it in L2 at 5.8 µs per column
+// (1.75 ms per factorisation at n = 300: 42 % of a 3-car :cmamppi control step, profiles/r2 notes). Left to right in
+// panels of 64 columns, working in place in Lt:
+//   1. the 64 x 64 diagonal block is factored in the register tile (chol_tile.cuh, R = 4) and kept in shared memory;
+//   2. the rows below solve X·L_bbᵀ = A_panel, ONE THREAD PER ROW, 16 entries at a time in registers (L_bb entries are
+//      warp-uniform shared-memory broadcasts, a thread re-reads only its own row of the panel);
+//   3. the trailing matrix gets A −= X·Xᵀ from the panel in shared memory: 64 x 64 tiles, a 4 x 4 register tile per
+//      thread with rows/columns strided by 16 (conflict-free with the odd pitch).
+// ≈ n³/3 FMAs on one SM = 70 µs of DFMA issue at n = 300, plus five 64-column tile factorisations.
+constexpr int CB_NB = 64, CB_P = 65, CB_MAX_N = 430;
+
+__global__ void __launch_bounds__(256) chol_blocked_kernel(const double *__restrict__ A, int n, const double *sigma_dev,
+                                                            double *__restrict__ Lt, int *info, int tag, const int *stop) {
+  if (stop && *stop) return;
+  extern __shared__ double cb[];  // Lbb[64][65] | X[n − 64][65]
+  __shared__ CholTileSmem<4> sm;
+  double *Lbb = cb, *X = cb + CB_NB * CB_P;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const double sc = sigma_dev ? (*sigma_dev) * (*sigma_dev) : 1.0;
+  for (int e = threadIdx.x; e < n * n; e += 256) {
+    const int i = e / n, k = e - i * n;
+    Lt[e] = k <= i ? sc * A[e] : 0.0;
+  }
+  __syncthreads();
+  bool ok = true;
+  for (int c0 = 0; c0 < n; c0 += CB_NB) {
+    const int nb = min(CB_NB, n - c0), m = n - c0 - nb;
+    // ---- 1. diagonal block ----
+    double w[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = ty + 16 * a, k = tx + 16 * b;
+        w[a][b] = (i < nb && k <= i) ? Lt[(size_t)(c0 + i) * n + c0 + k] : 0.0;
+      }
+    if (!chol_tile_factor<4>(w, nb, sm, tx, ty)) {  // block-uniform
+      ok = false;
+      break;
+    }
+    chol_tile_finish<4>(sm, nb);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = ty + 16 * a, k = tx + 16 * b;
+        const double v = (i < nb && k <= i) ? chol_tile_entry<4>(w, sm, a, b, i, k) : 0.0;
+        Lbb[i * CB_P + k] = v;
+        if (i < nb && k <= i) Lt[(size_t)(c0 + i) * n + c0 + k] = v;
+      }
+    __syncthreads();
+    if (m == 0) break;  // (only the last panel can be narrower than 64, and it has no rows below)
+    // ---- 2. rows below: X L_bbᵀ = A_panel, one thread per row ----
+    for (int r = threadIdx.x; r < m; r += 256) {
+      double *row = Lt + (size_t)(c0 + nb + r) * n + c0;
+      double *xr = X + (size_t)r * CB_P;
+      for (int jb = 0; jb < CB_NB; jb += 16) {  // 16 entries at a time in registers
+        double acc[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t] = row[jb + t];
+        for (int k = 0; k < jb; ++k) {  // the entries already solved (read back from this thread's own panel row)
+          const double xk = xr[k];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) acc[t] = fma(-xk, Lbb[(jb + t) * CB_P + k], acc[t]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double xj = acc[j] * sm.col[1][jb + j];  // 1 / l_jj
+          acc[j] = xj;
+#pragma unroll
+          for (int t = j + 1; t < 16; ++t) acc[t] = fma(-xj, Lbb[(jb + t) * CB_P + jb + j], acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) row[jb + t] = acc[t], xr[jb + t] = acc[t];
+      }
+    }
+    __syncthreads();
+    // ---- 3. trailing update A −= X Xᵀ (lower tiles) ----
+    const int nt = (m + 63) / 64;
+    for (int ti = 0; ti < nt; ++ti)
+      for (int tj = 0; tj <= ti; ++tj) {
+        double c[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) c[a][b] = 0.0;
+        const double *Xi = X + (size_t)(ti * 64 + ty) * CB_P, *Xj = X + (size_t)(tj * 64 + tx) * CB_P;
+        bool vi[4], vj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) vi[a] = ti * 64 + ty + 16 * a < m, vj[a] = tj * 64 + tx + 16 * a < m;
+#pragma unroll 4
+        for (int k = 0; k < CB_NB; ++k) {
+          double xi[4], xj[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            xi[a] = vi[a] ? Xi[(size_t)16 * a * CB_P + k] : 0.0;
+            xj[a] = vj[a] ? Xj[(size_t)16 * a * CB_P + k] : 0.0;
+          }
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) c[a][b] = fma(xi[a], xj[b], c[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int i = ti * 64 + ty + 16 * a, j = tj * 64 + tx + 16 * b;
+            if (i < m && j <= i) Lt[(size_t)(c0 + nb + i) * n + c0 + nb + j] -= c[a][b];
+          }
+      }
+    __syncthreads();
+  }
+  if (!ok) {
+    if (threadIdx.x == 0) atomicCAS(info, 0, tag);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) Lt[e] = __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
 constexpr int CHOL_SMEM_N = 160;  // 160 · 161 · 8 B = 201 KB
 
 // Wglobal: scratch of n (n|1) doubles, used when n > CHOL_SMEM_N
@@ -232,6 +352,12 @@ void launch_chol(const double *A, int n, const double *sigma_dev, double *Lt, do
   if (n <= 64) return (void)chol_reg_kernel<4><<<1, 256, 0, s>>>(A, n, sigma_dev, Lt, info, tag, stop);
   if (n <= 112) return (void)chol_reg_kernel<7><<<1, 256, 0, s>>>(A, n, sigma_dev, Lt, info, tag, stop);
   if (n <= 160) return (void)chol_reg_kernel<10><<<1, 256, 0, s>>>(A, n, sigma_dev, Lt, info, tag, stop);
+  if (n <= CB_MAX_N) {
+    const size_t smem = sizeof(double) * (size_t)n * CB_P;
+    cudaFuncSetAttribute(chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(double) * CB_MAX_N * CB_P));  // per device: set on every launch
+    return (void)chol_blocked_kernel<<<1, 256, smem, s>>>(A, n, sigma_dev, Lt, info, tag, stop);
+  }
   const int use_smem = n <= CHOL_SMEM_N;
   const size_t smem = use_smem ? sizeof(double) * n * (n | 1) : 0;
   cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

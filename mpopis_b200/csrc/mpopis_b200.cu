@@ -948,7 +948,7 @@ int mpopis_b200_create(const mpopis_cfg_t *cfg, mpopis_t **out) {
     TRY(dalloc(&h->d_psig, cs));
     TRY(dalloc(&h->d_pSig, cs));
     TRY(dalloc(&h->d_C, cs * cs));
-    TRY(dalloc(&h->d_ns, 5 * cs * cs + 8));
+    TRY(dalloc(&h->d_ns, 5 * cs * cs + ((cs + 31) / 32) * ((cs + 31) / 32) + 8));
   }
   if (cfg->log_trajectories) TRY(dalloc(&h->d_traj, Kloc * (size_t)h->T * h->ss));
   if (cfg->env == MPOPIS_ENV_EXTERNAL) {
@@ -1629,7 +1629,7 @@ int mpopis_b200_inv_sqrt(mpopis_t *h, const double *A, int64_t n, double *C_out)
   const size_t nn = (size_t)n * n;
   if (int rc = dA.alloc(nn)) return rc;
   if (int rc = dC.alloc(nn)) return rc;
-  if (int rc = dws.alloc(5 * nn + 8)) return rc;
+  if (int rc = dws.alloc(5 * nn + (size_t)((n + 31) / 32) * ((n + 31) / 32) + 8)) return rc;
   if (int rc = dinfo.alloc(1)) return rc;
   CU(cudaMemcpyAsync(dA, A, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
   cudaError_t e = (cudaError_t)launch_inv_sqrt(dA, (int)n, dC, dws, dinfo, 1, nullptr, h->coop_max, h->st);

@@ -221,12 +221,22 @@ def test_linear_algebra_vs_numpy(gpu_bound):
     env = make_env("car")
     g = configure(Engine(gpu_bound, **engine_kwargs("gmppi", env, 32, 50)), env, "gmppi")
     rng = np.random.default_rng(1)
-    for n in (15, 100, 300):  # cs of BASELINE configs 1, 2, 4 (300 exercises the global-memory Cholesky)
+    # cs of BASELINE configs 1, 2, 4; the register-tile sizes (16, 64, 112, 160); the blocked kernel (161..430: full and
+    # partial last panels, one row / one column below a panel) and the unblocked fallback beyond it
+    for n in (1, 2, 15, 16, 17, 64, 100, 112, 113, 160, 161, 192, 193, 200, 257, 300, 430, 431):
         A = rng.standard_normal((n, 2 * n))
         S = A @ A.T / (2 * n) + 0.05 * np.eye(n)
-        np.testing.assert_allclose(g.cholesky(S), np.linalg.cholesky(S), rtol=1e-10, atol=1e-12)
-        C = g.inv_sqrt(S)
-        np.testing.assert_allclose(C @ C @ S, np.eye(n), atol=1e-9)
+        np.testing.assert_allclose(g.cholesky(S), np.linalg.cholesky(S), rtol=1e-10, atol=1e-12, err_msg=f"n={n}")
+        if n in (15, 100, 300):
+            C = g.inv_sqrt(S)
+            np.testing.assert_allclose(C @ C @ S, np.eye(n), atol=1e-9)
+    for n in (200, 300):  # a failing pivot in the first and in a later panel of the blocked kernel
+        for bad in (3, n - 5):
+            S = np.eye(n)
+            S[bad, bad] = -1.0
+            with pytest.raises(EngineError) as ei:
+                g.cholesky(S)
+            assert ei.value.code == -4
     with pytest.raises(EngineError) as ei:
         g.cholesky(np.diag([1.0, -1.0, 2.0]))
     assert ei.value.code == -4  # PosDefException
