@@ -752,11 +752,19 @@ int launch_ce_select(const double *costs, int Ktot, int m, long long k0, int Klo
     return (int)cudaLaunchKernelEx(&cfg, ce_select_cluster_kernel, costs, Ktot, m, k0, Kloc, early_stop, bmin, bmax, nb_cap,
                                    eidx, m_loc, tau_out, stop_flag, stop);
   }
-  // Small K: 256-thread CTAs of 1024 keys. Large K (sharded policies select on the GATHERED costs, K = 2^19 .. 2^20):
-  // 1024-thread CTAs of 8192 keys — the dense radix pass flushes up to 2048 bins per CTA with global atomics and every
-  // phase ends in a grid barrier, so fewer, fatter CTAs (8-GPU trace: 170-214 µs per iteration with 512-592 small CTAs).
-  const bool big = Ktot > 131072;
-  int grid = big ? (Ktot + 8191) / 8192 : (Ktot + 1023) / 1024;
+  // Small K: 256-thread CTAs of 1024 keys. Large K (sharded policies select on the GATHERED costs, K = 2^18 .. 2^20):
+  // 1024-thread CTAs, at most one per SM — the dense radix pass flushes up to 2048 bins per CTA with global atomics and
+  // every phase ends in a grid barrier, so fewer, fatter CTAs (8-GPU trace: 170-214 µs per iteration with 512-592 small
+  // CTAs). Keys per CTA, select phase of a control step (9 selections) on one GPU, profiles/r2_multi_gpu.md:
+  //   K = 262 144: 8192 -> 0.61 ms, 4096 -> 0.46, 2048 -> 0.38 (256-thread path: 0.38);  K = 524 288: 0.61 / 0.45 / 0.46 (0.48)
+  static int big_thr = -1, big_keys = 2048;  // MPOPIS_SELECT_BIG / MPOPIS_SELECT_KEYS: A/B of the CTA shape (tools)
+  if (big_thr < 0) {
+    const char *e = getenv("MPOPIS_SELECT_BIG"), *k = getenv("MPOPIS_SELECT_KEYS");
+    big_thr = e ? atoi(e) : 131072;
+    if (k && atoi(k) >= 1024) big_keys = atoi(k);
+  }
+  const bool big = Ktot > big_thr;
+  int grid = big ? (Ktot + big_keys - 1) / big_keys : (Ktot + 1023) / 1024;
   const int cap = big ? (max_ctas / 4 > 148 ? 148 : max_ctas / 4) : max_ctas;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
