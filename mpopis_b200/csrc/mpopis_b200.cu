@@ -1090,16 +1090,14 @@ int mpopis_b200_comm_peer_attach(mpopis_t *h, const void *handles, int64_t n_byt
 int mpopis_b200_comm_peer_loopback(mpopis_t *h) {
   if (!h) return fail(MPOPIS_ERR_BAD_ARG, "null argument");
   if (h->world == 1) return 0;
-  // Virtual ranks share one device: a grid-cooperative launch of rank A does not start while rank B's collective
-  // kernel spins on A's flag (tools/coop_concurrency.cu), so the cooperative kernels are off the menu here — the
-  // elite selection runs as one thread-block cluster, and :cmamppi (cooperative Σ^-1/2 and merge sort) stays on the
-  // host-barrier transport.
+  // :cmamppi keeps the host-barrier transport here: its K-sized all-reduce is beyond the peer slots and would mix a
+  // host-synchronous collective into a sequence of device-side spins. (Grid-cooperative kernels — the selection — do
+  // run beside a spinning kernel of another stream: tools/coop_concurrency.cu.)
   if (h->cfg.policy == MPOPIS_POLICY_CMAMPPI)
     return fail(MPOPIS_ERR_BAD_ARG, "peer-memory collectives between loop-back ranks do not support :cmamppi");
   if (int rc = set_device(h)) return rc;
   drop_graph(h);
   h->comm.peer_err = h->info();
-  h->select_cluster = 1;
   // allocations may synchronise the device: make the ones the injected-noise path needs now, not under a spinning peer
   if (int rc = ensure_pin(h, sizeof(double) * std::max((size_t)h->cs * h->Kloc, (size_t)h->K))) return rc;
   if (comm_peer_alloc(h->comm, (size_t)h->cs * h->cs + 2 * (size_t)h->cs + 64) ||
