@@ -144,3 +144,59 @@ def test_sharded_elite_ranking_matches_a_global_stable_sort(G):
         gap = max(gap, g)
     assert elites == elite_ref
     assert gap == gap_ref
+
+
+class _FakeEngine:
+    """Stands in for a CUDA-backed Engine: records what sharding.connect asks of it (no GPU on this box)."""
+
+    def __init__(self, rank, device=0):
+        self.rank, self.device, self.calls, self.blobs = rank, device, [], None
+
+    def comm_init(self, nccl_id):
+        self.calls.append(("comm_init", len(nccl_id)))
+
+    def comm_peer_export(self):
+        self.calls.append(("export",))
+        return bytes([self.rank]) * 128
+
+    def comm_peer_attach(self, blobs):
+        self.calls.append(("attach", len(blobs)))
+        self.blobs = list(blobs)
+
+
+def _connect_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from mpopis_b200 import _lib, sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _lib.comm_id = lambda: b"i" * 128  # NCCL is not involved on the CPU box
+    res = {}
+    for name, peer, env in (("auto", None, None), ("off_by_env", None, "0"), ("off_by_arg", False, None)):
+        if env is None:
+            os.environ.pop("MPOPIS_COMM_PEER", None)
+        else:
+            os.environ["MPOPIS_COMM_PEER"] = env
+        e = _FakeEngine(rank)
+        res[name] = (sharding.connect(e, dist, rank, world, peer=peer), e.calls, e.blobs)
+    np.save(Path(out_dir) / f"c{rank}.npy", np.array([res], dtype=object), allow_pickle=True)
+    dist.destroy_process_group()
+
+
+def test_connect_negotiates_the_transport_identically_on_every_rank(tmp_path):
+    """sharding.connect (N > 1 host plumbing): NCCL id broadcast, then — one host, peer access — every rank exports its
+    128-byte blob, all-gathers them IN RANK ORDER and attaches; MPOPIS_COMM_PEER=0 / peer=False keep NCCL. With
+    world_size = 1 nothing is touched."""
+    from mpopis_b200 import sharding
+    solo = _FakeEngine(0)
+    assert sharding.connect(solo, None, 0, 1) == "none" and solo.calls == []
+    world = 2
+    mp.spawn(_connect_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        res = np.load(tmp_path / f"c{rank}.npy", allow_pickle=True)[0]
+        kind, calls, blobs = res["auto"]
+        assert kind == "peer" and calls == [("comm_init", 128), ("export",), ("attach", world)]
+        assert blobs == [bytes([r]) * 128 for r in range(world)]   # rank order, identical on every rank
+        for name in ("off_by_env", "off_by_arg"):
+            kind, calls, blobs = res[name]
+            assert kind == "nccl" and calls == [("comm_init", 128)] and blobs is None
