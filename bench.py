@@ -218,7 +218,14 @@ def main():
             return 0
         # the stated configuration itself (same K): ≈4 s per control step on 16 cores, so the number of timed steps is
         # bounded (the CPU rate does not depend on how many steps are averaged); one untimed warm-up step
-        K_ref = min(K, 131072)  # N = 1 (K = 65 536): the full configuration; larger K: a bounded sample of the samples
+        # N = 1 (K = 65 536) with up to ~20 timed steps: the full configuration. Larger K or more steps: each step is a
+        # bounded sample of the K samples, sized so that the whole run stays near two minutes of CPU time (the port
+        # sustains ≈ 5.5·10⁶ rollout-steps/s on 16 cores, independent of K)
+        budget_s = 120.0 / max(args.steps + 1, 1)
+        K_fit = max(4096, int(budget_s * 5.5e6 * (threads / 16.0) / (T * N_ITS)) // 32 * 32)
+        K_ref = min(K, 131072, max(K_fit, 4096))
+        if K_ref > 60000 and K == 65536:
+            K_ref = K
         v, ms = cpu_reference(args.steps, 1, K_ref, threads)
         sample = (f"{args.steps} timed control steps of the stated workload at " +
                   (f"the full K={K}" if K_ref == K else f"K={K_ref} of {K} (the CPU rate does not depend on K)") +
