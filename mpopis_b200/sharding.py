@@ -122,3 +122,87 @@ def sharded_weighted_sum(E_local: np.ndarray, w_global: np.ndarray, k0: int, all
     kl = E_local.shape[1]
     wl = w_global[k0:k0 + kl]
     return allreduce(np.concatenate([E_local @ wl, [wl.sum()]]))
+
+
+# ---- numpy restatement of csrc/select.cu (elite selection without a sort) ------------------------------------------
+COST_KEY_NAN = 0xFFFFFFFFFFFFFFFE
+
+
+def cost_keys(costs: np.ndarray) -> np.ndarray:
+    """Order-preserving uint64 image of a Float64 under Base.isless (engine.cuh: cost_key): −0.0 < +0.0, NaN last."""
+    c = np.ascontiguousarray(costs, dtype=np.float64)
+    b = c.view(np.uint64)
+    k = np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))
+    return np.where(np.isnan(c), np.uint64(COST_KEY_NAN), k)
+
+
+def key_costs(keys: np.ndarray) -> np.ndarray:
+    k = np.asarray(keys, dtype=np.uint64)
+    b = np.where(k >> np.uint64(63), k & np.uint64((1 << 63) - 1), ~k)
+    return np.where(k >= np.uint64(COST_KEY_NAN), np.nan, b.view(np.float64))
+
+
+def ce_select_emulation(costs: np.ndarray, m: int, k0: int = 0, kloc: int | None = None, early_stop: bool = True):
+    """The algorithm of ce_select_kernel on the host, step by step (digits, prefixes, buckets as the kernel forms them):
+    returns (ids of the elites inside the window [k0, k0 + kloc) in index order, stop decision, τ as (key, index)).
+
+    1. exact radix select of the m-th smallest 96-bit composite (cost key << 32 | sample index): 11-bit digits from the
+       top, the candidate set narrowed per pass, ranked directly once <= 256 remain;
+    2. early stop (POL:458-461) without sorting the elites: decided "no" by the gap of the two smallest costs, by a
+       NaN / non-finite elite cost or by the pigeonhole bound (c_m − c₁)·200 >= 2m + 2; otherwise from the gaps between
+       consecutive non-empty buckets of width 0.005 (min / max key per bucket, the reference's own subtraction);
+    3. ownership: the elites whose global id falls into the shard's window."""
+    K = len(costs)
+    kloc = K if kloc is None else kloc
+    keys = cost_keys(costs)
+    comp = [(int(keys[i]) << 32) | i for i in range(K)]
+    need, cand, low = m - 1, list(range(K)), 96
+    tau = None
+    for pas in range(9):
+        shift, mask = (85 - 11 * pas, 0x7FF) if pas < 8 else (0, 0xFF)
+        hist: dict[int, list[int]] = {}
+        for i in cand:
+            hist.setdefault((comp[i] >> shift) & mask, []).append(i)
+        for d in sorted(hist):
+            if need < len(hist[d]):
+                cand = hist[d]
+                break
+            need -= len(hist[d])
+        low = shift
+        if len(cand) <= 256:  # direct ranking
+            tau = sorted(comp[i] for i in cand)[need]
+            break
+    assert tau is not None
+    tk, ti = tau >> 32, tau & 0xFFFFFFFF
+    elite = np.array([comp[i] <= tau for i in range(K)])
+    assert int(elite.sum()) == m
+    # ---- stop decision ----
+    order2 = np.sort(keys)[:2]
+    g1, g2 = int(order2[0]), (int(order2[1]) if K > 1 else None)
+    first_gap_decides = m > 1 and g2 is not None and not (abs(float(key_costs(np.array([g2]))[0]) - float(key_costs(np.array([g1]))[0])) < 10e-3)
+    c1, cm = float(key_costs(np.array([g1], dtype=np.uint64))[0]), float(key_costs(np.array([tk], dtype=np.uint64))[0])
+    stop = False
+    if early_stop and m > 1 and not first_gap_decides and tk < COST_KEY_NAN and np.isfinite(c1) and np.isfinite(cm):
+        span = (cm - c1) * 200.0
+        nb_cap = 2 * m + 4
+        if span < 2 * m + 2 and span + 1.0 <= nb_cap:
+            nb = int(span) + 1
+            bmin, bmax = [None] * nb, [None] * nb
+            for i in np.nonzero(elite)[0]:
+                bk = min(max(int((float(costs[i]) - c1) * 200.0), 0), nb - 1)
+                k = int(keys[i])
+                bmin[bk] = k if bmin[bk] is None else min(bmin[bk], k)
+                bmax[bk] = k if bmax[bk] is None else max(bmax[bk], k)
+            gap_seen, last = False, None
+            for bk in range(nb):
+                if bmin[bk] is None:
+                    continue
+                if last is not None:
+                    a = float(key_costs(np.array([bmin[bk]], dtype=np.uint64))[0])
+                    b = float(key_costs(np.array([last], dtype=np.uint64))[0])
+                    if not (abs(a - b) < 10e-3):
+                        gap_seen = True
+                last = bmax[bk]
+            stop = not gap_seen
+    ids = np.nonzero(elite)[0]
+    return ids[(ids >= k0) & (ids < k0 + kloc)], stop, (tk, ti)

@@ -92,58 +92,60 @@ def test_shard_range():
         shard_range(128, 2, 2)
 
 
-def _rank_with_early_exit(runs, me, m):
-    """numpy restatement of sort.cu: global_rank_kernel for rank `me` — runs[r] = (costs sorted, global ids) of rank r.
-    Returns (m_loc, max gap over this rank's elites) exactly as the kernel computes them, including the early exit
-    (stop walking further runs once the position reaches m)."""
-    ck, ci = runs[me]
-    m_loc, gap = 0, -1.0
-    for j in range(len(ck)):
-        key, gid = ck[j], ci[j]
-        pos = j
-        succ = (ck[j + 1], ci[j + 1]) if j + 1 < len(ck) else (np.inf, 2 ** 31 - 1)
-        for r, (rk, ri) in enumerate(runs):
-            if r == me:
-                continue
-            if pos >= m:
-                break
-            lo = int(np.searchsorted(rk, key, side="left"))
-            while lo < len(rk) and rk[lo] == key and ri[lo] < gid:  # ties: (key, global id) lexicographic
-                lo += 1
-            pos += lo
-            if lo < len(rk) and (rk[lo], ri[lo]) < succ:
-                succ = (rk[lo], ri[lo])
-        if pos < m:
-            m_loc = max(m_loc, j + 1)
-            if pos + 1 < m:
-                gap = max(gap, abs(succ[0] - key))
-    return m_loc, gap
+def _reference_select(costs, m):
+    """POL:455-461 literally: stable sortperm (Base.isless: −0.0 < 0.0, NaN last), elite slice, maximum(abs.(diff))."""
+    from mpopis_b200.sharding import cost_keys
+    order = np.lexsort((np.arange(len(costs)), cost_keys(costs)))
+    el = costs[order[:m]]
+    with np.errstate(invalid="ignore"):
+        d = np.abs(np.diff(el))
+    gap = np.nan if (d.size and np.isnan(d).any()) else (d.max() if d.size else np.nan)
+    return np.sort(order[:m]), bool(gap < 10e-3) if m > 1 else False
 
 
-@pytest.mark.parametrize("G", [2, 3, 8])
-def test_sharded_elite_ranking_matches_a_global_stable_sort(G):
-    """The sharded :cemppi selection (local sort, all-gathered runs, per-element rank search with early exit) picks
-    exactly the m globally smallest samples (ties by global index) and the same early-stop statistic
-    maximum(abs.(diff(elite costs))) as a global sortperm (POL:455-461) — checked on the algorithm, for 2, 3 and 8 ranks."""
+def _cost_families(rng, K):
+    base = rng.normal(0.0, 3.0, K)
+    yield "normal", base
+    yield "ties", np.round(base, 1)
+    yield "constant", np.full(K, 2.5)
+    yield "converged", 7.0 + rng.uniform(0, 4e-3, K)                      # every elite gap < 10e-3: stop
+    yield "one_gap_at_threshold", np.concatenate([np.arange(K // 2) * 1e-3, [K * 1e-3 + 9.0e-3], np.full(K - K // 2 - 1, 50.0)])
+    yield "one_gap_above", np.concatenate([np.arange(K // 2) * 9.99e-3, np.full(K - K // 2, 50.0)])
+    yield "gap_exactly_10e-3", np.concatenate([np.arange(K // 2) * 10e-3, np.full(K - K // 2, 50.0)])
+    c = base.copy(); c[::7] = np.nan
+    yield "nan_sprinkled", c
+    yield "all_nan", np.full(K, np.nan)
+    c = np.abs(base) * 1e-3; c[::5] = -0.0; c[1::5] = 0.0
+    yield "signed_zeros", c
+    c = base.copy(); c[:3] = -np.inf; c[3:6] = np.inf
+    yield "infinities", c
+    yield "huge_spread", base * 1e200
+    yield "denormals", base * 5e-324 * 1e3
+
+
+@pytest.mark.parametrize("G", [1, 2, 3, 8])
+def test_selection_algorithm_matches_a_global_stable_sort(G):
+    """The sort-free :cemppi selection of csrc/select.cu (radix select on (cost key, sample id), early-stop test from the two
+    smallest costs / the pigeonhole bound / value buckets, ownership windows), restated step by step in numpy
+    (sharding.ce_select_emulation), picks exactly the m globally smallest samples — ties by global index — and takes the
+    reference's stop decision maximum(abs.(diff(elite costs))) < 10e-3 (POL:455-461), for 1, 2, 3 and 8 shards."""
+    from mpopis_b200.sharding import ce_select_emulation
     rng = np.random.default_rng(G)
-    kloc = 257
-    costs = np.round(rng.normal(0.0, 3.0, G * kloc), 1)  # rounding creates plenty of ties
-    m = int(round(0.2 * G * kloc))
-    order = np.lexsort((np.arange(costs.size), costs))
-    elite_ref = set(order[:m].tolist())
-    gap_ref = float(np.max(np.abs(np.diff(costs[order[:m]]))))
-    runs = []
-    for r in range(G):
-        ids = np.arange(r * kloc, (r + 1) * kloc)
-        o = np.lexsort((ids, costs[ids]))
-        runs.append((costs[ids][o], ids[o]))
-    elites, gap = set(), -1.0
-    for r in range(G):
-        m_loc, g = _rank_with_early_exit(runs, r, m)
-        elites |= set(runs[r][1][:m_loc].tolist())
-        gap = max(gap, g)
-    assert elites == elite_ref
-    assert gap == gap_ref
+    kloc = 264
+    K = G * kloc
+    for m in (2, int(round(0.2 * K)), K // 2):
+        for name, costs in _cost_families(rng, K):
+            costs = np.asarray(costs, dtype=np.float64)
+            elite_ref, stop_ref = _reference_select(costs, m)
+            got = []
+            for r in range(G):
+                ids, stop, _ = ce_select_emulation(costs, m, k0=r * kloc, kloc=kloc)
+                assert stop == stop_ref, f"{name}, m={m}, shard {r}: stop {stop} vs reference {stop_ref}"
+                assert np.all((ids >= r * kloc) & (ids < (r + 1) * kloc))
+                got.append(ids)
+            assert np.array_equal(np.concatenate(got), elite_ref), f"{name}, m={m}: elite set differs"
+    ids, stop, _ = ce_select_emulation(np.array([3.0, 1.0, 2.0]), 1)   # m = 1: nothing to diff, no stop (POL:458 on one cost)
+    assert ids.tolist() == [1] and stop is False
 
 
 class _FakeEngine:
