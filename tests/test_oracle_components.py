@@ -258,9 +258,9 @@ def test_oas_and_rblw_against_their_defining_iterations(orc):
         ρ_{j+1} = [(1 − 2/p) tr(Σ_j S) + tr²(Σ_j)] / [(n + 1 − 2/p) tr(Σ_j S) + (1 − n/p) tr²(Σ_j)],  Σ_j = (1 − ρ_j) S + ρ_j F
     (its closed form is what the oracle and the engine implement) and the RBLW intensity by their eq. (17). Running the
     iteration here checks the closed form without sharing its code. sklearn's OAS is NOT usable as a cross-check: it
-    documents a deliberately different formula (0.3085 vs 0.3060 on this matrix). :lw / :ss (Ledoit–Wolf and
-    Schäfer–Strimmer towards diag(S)) have no independent implementation in this image and stay unpinned until
-    tests/golden/julia_v1.json exists (julia/make_fixtures.jl)."""
+    documents a deliberately different formula (0.3085 vs 0.3060 on this matrix). :lw / :ss (shrinkage towards diag(S)) are checked against the
+    element-by-element definition of Schäfer & Strimmer in the next test; the reference's own numbers for all four still
+    need tests/golden/julia_v1.json (julia/make_fixtures.jl)."""
     rng = np.random.default_rng(0)
     for p, n in ((20, 60), (100, 30), (100, 819)):
         A = rng.normal(size=(p, p))
@@ -283,3 +283,33 @@ def test_oas_and_rblw_against_their_defining_iterations(orc):
         _, S_rblw = e.cov_estimate(X, "rblw")
         assert abs(e.last_shrinkage() - rho_rblw) < 1e-12
         np.testing.assert_allclose(S_rblw, (1 - rho_rblw) * S + rho_rblw * F, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("method", ["lw", "ss"])
+def test_diagonal_target_shrinkage_against_schaefer_strimmer_directly(orc, method):
+    """Independent check of the O(n·p) shrinkage statistic behind :lw / :ss (the reference's default
+    estimator for the car is :ss). Schäfer & Strimmer (2005), target D "diagonal, unequal variances", define
+        λ* = Σ_{i≠j} Var^(s_ij) / Σ_{i≠j} s_ij²,   Var^(s_ij) = n/(n−1)³ Σ_k (w_kij − w̄_ij)²,   s_ij = n/(n−1) w̄_ij,
+        w_kij = (x_ki − x̄_i)(x_kj − x̄_j)
+    (:ss — their own variant — applies it to the correlations, i.e. to data standardised by the sample standard
+    deviations; both shrink S_mle towards diag(S_mle)). This test evaluates the definition element by element, O(n·p²),
+    with no algebra shared with the oracle's closed form Σ_k[(Σ_i z²)² − Σ_i z⁴]. It pins the formula as published; the
+    reference's own CovarianceEstimation.jl numbers still need julia/make_fixtures.jl."""
+    rng = np.random.default_rng(11)
+    for p, n in ((6, 40), (30, 30), (100, 30), (40, 819)):
+        A = rng.normal(size=(p, p))
+        X = A @ rng.normal(size=(p, n)) + rng.normal(size=(p, 1))
+        Xc = X - X.mean(axis=1, keepdims=True)
+        S = Xc @ Xc.T / n                                   # the MLE the reference shrinks (corrected = false)
+        Z = Xc / np.sqrt(np.diag(S))[:, None] if method == "ss" else Xc
+        W = Z[:, None, :] * Z[None, :, :]                   # w_kij, shape p x p x n
+        wbar = W.mean(axis=2)
+        var_s = n / (n - 1) ** 3 * ((W - wbar[:, :, None]) ** 2).sum(axis=2)
+        s = n / (n - 1) * wbar
+        off = ~np.eye(p, dtype=bool)
+        lam = float(np.clip(var_s[off].sum() / (s[off] ** 2).sum(), 0.0, 1.0))
+        e = orc.engine(policy="cemppi", env=_abi.ENV_MOUNTAIN_CAR, num_samples=max(n, 2), horizon=p, opt_its=2, lam=1.0)
+        _, S_hat = e.cov_estimate(X, method)
+        assert abs(e.last_shrinkage() - lam) < 1e-10 * max(1.0, lam), (p, n, e.last_shrinkage(), lam)
+        target = (1 - lam) * S + lam * np.diag(np.diag(S))
+        np.testing.assert_allclose(S_hat, target, rtol=1e-9, atol=1e-12)
