@@ -177,7 +177,7 @@ void comm_destroy(Comm &c) {
 //               buffer suffices because an all-reduce always separates two gathers (the step ends in one) and the
 //               consumers of the gathered costs are stream-ordered before this rank's contribution to it.
 // Epochs live in device memory and are advanced by the kernels, so a captured CUDA graph replays them unchanged.
-// A spin that sees no peer for ~10 s sets *peer_err (sticky, surfaces as MPOPIS_ERR_NCCL) instead of hanging the GPU.
+// A spin that sees no peer for ~30 s sets *peer_err (sticky, surfaces as MPOPIS_ERR_NCCL) instead of hanging the GPU.
 namespace {
 
 constexpr size_t PEER_CTRL_BYTES = 1024;
@@ -197,10 +197,10 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // spin until *flag reaches `want` (epochs only grow); false on timeout. Once a collective of this handle has timed out
-// (*err set, sticky until the host reads it) later ones give up after ~1 ms instead of 10 s each.
+// (*err set, sticky until the host reads it) later ones give up after ~1 ms instead of 30 s each.
 __device__ bool wait_flag(const unsigned *flag, unsigned want, const int *err) {
   const long long t0 = clock64();
-  const long long limit = (err && *(const volatile int *)err == COMM_PEER_TIMEOUT) ? 2000000LL : 20000000000LL;
+  const long long limit = (err && *(const volatile int *)err == COMM_PEER_TIMEOUT) ? 2000000LL : 60000000000LL;
   while ((int)(ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(40);
     if (clock64() - t0 > limit) return false;
@@ -223,7 +223,7 @@ __device__ __forceinline__ void ll_store(LLLine *dst, double v, unsigned flag) {
                "r"((unsigned)__double2hiint(v)), "r"(flag)
                : "memory");
 }
-// false on timeout (≈10 s; ≈1 ms once a collective of this handle has already timed out)
+// false on timeout (≈30 s; ≈1 ms once a collective of this handle has already timed out)
 __device__ __forceinline__ bool ll_load(const LLLine *src, unsigned flag, double *v, const int *err) {
   unsigned lo, f0, hi, f1;
   long long t0 = 0;
@@ -233,7 +233,7 @@ __device__ __forceinline__ bool ll_load(const LLLine *src, unsigned flag, double
     if ((spins & 1023u) == 1023u) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      const long long limit = (err && *(const volatile int *)err == COMM_PEER_TIMEOUT) ? 2000000LL : 20000000000LL;
+      const long long limit = (err && *(const volatile int *)err == COMM_PEER_TIMEOUT) ? 2000000LL : 60000000000LL;
       if (now - t0 > limit) return false;
     }
   }

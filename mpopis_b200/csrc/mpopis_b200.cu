@@ -668,7 +668,7 @@ int plan_step(mpopis_t *h) {
 
 int check_info(mpopis_t *h, int info) {
   if (info == COMM_PEER_TIMEOUT)
-    return fail(MPOPIS_ERR_NCCL, "a peer-memory collective waited 10 s for a rank that never arrived (rank %d of %d)",
+    return fail(MPOPIS_ERR_NCCL, "a peer-memory collective waited 30 s for a rank that never arrived (rank %d of %d)",
                 h->rank, h->world);
   if (info != 0)
     return fail(MPOPIS_ERR_NOT_PD, "PosDefException: matrix is not positive definite; Cholesky factorization failed (%s)",
