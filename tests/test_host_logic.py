@@ -159,3 +159,68 @@ def test_policy_logger_with_oracle_backend(orc):
     mc = make_env("mc")
     pol = M.MPPI_Policy(mc, num_samples=8, horizon=5, λ=0.1, U0=[0.0], cov_mat=[1.5], backend=orc.bound())
     assert pol(mc).shape == (1,)  # Vector for as == 1 (UTL:63-66)
+
+
+def test_trial_replicas_schedule_breadth_first_in_waves():
+    """run_trial_replicas (car_example.jl:170 as concurrent replicas) — the host-side schedule, with a
+    recording stand-in for the engine: trials are dealt round-robin over the devices, every trial gets its own seed,
+    step s of every resident trial is enqueued before step s + 1 of any, `concurrency` bounds the resident trials per
+    wave, nothing is read back before a wave's last step, and every handle is closed."""
+    log = []
+
+    class FakeEnv:
+        state, t = np.arange(8.0), 3
+
+    class FakeEngine:
+        cs = 4
+
+        def __init__(self, dev, idx):
+            self.dev, self.idx, self.steps = dev, idx, 0
+
+        def seed(self, s):
+            log.append(("seed", self.idx, s))
+
+        def resident_reset(self, state, t, U):
+            assert t == 3 and U.shape == (4,) and not U.any()
+            log.append(("reset", self.idx))
+
+        def resident_plan(self, advance):
+            assert advance is True
+            self.steps += 1
+            log.append(("plan", self.idx, self.steps))
+
+        def resident_read(self):
+            log.append(("read", self.idx))
+            return np.full(8, self.idx), np.zeros(4), np.zeros(2), None
+
+        def resident_reward_sum(self):
+            return float(self.idx)
+
+        def resident_total_its(self):
+            return 10 * self.steps
+
+        def close(self):
+            log.append(("close", self.idx))
+
+    made = []
+
+    def make_engine(dev):
+        made.append(dev)
+        return FakeEnv(), FakeEngine(dev, len(made) - 1)
+
+    out, wall = M.run_trial_replicas(make_engine, num_trials=5, num_steps=3, devices=(0, 1), seeds=[11, 12, 13, 14, 15],
+                                     concurrency=2)
+    assert made == [0, 1, 0, 1, 0] and wall >= 0.0
+    assert [o["device"] for o in out] == made and [o["seed"] for o in out] == [11, 12, 13, 14, 15]
+    assert [o["reward_sum"] for o in out] == [0.0, 1.0, 2.0, 3.0, 4.0] and all(o["its"] == 30 for o in out)
+    waves = [[0, 1], [2, 3], [4]]
+    pos = 0
+    for wave in waves:
+        expect = [x for i in wave for x in (("seed", i, 11 + i), ("reset", i))]
+        expect += [("plan", i, s) for s in (1, 2, 3) for i in wave]            # breadth first
+        expect += [x for i in wave for x in (("read", i), ("close", i))]
+        assert log[pos:pos + len(expect)] == expect
+        pos += len(expect)
+    assert pos == len(log)
+    out, _ = M.run_trial_replicas(make_engine, num_trials=2, num_steps=1)      # defaults: seeds 1.., one device, one wave
+    assert [o["seed"] for o in out] == [1, 2] and [o["device"] for o in out] == [0, 0]
