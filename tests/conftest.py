@@ -4,9 +4,9 @@ from pathlib import Path
 
 # loop-back groups run up to 8 virtual ranks x 2 streams on one device and their peer-memory collectives spin on
 # flags: with the default 8 hardware queues a spinning kernel could sit in front of the very kernel it waits for
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
 # ... and they share ONE CUDA context: a lazily loaded kernel would wait for the spinning peer (csrc/comm.cu)
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+os.environ["CUDA_MODULE_LOADING"] = "EAGER"  # set, not setdefault: a LAZY inherited from the caller would fail the peer tests
 
 import numpy as np
 import pytest
