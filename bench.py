@@ -182,6 +182,26 @@ def make_sweep_engine(bound, label, K, device=0):
     return env, eng
 
 
+def measure_trial_replicas(make, devices, trials=16, steps=30):
+    """SURVEY §8f-2 in numbers: `trials` independent trials of BASELINE config C2 (K = 150, the reference's own size), each
+    `steps` control steps with the env resident on the device, run one after the other (the reference's
+    `for k ∈ 1:num_trials`, car_example.jl:170) and as concurrent replicas (mpopis_b200/trials.py) over the visible
+    devices. Wall-clock trials/s including the creation of every trial's handle. Never raises: a failure is reported in
+    the object so that the bench line survives."""
+    try:
+        from mpopis_b200.trials import run_trial_replicas
+        run_trial_replicas(make, min(2, trials), 3, devices=devices)  # warm-up: module load, first graph capture
+        _, t_seq = run_trial_replicas(make, trials, steps, devices=devices[:1], concurrency=1)
+        res, t_con = run_trial_replicas(make, trials, steps, devices=devices)
+        return {"config": "C2 :cemppi K=150, env resident on the device", "trials": trials, "steps_per_trial": steps,
+                "devices": len(devices), "sequential_trials_per_s": trials / t_seq, "replica_trials_per_s": trials / t_con,
+                "speedup": t_seq / t_con, "its_per_trial": float(np.mean([r["its"] for r in res])),
+                "note": "wall clock, handle creation included; replicas: one handle / stream / CUDA graph / Philox key "
+                        "per trial, step s of every trial enqueued before step s + 1 of any"}
+    except Exception as e:  # noqa: BLE001 - the measurement is an extra, the line must survive
+        return {"error": repr(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -445,6 +465,10 @@ def main():
                 v_c, ms_c = cpu_reference(2, 1, Ks, threads, make=lambda b, Kx, tag=tag: make_sweep_engine(b, tag, Kx))
                 row["cpu_port_ms_per_step"], row["cpu_port_rollout_steps_per_s"], row["cpu_cores"] = ms_c, v_c, threads
             k_sweep.append(row)
+    trial_replicas = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        devs = tuple(range(torch.cuda.device_count())) if local_rank == 0 else (local_rank,)
+        trial_replicas = measure_trial_replicas(lambda dev: make_sweep_engine(bound, "C2", 150, dev), devs)
 
     line = dict(base, value=value, ms_per_step=dev_ms / args.steps,
                 config={"workload": workload, "l2": "flushed between steps (256 MiB memset outside the timed intervals)",
@@ -454,7 +478,8 @@ def main():
                      "ms_per_step": e2e_s / args.steps * 1e3},
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_fp64=roofline_fp64,
                 roofline_g8=roofline_g8, roofline_step_hbm=roofline_step_hbm, parity=parity,
-                fp64_peak_dfma_per_s=fp64_peak, its_per_step=its_total / args.steps, k_sweep=k_sweep)
+                fp64_peak_dfma_per_s=fp64_peak, its_per_step=its_total / args.steps, k_sweep=k_sweep,
+                trial_replicas=trial_replicas)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, ms = cpu_reference(2, 1, K, threads)  # the stated configuration itself: ≈4 s per control step on 16 cores
