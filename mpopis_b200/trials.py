@@ -17,21 +17,27 @@ import time
 import numpy as np
 
 
-def run_trial_replicas(make_engine, num_trials: int, num_steps: int, *, devices=(0,), seeds=None, concurrency=None):
+def run_trial_replicas(make_engine, num_trials: int, num_steps: int, *, devices=(0,), seeds=None, concurrency=None,
+                       timing: dict | None = None):
     """make_engine(device) -> (env, engine) with the engine configured (set_*_env, set_sigma, ...).
-    Returns a list of per-trial dicts {state, U, control, reward_sum, its, seed, device} and the wall time in s."""
+    Returns a list of per-trial dicts {state, U, control, reward_sum, its, seed, device} and the wall time in s.
+    `timing` (optional dict) receives {"create_s", "run_s"}: handle creation vs enqueueing the steps and reading back."""
     seeds = list(seeds) if seeds is not None else list(range(1, num_trials + 1))
     concurrency = num_trials if concurrency is None else max(1, int(concurrency))
     out = [None] * num_trials
     t0 = time.perf_counter()
+    t_create = t_run = 0.0
     for first in range(0, num_trials, concurrency):  # waves of `concurrency` resident trials
         batch = []
+        tc = time.perf_counter()
         for i in range(first, min(num_trials, first + concurrency)):
             dev = devices[i % len(devices)]
             env, eng = make_engine(dev)
             eng.seed(seeds[i])
             eng.resident_reset(env.state, getattr(env, "t", 0), np.zeros(eng.cs))
             batch.append((i, dev, eng))
+        tr = time.perf_counter()
+        t_create += tr - tc
         for _ in range(num_steps):
             for _, _, eng in batch:  # breadth first: one control step of every trial is in flight together
                 eng.resident_plan(True)
@@ -39,5 +45,9 @@ def run_trial_replicas(make_engine, num_trials: int, num_steps: int, *, devices=
             state, U, ctrl, _ = eng.resident_read()
             out[i] = {"state": state, "U": U, "control": ctrl, "reward_sum": eng.resident_reward_sum(),
                       "its": eng.resident_total_its(), "seed": seeds[i], "device": dev}
+        t_run += time.perf_counter() - tr
+        for _, _, eng in batch:
             eng.close()
+    if timing is not None:
+        timing["create_s"], timing["run_s"] = t_create, t_run
     return out, time.perf_counter() - t0

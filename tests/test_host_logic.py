@@ -218,7 +218,7 @@ def test_trial_replicas_schedule_breadth_first_in_waves():
     for wave in waves:
         expect = [x for i in wave for x in (("seed", i, 11 + i), ("reset", i))]
         expect += [("plan", i, s) for s in (1, 2, 3) for i in wave]            # breadth first
-        expect += [x for i in wave for x in (("read", i), ("close", i))]
+        expect += [("read", i) for i in wave] + [("close", i) for i in wave]   # read back the whole wave, then release it
         assert log[pos:pos + len(expect)] == expect
         pos += len(expect)
     assert pos == len(log)
