@@ -260,7 +260,7 @@ int mpopis_b200_last_shrinkage(mpopis_t *h, double *lambda_out);
  * thread-per-rollout kernel: 32, 64, 96 or 128), "rollout_profile" (1 = record per-warp cycles, see warp_cycles),
  * "rollout_stage" (noise tensor of kernel 3: 0 = register prefetch, 1 = TMA bulk copies into a shared-memory ring),
  * "graph" (1 = replay the control step as a CUDA graph, the default), "fuse_cov" (1 = shrinkage + ridge folded into
- * the Cholesky launch), "select_cluster" (1 = elite selection as one 8-CTA cluster instead of the cooperative grid),
+ * the Cholesky launch), "ce_small_fused" (1 = the whole :cemppi adaptation of K <= 512, cs <= 112 as one single-CTA launch),
  * "moments_small" (1 = single-CTA moment chain for <= 512 columns, the default; 0 = the multi-kernel chain).
  * get_option additionally reads "rollout_variant_used" (what 6 resolved to at the latest launch), "graph_active",
  * "ce_select" and "comm_peer". */

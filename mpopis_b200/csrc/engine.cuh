@@ -207,7 +207,7 @@ void launch_select_init(void *ws, unsigned long long *bmin, unsigned long long *
 // tau_out (nullable, 4 doubles): {τ cost, τ index, smallest cost, buckets used}. Returns a cudaError_t.
 int launch_ce_select(const double *costs, int Ktot, int m, long long k0, int Kloc, int early_stop, void *ws,
                      unsigned long long *bmin, unsigned long long *bmax, long long nb_cap, int *eidx, int *m_loc,
-                     double *tau_out, int *stop_flag, const int *stop, int max_ctas, int use_cluster, cudaStream_t s);
+                     double *tau_out, int *stop_flag, const int *stop, int max_ctas, cudaStream_t s);
 int elite_gather_nchunks(int m_max);
 // X[r][j] = E[r][eidx[j]], partial[(2c + {0,1}) * cs + r] = Σ x, Σ x² over chunk c
 void launch_elite_gather_sums(const double *E, long long ldk, int cs, const int *eidx, const int *m_loc, int m_max,

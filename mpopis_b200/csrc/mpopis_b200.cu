@@ -78,7 +78,6 @@ struct mpopis_handle {
   double gamma = 0.0;
   uint64_t seed = 0;
   long long step = 0;
-  int select_cluster = 0;  // "select_cluster" option: the single-cluster flavour of the elite selection (select.cu)
   int rollout_spin = -1;  // split kernel hand-over: -1 auto, 0 mbarrier, 1 spin on shared-memory counters
   int rollout_variant = 6, rollout_variant_used = -1, rollout_block = 64, rollout_stage = 0, coop_max = 1, sort_max = 1, sel_max = 1;
   bool moments_small = true;  // single-CTA moment chain for small n ("moments_small" option, A/B)
@@ -291,7 +290,7 @@ int ce_adapt(mpopis_t *h) {
   cudaStream_t st = h->st;
   const cudaError_t e = (cudaError_t)launch_ce_select(h->d_costs, K, m, h->k0, Kloc, h->cfg.early_stop, h->d_sel_ws,
                                                       h->d_bmin, h->d_bmax, h->nb_cap, h->d_eidx, h->d_mloc, h->d_tau,
-                                                      stop, stop, h->sel_max, h->select_cluster, st);
+                                                      stop, stop, h->sel_max, st);
   if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
   mark(h, "select");
   const int mmax = m < Kloc ? m : Kloc, nch = elite_gather_nchunks(mmax);
@@ -1236,8 +1235,6 @@ int mpopis_b200_set_option(mpopis_t *h, const char *key, double value) {
     h->rollout_block = b;
   } else if (!strcmp(key, "moments_small")) {
     h->moments_small = value != 0.0;
-  } else if (!strcmp(key, "select_cluster")) {
-    h->select_cluster = value != 0.0;
   } else if (!strcmp(key, "rollout_spin")) {
     h->rollout_spin = value < 0 ? -1 : (value != 0.0);
   } else if (!strcmp(key, "ce_small_fused")) {
@@ -1445,7 +1442,7 @@ int mpopis_b200_elite_select(mpopis_t *h, const double *costs, int64_t K, int64_
     CU(cudaMemsetAsync(misc, 0, sizeof(int) * 2, h->st));
     const cudaError_t e = (cudaError_t)launch_ce_select(dc, (int)K, (int)m, k0, (int)kloc, early_stop, ws.p, bmin, bmax, cap,
                                                         eidx, misc.p, dtau, misc.p + 1, nullptr, h->sel_max,
-                                                        h->select_cluster, h->st);
+                                                        h->st);
     if (e != cudaSuccess) return fail(MPOPIS_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
   }
   h->launches += 3;

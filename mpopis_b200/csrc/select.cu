@@ -386,264 +386,10 @@ __global__ void __launch_bounds__(ST) ce_select_kernel(const double *__restrict_
   }
 }
 
-// ---- the same selection inside ONE thread-block cluster ------------------------------------------------------------------
-// The cooperative kernel above pays a grid-wide barrier (≈ 3-4 µs with 64 CTAs) per radix pass / phase — 6 of them,
-// ≈ 50 µs per AIS iteration at K = 65 536 where the work itself is a few µs. Up to K = 2^21 the whole selection fits one
-// cluster of 8 CTAs x 1024 threads: the barriers become cluster.sync() (hardware, sub-µs), the histograms, candidate list
-// and partial results live in (distributed) shared memory and are read across the cluster instead of travelling
-// through L2 atomics. Same algorithm, same results bit for bit (tests/test_gpu_select.py runs both).
-constexpr int CL = 8, CT = 1024;
-
-struct ClusterSmem {
-  unsigned hist[2][NBIN];
-  unsigned long long min_key;
-  unsigned long long cand_k[NCAND];
-  unsigned cand_i[NCAND];
-  unsigned ncand;
-  int cnt;
-  unsigned long long seg_first, seg_last;
-  int seg_flags;
-  unsigned long long tk;
-  unsigned ti;
-  int warp_tot[CT / 32];
-  int sel[3];
-};
-
-__global__ void __launch_bounds__(CT) ce_select_cluster_kernel(const double *__restrict__ costs, int Ktot, int m,
-                                                                long long k0, int Kloc, int early_stop,
-                                                                unsigned long long *__restrict__ bmin,
-                                                                unsigned long long *__restrict__ bmax, long long nb_cap,
-                                                                int *__restrict__ eidx, int *m_loc, double *tau_out,
-                                                                int *stop_flag, const int *stop) {
-  if (stop && *stop) return;  // uniform: nobody writes the flag before the last cluster barrier
-  cg::cluster_group cluster = cg::this_cluster();
-  __shared__ ClusterSmem sm;
-  __shared__ Seg segs[CT / 32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int b = (int)cluster.block_rank();
-  const int S = (Ktot + CL - 1) / CL;
-  const int ibeg = min(Ktot, b * S), iend = min(Ktot, ibeg + S);
-  if (tid == 0) sm.ncand = 0, sm.min_key = KMAX;
-  __syncthreads();
-
-  unsigned long long pk = 0, tk = 0;
-  unsigned pi = 0, ti = 0;
-  long long need = m - 1;
-  int low = 96;
-  bool have_tau = false;
-  for (int pass = 0; pass < 9; ++pass) {
-    const int shift = pass < 8 ? 85 - 11 * pass : 0;
-    const unsigned mask = pass < 8 ? 0x7FFu : 0xFFu;
-    unsigned *hl = sm.hist[pass & 1];
-    for (int e = tid; e < NBIN; e += CT) hl[e] = 0;
-    __syncthreads();
-    unsigned long long mn = KMAX;
-    for (int i0 = ibeg; i0 < iend; i0 += CT) {
-      const int i = i0 + tid;
-      const unsigned long long k = i < iend ? cost_key(costs[i]) : KMAX;
-      if (pass == 0) mn = k < mn ? k : mn;
-      hist_add(hl, digit96(k, (unsigned)i, shift, mask), i < iend && match96(k, (unsigned)i, pk, pi, low));
-    }
-    if (pass == 0) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long v = __shfl_xor_sync(0xffffffffu, mn, o);
-        mn = v < mn ? v : mn;
-      }
-      if (lane == 0 && mn != KMAX) atomicMin(&sm.min_key, mn);
-    }
-    cluster.sync();
-    // every CTA sums the 8 histograms (2 bins per thread) and finds the bin of rank `need`
-    unsigned loc[2] = {0, 0};
-#pragma unroll
-    for (int q = 0; q < CL; ++q) {
-      const unsigned *hr = cluster.map_shared_rank(hl, q);
-      loc[0] += hr[2 * tid], loc[1] += hr[2 * tid + 1];
-    }
-    const unsigned tot = loc[0] + loc[1];
-    unsigned incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) sm.warp_tot[wid] = (int)incl;
-    __syncthreads();
-    unsigned wbase = 0;
-    for (int w = 0; w < wid; ++w) wbase += (unsigned)sm.warp_tot[w];
-    const unsigned excl = wbase + incl - tot;
-    if ((long long)excl <= need && need < (long long)(excl + tot)) {  // exactly one thread
-      const int q = need < (long long)(excl + loc[0]) ? 0 : 1;
-      sm.sel[0] = 2 * tid + q, sm.sel[1] = (int)(excl + (q ? loc[0] : 0)), sm.sel[2] = (int)loc[q];
-    }
-    __syncthreads();
-    const unsigned bin = (unsigned)sm.sel[0];
-    need -= sm.sel[1];
-    const unsigned ncand = (unsigned)sm.sel[2];
-    if (shift >= 32) pk |= (unsigned long long)bin << (shift - 32);
-    else {
-      const unsigned long long v = (unsigned long long)bin << shift;
-      pk |= v >> 32, pi |= (unsigned)v;
-    }
-    low = shift;
-    __syncthreads();
-    if (ncand <= NCAND || pass == 8) {
-      if (ncand == 1 && pass == 8) tk = pk, ti = pi, have_tau = true;
-      break;
-    }
-  }
-  if (!have_tau) {  // collect the <= 256 remaining candidates in CTA 0's shared memory and rank them directly
-    ClusterSmem *s0 = cluster.map_shared_rank(&sm, 0);
-    for (int i = ibeg + tid; i < iend; i += CT) {
-      const unsigned long long k = cost_key(costs[i]);
-      if (match96(k, (unsigned)i, pk, pi, low)) {
-        const unsigned slot = atomicAdd(&s0->ncand, 1u);
-        if (slot < NCAND) s0->cand_k[slot] = k, s0->cand_i[slot] = (unsigned)i;
-      }
-    }
-    cluster.sync();
-    const unsigned n = min(s0->ncand, (unsigned)NCAND);
-    unsigned long long *ck = reinterpret_cast<unsigned long long *>(sm.hist[0]);  // local copy: 256 x 8 B + 256 x 4 B
-    unsigned *ci = sm.hist[1];
-    if (b != 0 && tid < (int)n) ck[tid] = s0->cand_k[tid], ci[tid] = s0->cand_i[tid];
-    if (b == 0 && tid < (int)n) ck[tid] = sm.cand_k[tid], ci[tid] = sm.cand_i[tid];
-    __syncthreads();
-    if (tid < (int)n) {
-      const unsigned long long k = ck[tid];
-      const unsigned i = ci[tid];
-      int below = 0;
-      for (unsigned j = 0; j < n; ++j) below += (ck[j] < k || (ck[j] == k && ci[j] < i)) ? 1 : 0;
-      if (below == (int)need) sm.tk = k, sm.ti = i;
-    }
-    __syncthreads();
-    tk = sm.tk, ti = sm.ti;
-  }
-  // smallest key over the cluster
-  unsigned long long mnk = KMAX;
-#pragma unroll
-  for (int q = 0; q < CL; ++q) {
-    const unsigned long long v = cluster.map_shared_rank(&sm, q)->min_key;
-    mnk = v < mnk ? v : mnk;
-  }
-  const double c1 = key_cost(mnk), cm = key_cost(tk);
-  long long nb = 0;
-  if (early_stop && m > 1 && tk < COST_KEY_NAN && isfinite(c1) && isfinite(cm)) {
-    const double span = (cm - c1) * 200.0;
-    if (span < (double)(2LL * m + 2) && span + 1.0 <= (double)nb_cap) nb = (long long)span + 1;
-  }
-  // ---- mark: bucket min/max of all elites, count of the elites this shard owns ----
-  int cnt = 0;
-  for (int i0 = ibeg; i0 < iend; i0 += CT) {
-    const int i = i0 + tid;
-    bool elite = false;
-    unsigned long long k = 0;
-    if (i < iend) {
-      k = cost_key(costs[i]);
-      elite = le96(k, (unsigned)i, tk, ti);
-    }
-    if (elite && i >= k0 && i < k0 + Kloc) ++cnt;
-    if (nb > 0) {
-      long long bk = -1;
-      if (elite) {
-        bk = (long long)((key_cost(k) - c1) * 200.0);
-        bk = bk < 0 ? 0 : (bk >= nb ? nb - 1 : bk);
-      }
-      const long long b0 = __shfl_sync(0xffffffffu, bk, 0);
-      if (__all_sync(0xffffffffu, bk == b0)) {
-        if (b0 >= 0) {
-          unsigned long long lo = k, hi = k;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), c = __shfl_xor_sync(0xffffffffu, hi, o);
-            lo = a < lo ? a : lo, hi = c > hi ? c : hi;
-          }
-          if (lane == 0) atomicMin(&bmin[b0], lo), atomicMax(&bmax[b0], hi);
-        }
-      } else if (bk >= 0) {
-        atomicMin(&bmin[bk], k), atomicMax(&bmax[bk], k);
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) sm.warp_tot[wid] = cnt;
-  __syncthreads();
-  if (tid == 0) {
-    int t = 0;
-    for (int w = 0; w < CT / 32; ++w) t += sm.warp_tot[w];
-    sm.cnt = t;
-  }
-  __threadfence();  // bucket atomics of this CTA are visible device-wide before any CTA scans them
-  cluster.sync();
-  // ---- compaction: ids of the local elites in index order ----
-  {
-    int off = 0, all = 0;
-#pragma unroll
-    for (int q = 0; q < CL; ++q) {
-      const int c = cluster.map_shared_rank(&sm, q)->cnt;
-      off += q < b ? c : 0, all += c;
-    }
-    if (b == 0 && tid == 0) *m_loc = all;
-    for (int i0 = ibeg; i0 < iend; i0 += CT) {
-      const int i = i0 + tid;
-      bool own = false;
-      if (i < iend && i >= k0 && i < k0 + Kloc) own = le96(cost_key(costs[i]), (unsigned)i, tk, ti);
-      const unsigned bal = __ballot_sync(0xffffffffu, own);
-      __syncthreads();
-      if (lane == 0) sm.warp_tot[wid] = __popc(bal);
-      __syncthreads();
-      int base = off, tot = 0;
-      for (int w = 0; w < CT / 32; ++w) {
-        if (w < wid) base += sm.warp_tot[w];
-        tot += sm.warp_tot[w];
-      }
-      if (own) eidx[base + __popc(bal & ((1u << lane) - 1u))] = (int)(i - k0);
-      off += tot;
-    }
-  }
-  if (tau_out && b == 0 && tid == 0) tau_out[0] = key_cost(tk), tau_out[1] = (double)ti, tau_out[2] = c1, tau_out[3] = (double)nb;
-  // ---- bucket scan (buckets are left clean) ----
-  if (nb > 0) {
-    const long long Q = (nb + CL - 1) / CL;
-    const long long q0 = min(nb, (long long)b * Q), q1 = min(nb, q0 + Q);
-    const long long per = (q1 - q0 + CT - 1) / CT;
-    const long long t0 = min(q1, q0 + tid * per), t1 = min(q1, t0 + per);
-    Seg sg{0, 0, 0};
-    for (long long q = t0; q < t1; ++q) {
-      const unsigned long long lo = __ldcg(&bmin[q]), hi = __ldcg(&bmax[q]);
-      if (lo != KMAX) {
-        bmin[q] = KMAX, bmax[q] = 0;
-        sg = seg_join(sg, Seg{lo, hi, 1});
-      }
-    }
-    // ordered combine: lanes of a warp by shuffles (lane order), then the warps
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      Seg other;
-      other.first = __shfl_down_sync(0xffffffffu, sg.first, o);
-      other.last = __shfl_down_sync(0xffffffffu, sg.last, o);
-      other.flags = __shfl_down_sync(0xffffffffu, sg.flags, o);
-      if (lane + o < 32) sg = seg_join(sg, other);  // sg covers lanes [lane, lane + 2o)
-    }
-    if (lane == 0) segs[wid] = sg;
-    __syncthreads();
-    if (tid == 0) {
-      Seg acc = segs[0];
-      for (int w = 1; w < CT / 32; ++w) acc = seg_join(acc, segs[w]);
-      sm.seg_first = acc.first, sm.seg_last = acc.last, sm.seg_flags = acc.flags;
-    }
-    cluster.sync();
-    if (b == 0 && tid == 0) {
-      Seg acc{0, 0, 0};
-      for (int q = 0; q < CL; ++q) {
-        const ClusterSmem *r = cluster.map_shared_rank(&sm, q);
-        acc = seg_join(acc, Seg{r->seg_first, r->seg_last, r->seg_flags});
-      }
-      if ((acc.flags & 1) && !(acc.flags & 2)) *stop_flag = 1;  // maximum(abs.(diff(elite costs))) < 10e-3
-    }
-  }
-  cluster.sync();  // no CTA exits while its shared memory may still be read by a peer
-}
+// (Round 2 also built the same selection inside ONE thread-block cluster of 8 CTAs x 1024 threads — cluster.sync()
+// barriers, histograms and candidates in distributed shared memory. ncu at K = 65 536: 60 µs against 36 µs for the
+// cooperative kernel above: 8 SMs pull the keys and walk the buckets where 64 do; the grid barriers were never the cost,
+// the dependent L2 round trips of a latency-bound kernel are. It was removed: profiles/README.md, round 2.)
 
 __global__ void select_ws_init_kernel(Ws *ws, unsigned long long *bmin, unsigned long long *bmax, long long nb_cap) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -739,19 +485,7 @@ void launch_select_init(void *ws, unsigned long long *bmin, unsigned long long *
 
 int launch_ce_select(const double *costs, int Ktot, int m, long long k0, int Kloc, int early_stop, void *ws,
                      unsigned long long *bmin, unsigned long long *bmax, long long nb_cap, int *eidx, int *m_loc,
-                     double *tau_out, int *stop_flag, const int *stop, int max_ctas, int use_cluster, cudaStream_t s) {
-  // Opt-in ("select_cluster" option): measured SLOWER than the cooperative kernel at K = 65 536 (ncu: 60 vs 36 µs —
-  // 8 SMs pull the keys and walk the buckets where 64 do; the barriers were never the cost), kept as a tested variant.
-  if (Ktot <= (1 << 21) && use_cluster) {  // one cluster of 8 CTAs: barriers in hardware, histograms in distributed shared memory
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(CL), cfg.blockDim = dim3(CT), cfg.dynamicSmemBytes = 0, cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, ce_select_cluster_kernel, costs, Ktot, m, k0, Kloc, early_stop, bmin, bmax, nb_cap,
-                                   eidx, m_loc, tau_out, stop_flag, stop);
-  }
+                     double *tau_out, int *stop_flag, const int *stop, int max_ctas, cudaStream_t s) {
   // Small K: 256-thread CTAs of 1024 keys. Large K (sharded policies select on the GATHERED costs, K = 2^18 .. 2^20):
   // 1024-thread CTAs, at most one per SM — the dense radix pass flushes up to 2048 bins per CTA with global atomics and
   // every phase ends in a grid barrier, so fewer, fatter CTAs (8-GPU trace: 170-214 µs per iteration with 512-592 small

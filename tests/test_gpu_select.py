@@ -76,10 +76,8 @@ def cases():
     yield "big-converged", 7.0 + np.arange(1 << 20) * 1e-9, 209715
 
 
-@pytest.mark.parametrize("cluster", [0, 1], ids=["cooperative", "cluster"])
 @pytest.mark.parametrize("name,costs,m", list(cases()), ids=[c[0] for c in cases()])
-def test_elite_set_and_stop_decision(eng, name, costs, m, cluster):
-    eng.set_option("select_cluster", cluster)  # both flavours of the kernel: grid-cooperative and single-cluster
+def test_elite_set_and_stop_decision(eng, name, costs, m):
     ids_ref, stop_ref = reference(costs, m)
     ids, stop, tau = eng.elite_select(costs, m)
     assert np.array_equal(ids, ids_ref), f"{name}: elite sets differ ({ids.size} vs {ids_ref.size})"
